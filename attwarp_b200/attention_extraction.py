@@ -1,0 +1,192 @@
+"""Mirror of the hook-logger attention reducers of
+``Attention Guided Warping/attention_extraction/llava.py``.
+
+* ``MaskHookLogger``       (llava.py:37-153)  -- single sample per generate call
+* ``BatchMaskHookLogger``  (llava.py:338-448) -- per-sample image-token ranges
+
+Same constructor / method names.  ``_process_attention`` hands the live
+``[B, Hh, q, kv]`` attention tensor (fp16/bf16/fp32, on the GPU, no copy) to the stage-1 CUDA
+kernel, which slices the last query row at the per-sample token offset, renormalises per head,
+averages over heads and adds the step into a running device-side sum; ``finalize`` /
+``finalize_batch`` divide by the number of steps.  The reference's Python loop over the batch
+(llava.py:388-395) and its list/stack of per-step tensors are gone.  The input is upcast to
+fp32 in the kernel (the reference divides in the tensor's dtype).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class _RunningAttention:
+    """Device-side running sum of per-step head means."""
+
+    def __init__(self):
+        self.sum = None
+        self.steps = 0
+
+    def add_step(self, attn_weights: torch.Tensor, starts, ends):
+        B, Hh, q, kv = attn_weights.shape
+        ends = [min(int(e), kv) for e in ends]
+        lens = sorted({e - int(s) for s, e in zip(starts, ends)})
+        if len(lens) != 1:
+            raise ValueError(f"per-sample image-token spans differ in length: {lens}")
+        T = lens[0]
+        rows = attn_weights[:, :, -1, :].unsqueeze(1)          # [B, 1, Hh, kv] view, no copy
+        if rows.stride(3) != 1:
+            rows = rows.contiguous()
+        st = torch.as_tensor([int(s) for s in starts], dtype=torch.int32, device=rows.device)
+        if self.sum is None:
+            self.sum = torch.zeros(B, T, dtype=torch.float32, device=rows.device)
+        ops.aggregate_attention(rows, tok_start=st, num_tokens=T, out=self.sum, accumulate=True)
+        self.steps += 1
+
+    def mean(self):
+        return self.sum / float(self.steps)
+
+
+class MaskHookLogger(object):
+    """Captures last-token -> image-token attention of one decoder layer during generation."""
+
+    def __init__(self, model, device, layer_index=20):
+        self.device = device
+        self.model = model
+        self.layer_index = layer_index
+        self.hook_handle = None
+        self.image_token_start = None
+        self.image_token_end = None
+        self.num_image_tokens = 576  # 24x24 patches for LLaVA-1.5
+        self._acc = _RunningAttention()
+
+    @property
+    def attns(self):
+        """Number-of-steps view kept for callers that test ``len(logger.attns)``."""
+        return [None] * self._acc.steps
+
+    @torch.no_grad()
+    def _attention_hook(self, module, input, output):
+        if isinstance(output, tuple) and len(output) >= 2:
+            attn_weights = output[1]
+            if attn_weights is not None and isinstance(attn_weights, torch.Tensor):
+                if len(attn_weights.shape) == 4:
+                    self._process_attention(attn_weights)
+
+    @torch.no_grad()
+    def _process_attention(self, attn_weights):
+        kv = attn_weights.shape[-1]
+        if self.image_token_start is None or self.image_token_end is None:
+            st, ed = 1, min(1 + self.num_image_tokens, kv)            # llava.py:99-102
+        else:
+            st, ed = self.image_token_start, min(self.image_token_end, kv)
+        B = attn_weights.shape[0]
+        self._acc.add_step(attn_weights.detach(), [st] * B, [ed] * B)
+
+    def set_image_token_range(self, start, end):
+        self.image_token_start = start
+        self.image_token_end = end
+
+    @torch.no_grad()
+    def finalize(self):
+        """[num_image_tokens] mean over steps (and, like llava.py:131-132, over the batch)."""
+        if self._acc.steps == 0:
+            return torch.ones(self.num_image_tokens, device=self.device) / self.num_image_tokens
+        return self._acc.mean().mean(dim=0).to(self.device)
+
+    def reinit(self):
+        self._acc = _RunningAttention()
+        self.image_token_start = None
+        self.image_token_end = None
+
+    def register_hook(self):
+        if self.hook_handle is not None:
+            self.hook_handle.remove()
+        attn_layer = self.model.model.layers[self.layer_index].self_attn
+        self.hook_handle = attn_layer.register_forward_hook(self._attention_hook)
+
+    def remove_hook(self):
+        if self.hook_handle is not None:
+            self.hook_handle.remove()
+            self.hook_handle = None
+
+
+class BatchMaskHookLogger(object):
+    """Batched variant with per-sample image-token ranges (left-padding offsets)."""
+
+    def __init__(self, model, device, layer_index=20):
+        self.device = device
+        self.model = model
+        self.layer_index = layer_index
+        self.hook_handle = None
+        self.num_image_tokens = 576
+        self.image_token_starts = None
+        self.image_token_ends = None
+        self.batch_size = 0
+        self._acc = _RunningAttention()
+        self._original_forward = None
+
+    @property
+    def step_attentions(self):
+        return [None] * self._acc.steps
+
+    def set_batch_image_token_ranges(self, starts, ends):
+        assert len(starts) == len(ends)
+        self.image_token_starts = starts
+        self.image_token_ends = ends
+        self.batch_size = len(starts)
+
+    @torch.no_grad()
+    def _attention_hook(self, module, input, output):
+        if not isinstance(output, tuple) or len(output) < 2:
+            return
+        attn_weights = output[1]
+        if attn_weights is None or not isinstance(attn_weights, torch.Tensor):
+            return
+        if len(attn_weights.shape) != 4:
+            return
+        self._process_attention(attn_weights)
+
+    @torch.no_grad()
+    def _process_attention(self, attn_weights):
+        bsz = attn_weights.shape[0]
+        self._acc.add_step(attn_weights.detach(), self.image_token_starts[:bsz],
+                           self.image_token_ends[:bsz])
+
+    @torch.no_grad()
+    def finalize_batch(self):
+        """List of [24, 24] maps, one per sample (llava.py:401-411)."""
+        if self._acc.steps == 0:
+            return [torch.ones(self.num_image_tokens, device=self.device) / self.num_image_tokens
+                    for _ in range(self.batch_size)]
+        avg = self._acc.mean()
+        return [avg[i].view(24, 24) for i in range(self.batch_size)]
+
+    def reinit(self):
+        self._acc = _RunningAttention()
+        self.image_token_starts = None
+        self.image_token_ends = None
+        self.batch_size = 0
+
+    def register_hook_and_patch(self):
+        """Hook the layer and force ``output_attentions=True`` on it only (llava.py:422-438)."""
+        if self.hook_handle is not None:
+            self.hook_handle.remove()
+        attn_layer = self.model.model.layers[self.layer_index].self_attn
+        self.hook_handle = attn_layer.register_forward_hook(self._attention_hook)
+        self._original_forward = attn_layer.forward
+        original = self._original_forward
+
+        def forward_with_attentions(*args, **kwargs):
+            kwargs["output_attentions"] = True
+            return original(*args, **kwargs)
+
+        attn_layer.forward = forward_with_attentions
+
+    def remove_hook_and_unpatch(self):
+        if self.hook_handle is not None:
+            self.hook_handle.remove()
+            self.hook_handle = None
+        if self._original_forward is not None:
+            self.model.model.layers[self.layer_index].self_attn.forward = self._original_forward
+            self._original_forward = None

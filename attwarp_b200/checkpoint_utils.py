@@ -1,0 +1,143 @@
+"""Mirror of the warp helpers of ``model/marginalnet_full_dataset/checkpoint_utils.py``.
+
+* ``cdf_from_density(p)``                               (checkpoint_utils.py:30-41)
+* ``gt_marginals(A)``                                   (checkpoint_utils.py:43-51)
+* ``upsample_pdf_right_inverse(y, target_len, eps)``    (checkpoint_utils.py:64-131)
+* ``warp_from_cdf_torch(img, Fx_img, Fy_img, out_size)`` (checkpoint_utils.py:133-204)
+* ``adaptive_avg_pool2d_24`` -- the ``F.adaptive_avg_pool2d(A_full, (24, 24))`` prologue of
+  ``trainer.py:197``
+
+Same signatures and error behaviour.  The reference moves everything to the CPU and loops over
+samples in Python around ``cv2.remap``; here tensors stay on (or are moved to) the GPU, the
+batch is one launch per stage, and the result is returned on ``img.device`` with ``img.dtype``
+exactly like checkpoint_utils.py:203.  No CPU fallback: a CUDA device is required.
+The plotting helpers of the reference (checkpoint_utils.py:206-399) are out of scope.
+"""
+
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import check, current_stream, load, ptr
+
+
+def _cuda_device(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("attwarp_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def cdf_from_density(p: torch.Tensor) -> torch.Tensor:
+    """p: (B,N) -> (B,N) non-decreasing CDF in [0,1], ends at 1."""
+    lib = load()
+    dev = _cuda_device(p)
+    rows = p.detach().to(dev).float().contiguous()
+    assert rows.dim() == 2, "cdf_from_density expects (B, N)"
+    out = torch.empty_like(rows)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_cdf_from_density(ptr(rows), rows.shape[0], rows.shape[1], ptr(out),
+                                           current_stream(dev)))
+    return out.to(p.device)
+
+
+def gt_marginals(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """A:(B,1,H,W) -> (px:(B,W), py:(B,H)) normalised."""
+    lib = load()
+    B, _, H, W = A.shape
+    dev = _cuda_device(A)
+    a = A.detach().to(dev).float()[:, 0].contiguous()
+    px = torch.empty(B, W, dtype=torch.float32, device=dev)
+    py = torch.empty(B, H, dtype=torch.float32, device=dev)
+    wsb = lib.attwarp_maps_workspace_bytes(B, H, W)
+    ws = ops._workspace(wsb, dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_gt_marginals(ptr(a), B, H, W, ptr(ws), ws.numel(), ptr(px), ptr(py),
+                                       current_stream(dev)))
+    return px.to(A.device), py.to(A.device)
+
+
+_M_cache = {}
+
+
+def right_inverse_matrix(L_in: int, L_out: int, eps: float, device) -> torch.Tensor:
+    """M = A^T (A A^T + eps I)^-1 as float32 [L_in, L_out] on ``device``; A is the
+    AdaptiveAvgPool1d matrix with windows [floor(i*L_in/L_out), ceil((i+1)*L_in/L_out))
+    (checkpoint_utils.py:104-121).  A constant of (L_in, L_out, eps): built once in float64 on
+    the host and cached."""
+    key = (int(L_in), int(L_out), float(eps), str(device))
+    M = _M_cache.get(key)
+    if M is None:
+        i = np.arange(L_out, dtype=np.int64)
+        starts = (i * L_in) // L_out
+        ends = ((i + 1) * L_in + L_out - 1) // L_out
+        A = np.zeros((L_out, L_in), dtype=np.float64)
+        for k in range(L_out):
+            A[k, starts[k]:ends[k]] = 1.0 / max(int(ends[k] - starts[k]), 1)
+        G = A @ A.T
+        if eps > 0:
+            G = G + eps * np.eye(L_out)
+        Mh = np.linalg.solve(G, A).T            # (L_in, L_out); G is symmetric
+        M = torch.from_numpy(np.ascontiguousarray(Mh.astype(np.float32))).to(device)
+        _M_cache[key] = M
+    return M
+
+
+def upsample_pdf_right_inverse(y: torch.Tensor, target_len: int, eps: float = 1e-8) -> torch.Tensor:
+    """Minimum-norm right inverse of AdaptiveAvgPool1d; y (L_out,), (B,L_out) or (B,C,L_out)."""
+    if y.dim() not in (1, 2, 3):
+        raise ValueError(f"upsample_pdf_right_inverse expects 1D/2D/3D y; got shape {tuple(y.shape)}")
+    lib = load()
+    dev = _cuda_device(y)
+    L_out, L_in = y.shape[-1], int(target_len)
+    rows = y.detach().to(dev).float().reshape(-1, L_out).contiguous()
+    M = right_inverse_matrix(L_in, L_out, eps, dev)
+    x = torch.empty(rows.shape[0], L_in, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_upsample_right_inverse(ptr(rows), ptr(M), rows.shape[0], L_out, L_in,
+                                                 ptr(x), current_stream(dev)))
+    return x.reshape(tuple(y.shape[:-1]) + (L_in,)).to(device=y.device, dtype=y.dtype)
+
+
+def adaptive_avg_pool2d_24(A: torch.Tensor, out_hw=(24, 24)) -> torch.Tensor:
+    """F.adaptive_avg_pool2d(A, (24,24)) for A (B,1,H,W) float32 (trainer.py:197)."""
+    lib = load()
+    B, Cc, H, W = A.shape
+    dev = _cuda_device(A)
+    a = A.detach().to(dev).float().reshape(B * Cc, H, W).contiguous()
+    gh, gw = out_hw
+    out = torch.empty(B * Cc, gh, gw, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_adaptive_avg_pool2d(ptr(a), B * Cc, H, W, gh, gw, ptr(out),
+                                              current_stream(dev)))
+    return out.reshape(B, Cc, gh, gw).to(A.device)
+
+
+def warp_from_cdf_torch(img: torch.Tensor, Fx_img: torch.Tensor, Fy_img: torch.Tensor,
+                        out_size: tuple | None = None) -> torch.Tensor:
+    """img (B,C,H,W) uint8 or float32; Fx_img (B,W), Fy_img (B,H) CDFs in [0,1];
+    out_size (H_out, W_out) or None.  Returns (B,C,H_out,W_out) on img.device with img.dtype.
+
+    Deliberate superset of the reference: C == 1 works (the reference crashes at
+    checkpoint_utils.py:202 because cv2.remap drops the singleton channel)."""
+    assert img.ndim == 4, f"img must be (B,C,H,W); got {img.shape}"
+    B, Cc, H, W = img.shape
+    H_out, W_out = (H, W) if out_size is None else out_size
+    if Fx_img.shape[-1] != W:
+        raise ValueError(f"Fx_img[0] length {Fx_img.shape[-1]} != image width W={W}")
+    if Fy_img.shape[-1] != H:
+        raise ValueError(f"Fy_img[0] length {Fy_img.shape[-1]} != image height H={H}")
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"warp_from_cdf_torch: img dtype {img.dtype} not supported (uint8/float32)")
+    dev = _cuda_device(img)
+    src = img.detach().to(dev).contiguous()
+    Fx = Fx_img.detach().to(dev).float().reshape(B, W)
+    Fy = Fy_img.detach().to(dev).float().reshape(B, H)
+    map_x, map_y = ops.maps_from_cdf(Fx, Fy, (int(H_out), int(W_out)))
+    out = ops.remap_bilinear(src, map_x, map_y, layout="chw")
+    return out.to(device=img.device, dtype=img.dtype)

@@ -1,0 +1,321 @@
+// api.cu -- the C ABI declared in include/attwarp.h: argument validation, error state, fused
+// batch drivers and the host-buffer convenience entry point.  No kernels live here.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace aw {
+
+// declared in the other translation units
+size_t maps_workspace_bytes_impl(int B, int H, int W);
+int launch_gt_marginals(const float* A, int B, int H, int W, void* ws, size_t ws_bytes, float* px,
+                        float* py, cudaStream_t st);
+int launch_maps_from_cdf(const float* Fx, const float* Fy, int B, int H, int W, int Wo, int Ho,
+                         float* map_x, float* map_y, cudaStream_t st);
+int launch_safe_softmax(const float* logits, int B, int N, float eps, float* out, cudaStream_t st);
+int launch_mix_with_uniform(const float* p, int B, int N, float alpha, float* out, cudaStream_t st);
+int launch_cdf_from_density(const float* p, int B, int N, float* F, cudaStream_t st);
+int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,
+                                  float* x, cudaStream_t st);
+int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
+                               cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ATTWARP_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    return ATTWARP_OK;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+static int check_transform(const attwarp_transform_params* tp) {
+    AW_REQUIRE(tp != nullptr, "transform params must not be NULL");
+    AW_REQUIRE(tp->transform >= ATTWARP_T_IDENTITY && tp->transform <= ATTWARP_T_LOG,
+               "unknown transform id %d", tp->transform);
+    return ATTWARP_OK;
+}
+
+// ---- per-thread device scratch for the host-buffer entry point --------------------------------
+struct HostArena {
+    cudaStream_t stream = nullptr;
+    void* dev = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    int ensure(size_t bytes) {
+        int cur = 0;
+        AW_CUDA(cudaGetDevice(&cur));
+        if (stream == nullptr || cur != device) {
+            if (dev != nullptr) cudaFree(dev);
+            dev = nullptr;
+            cap = 0;
+            AW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            device = cur;
+        }
+        if (bytes > cap) {
+            if (dev != nullptr) AW_CUDA(cudaFree(dev));
+            dev = nullptr;
+            cap = 0;
+            const size_t want = align_up(bytes + bytes / 4, 1 << 20);
+            AW_CUDA(cudaMalloc(&dev, want));
+            cap = want;
+        }
+        return ATTWARP_OK;
+    }
+};
+static thread_local HostArena g_arena;
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case ATTWARP_U8: return 1;
+        case ATTWARP_F32: return 4;
+        case ATTWARP_F64: return 8;
+        case ATTWARP_BF16:
+        case ATTWARP_F16: return 2;
+        default: return 0;
+    }
+}
+
+}  // namespace aw
+
+using namespace aw;
+
+extern "C" {
+
+int attwarp_abi_version(void) { return ATTWARP_ABI_VERSION; }
+
+const char* attwarp_last_error(void) { return g_err; }
+
+int attwarp_device_info(int* sm, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    AW_CUDA(cudaGetDevice(&dev));
+    int n = 0, maj = 0, min = 0;
+    AW_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    AW_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+    AW_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm) *sm = n;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min;
+    return ATTWARP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t attwarp_aggregate_workspace_bytes(int B, int L, int Hh, int T) {
+    if (B <= 0 || L <= 0 || Hh <= 0 || T <= 0) return 0;
+    return sizeof(float) * (size_t)B * aggregate_nsplit(B, L, Hh) * T;
+}
+
+int attwarp_aggregate_attention(const void* attn, int dtype, int B, int L, int Hh, int T,
+                                int64_t stride_b, int64_t stride_l, int64_t stride_h,
+                                const int32_t* tok_start, float eps, void* workspace,
+                                size_t workspace_bytes, float* out, int accumulate,
+                                float out_scale, void* stream) {
+    AW_REQUIRE(attn && out, "aggregate: NULL pointer");
+    AW_REQUIRE(B > 0 && L > 0 && Hh > 0 && T > 0, "aggregate: sizes must be positive (B=%d L=%d Hh=%d T=%d)", B, L, Hh, T);
+    AW_REQUIRE(B <= 65535, "aggregate: B=%d exceeds 65535", B);
+    if (workspace == nullptr || workspace_bytes < attwarp_aggregate_workspace_bytes(B, L, Hh, T))
+        return fail(ATTWARP_ERR_WORKSPACE, "aggregate: workspace too small (%zu < %zu)", workspace_bytes,
+                    attwarp_aggregate_workspace_bytes(B, L, Hh, T));
+    const int nsplit = aggregate_nsplit(B, L, Hh);
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_aggregate_partial(attn, dtype, B, L, Hh, T, stride_b, stride_l, stride_h, tok_start,
+                                      eps, static_cast<float*>(workspace), nsplit, st);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_aggregate_finalize(static_cast<const float*>(workspace), B, nsplit, T,
+                                     1.0f / ((float)L * (float)Hh), out, accumulate, out_scale, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t attwarp_maps_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return maps_workspace_bytes_impl(B, H, W);
+}
+
+int attwarp_maps_from_attention(const void* att, int att_dtype, int B, int H, int W, int Wo, int Ho,
+                                const attwarp_transform_params* tp, void* workspace,
+                                size_t workspace_bytes, float* map_x, float* map_y, void* stream) {
+    AW_REQUIRE(att && map_x && map_y, "maps_from_attention: NULL pointer");
+    AW_REQUIRE(B > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "maps_from_attention: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "maps_from_attention: B=%d exceeds 65535", B);
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_maps_from_attention(att, att_dtype, B, H, W, Wo, Ho, *tp, workspace, workspace_bytes,
+                                      map_x, map_y, nullptr, as_stream(stream));
+}
+
+int attwarp_maps_from_tokens(const float* tok, int B, int gh, int gw, int H, int W, int Wo, int Ho,
+                             const attwarp_transform_params* tp, float* map_x, float* map_y,
+                             void* stream) {
+    AW_REQUIRE(tok && map_x && map_y, "maps_from_tokens: NULL pointer");
+    AW_REQUIRE(B > 0 && gh > 0 && gw > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "maps_from_tokens: sizes must be positive");
+    AW_REQUIRE(gh <= H && gw <= W, "maps_from_tokens: token grid %dx%d larger than the image %dx%d", gh, gw, H, W);
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_maps_from_tokens(tok, 1, 1.0f, nullptr, B, gh, gw, H, W, Wo, Ho, *tp, map_x, map_y,
+                                   nullptr, as_stream(stream));
+}
+
+int attwarp_maps_from_cdf(const float* Fx, const float* Fy, int B, int H, int W, int Wo, int Ho,
+                          float* map_x, float* map_y, void* stream) {
+    AW_REQUIRE(Fx && Fy && map_x && map_y, "maps_from_cdf: NULL pointer");
+    AW_REQUIRE(B > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "maps_from_cdf: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "maps_from_cdf: B=%d exceeds 65535", B);
+    return launch_maps_from_cdf(Fx, Fy, B, H, W, Wo, Ho, map_x, map_y, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int attwarp_remap_bilinear(const void* src, void* dst, int dtype, int layout, int B, int C, int H,
+                           int W, int Ho, int Wo, const float* map_x, const float* map_y,
+                           void* stream) {
+    AW_REQUIRE(src && dst && map_x && map_y, "remap: NULL pointer");
+    AW_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "remap: sizes must be positive");
+    AW_REQUIRE(layout == ATTWARP_LAYOUT_HWC || layout == ATTWARP_LAYOUT_CHW, "remap: bad layout %d", layout);
+    AW_REQUIRE(src != dst, "remap: in-place operation is not supported");
+    return launch_remap(src, dst, dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, int L, int Hh,
+                                       int64_t stride_b, int64_t stride_l, int64_t stride_h,
+                                       const int32_t* tok_start, int gh, int gw, const void* src,
+                                       void* dst, int img_dtype, int layout, int C, int H, int W,
+                                       int Ho, int Wo, const attwarp_transform_params* tp,
+                                       void* workspace, size_t workspace_bytes, float* tok_out,
+                                       float* map_x, float* map_y, void* stream) {
+    AW_REQUIRE(attn && src && dst && tok_out && map_x && map_y, "warp_from_attention_tokens: NULL pointer");
+    AW_REQUIRE(B > 0 && L > 0 && Hh > 0 && gh > 0 && gw > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0,
+               "warp_from_attention_tokens: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "warp_from_attention_tokens: B=%d exceeds 65535", B);
+    AW_REQUIRE(gh <= H && gw <= W, "token grid %dx%d larger than the image %dx%d", gh, gw, H, W);
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    const int T = gh * gw;
+    if (workspace == nullptr || workspace_bytes < attwarp_aggregate_workspace_bytes(B, L, Hh, T))
+        return fail(ATTWARP_ERR_WORKSPACE, "warp_from_attention_tokens: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int nsplit = aggregate_nsplit(B, L, Hh);
+    float* partial = static_cast<float*>(workspace);
+    rc = launch_aggregate_partial(attn, attn_dtype, B, L, Hh, T, stride_b, stride_l, stride_h, tok_start,
+                                  1e-12f, partial, nsplit, st);
+    if (rc != ATTWARP_OK) return rc;
+    // stage-1 finalize is fused into the maps kernel (it sums the split partials in order)
+    rc = launch_maps_from_tokens(partial, nsplit, 1.0f / ((float)L * (float)Hh), tok_out, B, gh, gw, H, W,
+                                 Wo, Ho, *tp, map_x, map_y, nullptr, st);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_remap(src, dst, img_dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
+}
+
+int attwarp_warp_image_host(const void* image_host, int img_dtype, int C, int H, int W,
+                            const void* att_host, int att_dtype, int Wo, int Ho,
+                            const attwarp_transform_params* tp, void* out_host, int* used_fallback) {
+    AW_REQUIRE(image_host && att_host && out_host, "warp_image_host: NULL pointer");
+    AW_REQUIRE(C > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "warp_image_host: sizes must be positive");
+    AW_REQUIRE(img_dtype == ATTWARP_U8 || img_dtype == ATTWARP_F32, "warp_image_host: image dtype must be u8/f32");
+    AW_REQUIRE(att_dtype == ATTWARP_U8 || att_dtype == ATTWARP_F32 || att_dtype == ATTWARP_F64,
+               "warp_image_host: attention dtype must be u8/f32/f64");
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    const size_t es = dtype_size(img_dtype);
+    const size_t img_b = align_up((size_t)H * W * C * es, 256);
+    const size_t out_b = align_up((size_t)Ho * Wo * C * es, 256);
+    const size_t att_b = align_up((size_t)H * W * dtype_size(att_dtype), 256);
+    const size_t ws_b = align_up(maps_workspace_bytes_impl(1, H, W), 256);
+    const size_t mx_b = align_up(sizeof(float) * Wo, 256), my_b = align_up(sizeof(float) * Ho, 256);
+    rc = g_arena.ensure(img_b + out_b + att_b + ws_b + mx_b + my_b + 256);
+    if (rc != ATTWARP_OK) return rc;
+    char* p = static_cast<char*>(g_arena.dev);
+    void* d_img = p; p += img_b;
+    void* d_out = p; p += out_b;
+    void* d_att = p; p += att_b;
+    void* d_ws = p; p += ws_b;
+    float* d_mx = reinterpret_cast<float*>(p); p += mx_b;
+    float* d_my = reinterpret_cast<float*>(p); p += my_b;
+    int* d_flag = reinterpret_cast<int*>(p);
+    cudaStream_t st = g_arena.stream;
+    AW_CUDA(cudaMemcpyAsync(d_att, att_host, (size_t)H * W * dtype_size(att_dtype), cudaMemcpyHostToDevice, st));
+    AW_CUDA(cudaMemcpyAsync(d_img, image_host, (size_t)H * W * C * es, cudaMemcpyHostToDevice, st));
+    rc = launch_maps_from_attention(d_att, att_dtype, 1, H, W, Wo, Ho, *tp, d_ws, ws_b, d_mx, d_my, d_flag, st);
+    if (rc != ATTWARP_OK) return rc;
+    rc = launch_remap(d_img, d_out, img_dtype, ATTWARP_LAYOUT_HWC, 1, C, H, W, Ho, Wo, d_mx, d_my, st);
+    if (rc != ATTWARP_OK) return rc;
+    AW_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)Ho * Wo * C * es, cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    AW_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AW_CUDA(cudaStreamSynchronize(st));
+    if (used_fallback) *used_fallback = flag;
+    return ATTWARP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int attwarp_safe_softmax(const float* logits, int B, int N, float eps, float* out, void* stream) {
+    AW_REQUIRE(logits && out, "safe_softmax: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "safe_softmax: sizes must be positive");
+    return launch_safe_softmax(logits, B, N, eps, out, as_stream(stream));
+}
+
+int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* out, void* stream) {
+    AW_REQUIRE(p && out, "mix_with_uniform: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "mix_with_uniform: sizes must be positive");
+    return launch_mix_with_uniform(p, B, N, alpha, out, as_stream(stream));
+}
+
+int attwarp_cdf_from_density(const float* p, int B, int N, float* F, void* stream) {
+    AW_REQUIRE(p && F, "cdf_from_density: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "cdf_from_density: sizes must be positive");
+    return launch_cdf_from_density(p, B, N, F, as_stream(stream));
+}
+
+int attwarp_gt_marginals(const float* A, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                         float* px, float* py, void* stream) {
+    AW_REQUIRE(A && px && py, "gt_marginals: NULL pointer");
+    AW_REQUIRE(B > 0 && H > 0 && W > 0, "gt_marginals: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "gt_marginals: B=%d exceeds 65535", B);
+    return launch_gt_marginals(A, B, H, W, workspace, workspace_bytes, px, py, as_stream(stream));
+}
+
+int attwarp_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in, float* x,
+                                   void* stream) {
+    AW_REQUIRE(y && M && x, "upsample_right_inverse: NULL pointer");
+    AW_REQUIRE(B > 0 && L_out > 0 && L_in > 0, "upsample_right_inverse: sizes must be positive");
+    AW_REQUIRE(B <= 65535 && L_out <= 4096, "upsample_right_inverse: B<=65535 and L_out<=4096 required");
+    return launch_upsample_right_inverse(y, M, B, L_out, L_in, x, as_stream(stream));
+}
+
+int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
+                                void* stream) {
+    AW_REQUIRE(A && out, "adaptive_avg_pool2d: NULL pointer");
+    AW_REQUIRE(B > 0 && H > 0 && W > 0 && gh > 0 && gw > 0, "adaptive_avg_pool2d: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "adaptive_avg_pool2d: B=%d exceeds 65535", B);
+    return launch_adaptive_avg_pool2d(A, B, H, W, gh, gw, out, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+// common.cuh -- error plumbing and block-level primitives shared by the kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/attwarp.h"
+#include "warp_math.h"
+
+namespace aw {
+
+// ---- error state (thread-local; surfaced through attwarp_last_error) -------------------------
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> ATTWARP_ERR_CUDA
+
+#define AW_REQUIRE(cond, ...)                                             \
+    do {                                                                  \
+        if (!(cond)) return ::aw::fail(ATTWARP_ERR_INVALID_ARG, __VA_ARGS__); \
+    } while (0)
+
+#define AW_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return ::aw::fail(ATTWARP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int sm_count();
+
+// ---- internal launchers (defined in the .cu files, used by the fused drivers in api.cu) -------
+int launch_aggregate_partial(const void* attn, int dtype, int B, int L, int Hh, int T,
+                             int64_t sb, int64_t sl, int64_t sh, const int32_t* tok_start,
+                             float eps, float* partial, int nsplit, cudaStream_t st);
+int aggregate_nsplit(int B, int L, int Hh);
+int launch_aggregate_finalize(const float* partial, int B, int nsplit, int T, float scale,
+                              float* out, int accumulate, float out_scale, cudaStream_t st);
+int launch_maps_from_tokens(const float* tok, int nsplit, float scale, float* tok_out, int B,
+                            int gh, int gw, int H, int W, int Wo, int Ho,
+                            const attwarp_transform_params& tp, float* map_x, float* map_y,
+                            int* fallback_flags, cudaStream_t st);
+int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int W, int Wo,
+                               int Ho, const attwarp_transform_params& tp, void* ws,
+                               size_t ws_bytes, float* map_x, float* map_y, int* fallback_flags,
+                               cudaStream_t st);
+int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C, int H, int W,
+                 int Ho, int Wo, const float* map_x, const float* map_y, cudaStream_t st);
+
+#if defined(__CUDACC__)
+// ---- warp / block reductions -----------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum, result broadcast to every thread.  `red` is >= 32 elements of shared memory.
+// Deterministic: fixed shuffle tree per warp, then warp partials added in warp order.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    T tot = (T)0;
+    for (int i = 0; i < nw; ++i) tot += red[i];
+    return tot;
+}
+template <typename T>
+__device__ __forceinline__ T block_max(T v, T* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    T m = red[0];
+    for (int i = 1; i < nw; ++i) m = red[i] > m ? red[i] : m;
+    return m;
+}
+
+// In-place inclusive scan of a[0..n) (shared memory, double) by the whole block.
+// Each thread scans a contiguous chunk sequentially, chunk totals are scanned through `red`
+// (>= blockDim.x doubles) by thread order, then offsets are added.  Deterministic.
+__device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* red) {
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int per = (n + nt - 1) / nt;
+    const int beg = min(t * per, n), end = min(beg + per, n);
+    double run = 0.0;
+    for (int i = beg; i < end; ++i) {
+        run += a[i];
+        a[i] = run;
+    }
+    __syncthreads();
+    red[t] = run;
+    __syncthreads();
+    // exclusive prefix of chunk totals: warp 0 walks the (<= 1024) totals, 32 at a time
+    if (t < 32) {
+        double carry = 0.0;
+        for (int base = 0; base < nt; base += 32) {
+            const int i = base + t;
+            double v = i < nt ? red[i] : 0.0;
+            double inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (t >= o) inc += up;
+            }
+            if (i < nt) red[i] = carry + inc - v;  // exclusive
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    const double off = red[t];
+    if (off != 0.0)
+        for (int i = beg; i < end; ++i) a[i] += off;
+    __syncthreads();
+}
+
+// ---- loads ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ double load_as_double(const T* p);
+template <>
+__device__ __forceinline__ double load_as_double<uint8_t>(const uint8_t* p) { return (double)__ldg(p); }
+template <>
+__device__ __forceinline__ double load_as_double<float>(const float* p) { return (double)__ldg(p); }
+template <>
+__device__ __forceinline__ double load_as_double<double>(const double* p) { return __ldg(p); }
+#endif  // __CUDACC__
+
+}  // namespace aw

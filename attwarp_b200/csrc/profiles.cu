@@ -1,0 +1,407 @@
+// profiles.cu -- stages 2b-4: attention -> marginal profiles -> CDF knots -> inverse-CDF maps.
+//
+// Replaces, in float64 like the reference:
+//   * warp_image_by_attention up to np.interp ("Attention Guided Warping/new_method.py:207-261")
+//   * the knot/tie-break/np.interp part of warp_from_cdf_torch
+//     ("model/marginalnet_full_dataset/checkpoint_utils.py:157-189")
+//
+// Work per image is O(H*W) reads for a materialised attention map (marginals_partial_kernel,
+// many CTAs per image) and O(H+W) afterwards (one CTA per image: block scan in shared memory,
+// knots in shared memory, one bisection per output coordinate).  The 2-D meshgrid of the
+// reference (new_method.py:263-265) is never built: the maps stay separable.
+#include "common.cuh"
+
+namespace aw {
+namespace {
+
+constexpr int kProfThreads = 256;
+constexpr int kMargThreads = 256;
+constexpr int kMargRows = 64;          // rows per CTA of the marginals kernel
+constexpr int kMargColsPerThread = 4;  // columns per thread
+constexpr int kMargCols = kMargThreads * kMargColsPerThread;
+
+struct TransformArgs {
+    int transform;
+    int apply_inverse;
+    double exp_scale;
+    double exp_divisor;
+};
+
+// -------------------------------------------------------------------------------------------
+// Shared tail: profiles (shared memory) -> knots -> inverse maps for one image.
+//   prof_x[W], prof_y[H]: raw marginal sums of the biased map (new_method.py:215-216)
+//   knots: scratch of max(W,H)+1 doubles; red: >= blockDim.x doubles
+// -------------------------------------------------------------------------------------------
+__device__ void invert_axis(double* prof, int n, double total, int n_out, double* knots,
+                            double* red, float* __restrict__ out_map) {
+    block_inclusive_scan(prof, n, red);                       // np.cumsum            :242,248
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+        double k;
+        if (i == 0) k = 0.0;
+        else if (i == n) k = (double)n_out;                   // forced last knot      :254-255
+        else k = dmul_nofma(ddiv_exact(prof[i - 1], total), (double)n_out);  //       :243-245
+        knots[i] = k;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x)     // np.interp + f32 cast :260-265
+        out_map[j] = (float)interp_index((double)j, knots, n + 1);
+    __syncthreads();
+}
+
+__device__ void profiles_to_maps(double* prof_x, double* prof_y, int W, int H, int Wo, int Ho,
+                                 const TransformArgs& ta, double* knots, double* red,
+                                 float* __restrict__ map_x, float* __restrict__ map_y,
+                                 int* __restrict__ fallback_flag) {
+    // sum of the biased map (needed by the fallback's np.mean) = sum of raw row sums
+    double part = 0.0;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) part += prof_y[i];
+    const double sum_biased = block_sum(part, red);
+
+    if (ta.apply_inverse) {                                   // :219-226
+        const double bx = kBaseAttention * (double)H, by = kBaseAttention * (double)W;
+        for (int i = threadIdx.x; i < W; i += blockDim.x)
+            prof_x[i] = transform_inv(prof_x[i] - bx, ta.transform, ta.exp_scale, ta.exp_divisor) + bx;
+        for (int i = threadIdx.x; i < H; i += blockDim.x)
+            prof_y[i] = transform_inv(prof_y[i] - by, ta.transform, ta.exp_scale, ta.exp_divisor) + by;
+        __syncthreads();
+    }
+    part = 0.0;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) part += prof_x[i];
+    double total_x = block_sum(part, red);                    // :228
+    part = 0.0;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) part += prof_y[i];
+    double total_y = block_sum(part, red);                    // :229
+
+    const bool fallback = (total_x < kEpsilon) || (total_y < kEpsilon);   // :231
+    if (fallback) {                                           // :233-239
+        for (int i = threadIdx.x; i < W; i += blockDim.x) prof_x[i] = 1.0;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) prof_y[i] = 1.0;
+        const double mean = sum_biased / ((double)H * (double)W);
+        total_x = fmax((double)W * (mean * (double)H), kEpsilon);
+        total_y = fmax((double)H * (mean * (double)W), kEpsilon);
+        __syncthreads();
+    }
+    if (fallback_flag != nullptr && threadIdx.x == 0) *fallback_flag = fallback ? 1 : 0;
+
+    invert_axis(prof_x, W, total_x, Wo, knots, red, map_x);
+    invert_axis(prof_y, H, total_y, Ho, knots, red, map_y);
+}
+
+// -------------------------------------------------------------------------------------------
+// (P1) maps from a token grid that is index-upsampled on the fly.
+//   tok[b][gh*gw] given either final (nsplit==1, scale==1) or as stage-1 partials
+//   [b][nsplit][gh*gw] to be summed in split order and scaled (fused stage-1 finalize).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kProfThreads)
+maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
+                        float* __restrict__ tok_out, int gh, int gw, int H, int W, int Wo, int Ho,
+                        TransformArgs ta, float* __restrict__ map_x, float* __restrict__ map_y,
+                        int* __restrict__ fallback_flags) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int G = gh * gw;
+    double* red = smem;                       // kProfThreads
+    double* grid = red + kProfThreads;        // G   transformed + biased token values
+    double* csum = grid + G;                  // gw  column sums over the full-res rows
+    double* rsum = csum + gw;                 // gh
+    double* prof_x = rsum + gh;               // W
+    double* prof_y = prof_x + W;              // H
+    double* knots = prof_y + H;               // max(W,H)+1
+
+    const float* src = tok + (int64_t)b * nsplit * G;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        float v;
+        if (nsplit == 1 && scale == 1.0f) {
+            v = src[i];
+        } else {
+            float s = 0.f;
+            for (int k = 0; k < nsplit; ++k) s += src[(int64_t)k * G + i];
+            v = s * scale;
+        }
+        if (tok_out != nullptr) tok_out[(int64_t)b * G + i] = v;
+        const double a = clamp_nonneg((double)v);                                   // :207-208
+        grid[i] = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;  // :210-212
+    }
+    __syncthreads();
+    // number of full-res rows (cols) that index-map to grid row i (col c): floor-partition sizes
+    for (int c = threadIdx.x; c < gw; c += blockDim.x) {
+        double s = 0.0;
+        for (int i = 0; i < gh; ++i) {
+            const int y0 = (int)(((int64_t)i * H + gh - 1) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
+            s += (double)(y1 - y0) * grid[i * gw + c];
+        }
+        csum[c] = s;
+    }
+    for (int i = threadIdx.x; i < gh; i += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < gw; ++c) {
+            const int x0 = (int)(((int64_t)c * W + gw - 1) / gw), x1 = (int)(((int64_t)(c + 1) * W + gw - 1) / gw);
+            s += (double)(x1 - x0) * grid[i * gw + c];
+        }
+        rsum[i] = s;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) prof_x[x] = csum[(int)(((int64_t)x * gw) / W)];
+    for (int y = threadIdx.x; y < H; y += blockDim.x) prof_y[y] = rsum[(int)(((int64_t)y * gh) / H)];
+    __syncthreads();
+    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, map_x + (int64_t)b * Wo,
+                     map_y + (int64_t)b * Ho, fallback_flags ? fallback_flags + b : nullptr);
+}
+
+// -------------------------------------------------------------------------------------------
+// (P2) marginals of a materialised attention map: one pass over [H][W].
+//   grid = (col tiles, row chunks, B).  Each thread owns kMargColsPerThread adjacent columns and
+//   walks the rows of its chunk: column sums stay in registers (written as per-chunk partials),
+//   row sums are reduced per row with a warp-shuffle tree and combined across warps in shared
+//   memory (per-column-tile partials).  Both partial sets are summed in fixed order by the
+//   finish kernel -> deterministic.
+//   MODE 0: NumPy path  (clamp, transform, + 1e-9)   MODE 1: gt_marginals (clamp only)
+// -------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kMargThreads)
+marginals_partial_kernel(const T* __restrict__ att, int H, int W, TransformArgs ta,
+                         double* __restrict__ colpart, double* __restrict__ rowpart,
+                         int n_row_chunks, int n_col_tiles) {
+    __shared__ double s_row[kMargRows][kMargThreads / 32];
+    const int b = blockIdx.z, chunk = blockIdx.y, tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x0 = tile * kMargCols + threadIdx.x * kMargColsPerThread;
+    const int y0 = chunk * kMargRows, y1 = min(y0 + kMargRows, H);
+    const T* img = att + (int64_t)b * H * W;
+
+    double col[kMargColsPerThread];
+#pragma unroll
+    for (int k = 0; k < kMargColsPerThread; ++k) col[k] = 0.0;
+
+    for (int y = y0; y < y1; ++y) {
+        double rs = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMargColsPerThread; ++k) {
+            const int x = x0 + k;
+            if (x < W) {
+                double a = clamp_nonneg(load_as_double<T>(img + (int64_t)y * W + x));
+                if (MODE == 0) a = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
+                col[k] += a;
+                rs += a;
+            }
+        }
+        rs = warp_sum(rs);
+        if (lane == 0) s_row[y - y0][wid] = rs;
+    }
+    double* cp = colpart + ((int64_t)b * n_row_chunks + chunk) * W;
+#pragma unroll
+    for (int k = 0; k < kMargColsPerThread; ++k)
+        if (x0 + k < W) cp[x0 + k] = col[k];
+    __syncthreads();
+    double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
+    for (int r = threadIdx.x; r < y1 - y0; r += kMargThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kMargThreads / 32; ++w) s += s_row[r][w];
+        rp[y0 + r] = s;
+    }
+}
+
+// (P3) finish: sum the partials in fixed order, then the shared tail.
+__global__ void __launch_bounds__(kProfThreads)
+maps_from_partials_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
+                          int n_row_chunks, int n_col_tiles, int H, int W, int Wo, int Ho,
+                          TransformArgs ta, float* __restrict__ map_x, float* __restrict__ map_y,
+                          int* __restrict__ fallback_flags) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    double* red = smem;
+    double* prof_x = red + kProfThreads;
+    double* prof_y = prof_x + W;
+    double* knots = prof_y + H;
+    const double* cp = colpart + (int64_t)b * n_row_chunks * W;
+    const double* rp = rowpart + (int64_t)b * n_col_tiles * H;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < n_row_chunks; ++k) s += cp[(int64_t)k * W + x];
+        prof_x[x] = s;
+    }
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < n_col_tiles; ++k) s += rp[(int64_t)k * H + y];
+        prof_y[y] = s;
+    }
+    __syncthreads();
+    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, map_x + (int64_t)b * Wo,
+                     map_y + (int64_t)b * Ho, fallback_flags ? fallback_flags + b : nullptr);
+}
+
+// gt_marginals finish (checkpoint_utils.py:43-51): px = mx / max(sum mx, 1e-6), float32 out.
+__global__ void __launch_bounds__(kProfThreads)
+gt_marginals_finish_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
+                           int n_row_chunks, int n_col_tiles, int H, int W,
+                           float* __restrict__ px, float* __restrict__ py) {
+    __shared__ double red[kProfThreads];
+    const int b = blockIdx.x, axis = blockIdx.y;
+    const int n = axis == 0 ? W : H;
+    const int nparts = axis == 0 ? n_row_chunks : n_col_tiles;
+    const double* part = axis == 0 ? colpart + (int64_t)b * n_row_chunks * W
+                                   : rowpart + (int64_t)b * n_col_tiles * H;
+    float* out = axis == 0 ? px + (int64_t)b * W : py + (int64_t)b * H;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nparts; ++k) s += part[(int64_t)k * n + i];
+        acc += (double)(float)s;                      // the reference holds mx in float32
+    }
+    const float denom = fmaxf((float)block_sum(acc, red), 1e-6f);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nparts; ++k) s += part[(int64_t)k * n + i];
+        out[i] = (float)s / denom;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// (P4) maps from CDFs (torch path, checkpoint_utils.py:157-189), one CTA per (image, axis).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kProfThreads)
+maps_from_cdf_kernel(const float* __restrict__ Fx, const float* __restrict__ Fy, int H, int W,
+                     int Wo, int Ho, float* __restrict__ map_x, float* __restrict__ map_y) {
+    extern __shared__ double smem[];
+    __shared__ int s_tie;
+    const int b = blockIdx.x, axis = blockIdx.y;
+    const int n = axis == 0 ? W : H, n_out = axis == 0 ? Wo : Ho;
+    const float* F = axis == 0 ? Fx + (int64_t)b * W : Fy + (int64_t)b * H;
+    float* out = axis == 0 ? map_x + (int64_t)b * Wo : map_y + (int64_t)b * Ho;
+    double* knots = smem;  // n + 1
+    if (threadIdx.x == 0) s_tie = 0;
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+        double k;
+        if (i == 0) k = 0.0;                                       // concat([0.0], F) * out :171-175
+        else if (i == n) k = (double)n_out;                        // forced last knot      :177-178
+        else k = dmul_nofma((double)F[i - 1], (double)n_out);
+        knots[i] = k;
+    }
+    __syncthreads();
+    int tie = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tie |= (knots[i + 1] - knots[i] <= 0.0) ? 1 : 0;
+    if (tie) atomicOr(&s_tie, 1);                                  // np.any(np.diff <= 0)  :181,183
+    __syncthreads();
+    if (s_tie) {
+        // += (1e-4 / max(out,1)) * arange(n+1, dtype=float32): a float32 product    :182,184
+        const float step = (float)(1e-4 / (double)max(n_out, 1));
+        for (int i = threadIdx.x; i <= n; i += blockDim.x)
+            knots[i] = dadd_nofma(knots[i], (double)fmul_nofma(step, (float)i));
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x)          // np.interp :188-189, f32 :192-193
+        out[j] = (float)interp_index((double)j, knots, n + 1);
+}
+
+size_t maps_smem_bytes(int extra_doubles, int H, int W) {
+    return sizeof(double) * ((size_t)kProfThreads + extra_doubles + W + H + (size_t)max(W, H) + 1);
+}
+
+template <typename K>
+int opt_in_smem(K kern, size_t smem, const char* what) {
+    if (smem > 220 * 1024)
+        return fail(ATTWARP_ERR_UNSUPPORTED, "%s: image axes too long for shared-memory knots (%zu B)", what, smem);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return ATTWARP_OK;
+}
+
+TransformArgs to_args(const attwarp_transform_params& tp) {
+    TransformArgs ta;
+    ta.transform = tp.transform;
+    ta.apply_inverse = tp.apply_inverse;
+    ta.exp_scale = tp.exp_scale;
+    ta.exp_divisor = tp.exp_divisor;
+    return ta;
+}
+
+}  // namespace
+
+void marginals_geometry(int H, int W, int* n_row_chunks, int* n_col_tiles) {
+    *n_row_chunks = (H + kMargRows - 1) / kMargRows;
+    *n_col_tiles = (W + kMargCols - 1) / kMargCols;
+}
+
+int launch_maps_from_tokens(const float* tok, int nsplit, float scale, float* tok_out, int B,
+                            int gh, int gw, int H, int W, int Wo, int Ho,
+                            const attwarp_transform_params& tp, float* map_x, float* map_y,
+                            int* fallback_flags, cudaStream_t st) {
+    if (gh * gw > 8192) return fail(ATTWARP_ERR_UNSUPPORTED, "token grid %dx%d too large", gh, gw);
+    const size_t smem = maps_smem_bytes(gh * gw + gw + gh, H, W);
+    int rc = opt_in_smem(maps_from_tokens_kernel, smem, "maps_from_tokens");
+    if (rc != ATTWARP_OK) return rc;
+    maps_from_tokens_kernel<<<B, kProfThreads, smem, st>>>(tok, nsplit, scale, tok_out, gh, gw, H, W,
+                                                           Wo, Ho, to_args(tp), map_x, map_y,
+                                                           fallback_flags);
+    return check_launch("maps_from_tokens_kernel");
+}
+
+template <typename T, int MODE>
+static int launch_marginals(const void* att, int B, int H, int W, const TransformArgs& ta,
+                            double* colpart, double* rowpart, cudaStream_t st) {
+    int nrc, nct;
+    marginals_geometry(H, W, &nrc, &nct);
+    marginals_partial_kernel<T, MODE><<<dim3(nct, nrc, B), kMargThreads, 0, st>>>(
+        static_cast<const T*>(att), H, W, ta, colpart, rowpart, nrc, nct);
+    return check_launch("marginals_partial_kernel");
+}
+
+size_t maps_workspace_bytes_impl(int B, int H, int W) {
+    int nrc, nct;
+    marginals_geometry(H, W, &nrc, &nct);
+    return sizeof(double) * (size_t)B * ((size_t)nrc * W + (size_t)nct * H);
+}
+
+int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int W, int Wo, int Ho,
+                               const attwarp_transform_params& tp, void* ws, size_t ws_bytes,
+                               float* map_x, float* map_y, int* fallback_flags, cudaStream_t st) {
+    if (ws == nullptr || ws_bytes < maps_workspace_bytes_impl(B, H, W))
+        return fail(ATTWARP_ERR_WORKSPACE, "maps_from_attention: workspace too small (%zu < %zu)",
+                    ws_bytes, maps_workspace_bytes_impl(B, H, W));
+    int nrc, nct;
+    marginals_geometry(H, W, &nrc, &nct);
+    double* colpart = static_cast<double*>(ws);
+    double* rowpart = colpart + (size_t)B * nrc * W;
+    const TransformArgs ta = to_args(tp);
+    int rc;
+    switch (att_dtype) {
+        case ATTWARP_U8: rc = launch_marginals<uint8_t, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
+        case ATTWARP_F32: rc = launch_marginals<float, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
+        case ATTWARP_F64: rc = launch_marginals<double, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
+        default: return fail(ATTWARP_ERR_INVALID_ARG, "attention map dtype must be u8/f32/f64 (got %d)", att_dtype);
+    }
+    if (rc != ATTWARP_OK) return rc;
+    const size_t smem = maps_smem_bytes(0, H, W);
+    rc = opt_in_smem(maps_from_partials_kernel, smem, "maps_from_attention");
+    if (rc != ATTWARP_OK) return rc;
+    maps_from_partials_kernel<<<B, kProfThreads, smem, st>>>(colpart, rowpart, nrc, nct, H, W, Wo, Ho,
+                                                             ta, map_x, map_y, fallback_flags);
+    return check_launch("maps_from_partials_kernel");
+}
+
+int launch_gt_marginals(const float* A, int B, int H, int W, void* ws, size_t ws_bytes, float* px,
+                        float* py, cudaStream_t st) {
+    if (ws == nullptr || ws_bytes < maps_workspace_bytes_impl(B, H, W))
+        return fail(ATTWARP_ERR_WORKSPACE, "gt_marginals: workspace too small");
+    int nrc, nct;
+    marginals_geometry(H, W, &nrc, &nct);
+    double* colpart = static_cast<double*>(ws);
+    double* rowpart = colpart + (size_t)B * nrc * W;
+    TransformArgs ta = {0, 0, 1.0, 1.0};
+    int rc = launch_marginals<float, 1>(A, B, H, W, ta, colpart, rowpart, st);
+    if (rc != ATTWARP_OK) return rc;
+    gt_marginals_finish_kernel<<<dim3(B, 2), kProfThreads, 0, st>>>(colpart, rowpart, nrc, nct, H, W, px, py);
+    return check_launch("gt_marginals_finish_kernel");
+}
+
+int launch_maps_from_cdf(const float* Fx, const float* Fy, int B, int H, int W, int Wo, int Ho,
+                         float* map_x, float* map_y, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)max(W, H) + 1);
+    int rc = opt_in_smem(maps_from_cdf_kernel, smem, "maps_from_cdf");
+    if (rc != ATTWARP_OK) return rc;
+    maps_from_cdf_kernel<<<dim3(B, 2), kProfThreads, smem, st>>>(Fx, Fy, H, W, Wo, Ho, map_x, map_y);
+    return check_launch("maps_from_cdf_kernel");
+}
+
+}  // namespace aw

@@ -1,0 +1,151 @@
+// torch_path.cu -- stages 2-3 of the torch path: small row-wise float32 kernels.
+//
+// Replaces (file:line under "model/marginalnet_full_dataset/"):
+//   safe_softmax                model.py:8-14
+//   mix_with_uniform            model.py:98-101
+//   cdf_from_density            checkpoint_utils.py:30-41
+//   upsample_pdf_right_inverse  checkpoint_utils.py:64-131  (as y * M^T, M precomputed)
+//   F.adaptive_avg_pool2d       trainer.py:197
+// These move O(B*N) bytes (a few hundred KB at the benchmark sizes); they are latency-bound, one
+// CTA (or warp) per row, and exist so the path never leaves the device.
+#include "common.cuh"
+
+namespace aw {
+namespace {
+
+constexpr int kRowThreads = 128;
+
+__device__ __forceinline__ float nan_inf_to_zero(float v) { return (isnan(v) || isinf(v)) ? 0.f : v; }
+
+// One CTA per row.  safe_softmax: nan_to_num(0,0,0) -> subtract max -> softmax -> nan_to_num ->
+// / max(sum, eps).
+__global__ void __launch_bounds__(kRowThreads)
+safe_softmax_kernel(const float* __restrict__ logits, int N, float eps, float* __restrict__ out) {
+    __shared__ float red[32];
+    const float* row = logits + (int64_t)blockIdx.x * N;
+    float* o = out + (int64_t)blockIdx.x * N;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, nan_inf_to_zero(row[i]));
+    m = block_max(m, red);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s += expf(nan_inf_to_zero(row[i]) - m);
+    s = block_sum(s, red);
+    float s2 = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float p = nan_inf_to_zero(expf(nan_inf_to_zero(row[i]) - m) / s);
+        o[i] = p;
+        s2 += p;
+    }
+    s2 = block_sum(s2, red);
+    const float denom = fmaxf(s2, eps);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = o[i] / denom;
+}
+
+__global__ void mix_with_uniform_kernel(const float* __restrict__ p, int64_t total, float c1,
+                                        float c2, int copy_only, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    out[i] = copy_only ? p[i] : fadd_nofma(fmul_nofma(c1, p[i]), c2);
+}
+
+// cdf_from_density: clamp_min(0) (NaN survives), nan_to_num(0,0,0), / max(sum,1e-6), cumsum with
+// float64 accumulation rounded to float32 per element (what torch.cumsum does on CPU), last = 1.
+__global__ void __launch_bounds__(kRowThreads)
+cdf_from_density_kernel(const float* __restrict__ p, int N, float* __restrict__ F) {
+    extern __shared__ double sm[];
+    double* red = sm;              // kRowThreads
+    double* a = sm + kRowThreads;  // N
+    const float* row = p + (int64_t)blockIdx.x * N;
+    float* o = F + (int64_t)blockIdx.x * N;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float v = row[i];
+        v = isnan(v) ? v : fmaxf(v, 0.f);
+        v = nan_inf_to_zero(v);
+        a[i] = (double)v;
+        part += (double)v;
+    }
+    const float denom = fmaxf((float)block_sum(part, red), 1e-6f);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) a[i] = (double)((float)a[i] / denom);
+    __syncthreads();
+    block_inclusive_scan(a, N, red);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = (i == N - 1) ? 1.0f : (float)a[i];
+}
+
+// x[b][i] = sum_k M[i][k] * y[b][k]
+__global__ void upsample_right_inverse_kernel(const float* __restrict__ y,
+                                              const float* __restrict__ M, int L_out, int L_in,
+                                              float* __restrict__ x) {
+    extern __shared__ float ys[];
+    const int b = blockIdx.y;
+    for (int k = threadIdx.x; k < L_out; k += blockDim.x) ys[k] = y[(int64_t)b * L_out + k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L_in) return;
+    const float* m = M + (int64_t)i * L_out;
+    float acc = 0.f;
+    for (int k = 0; k < L_out; ++k) acc = fmaf(__ldg(m + k), ys[k], acc);
+    x[(int64_t)b * L_in + i] = acc;
+}
+
+// adaptive_avg_pool2d: one warp per output cell, window [floor(i*H/gh), ceil((i+1)*H/gh)).
+__global__ void adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw,
+                                           float* __restrict__ out) {
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    if (cell >= gh * gw) return;
+    const int i = cell / gw, j = cell - i * gw;
+    const int y0 = (int)(((int64_t)i * H) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
+    const int x0 = (int)(((int64_t)j * W) / gw), x1 = (int)(((int64_t)(j + 1) * W + gw - 1) / gw);
+    const float* img = A + (int64_t)b * H * W;
+    const int ww = x1 - x0, n = (y1 - y0) * ww;
+    double s = 0.0;
+    for (int e = lane; e < n; e += 32) {
+        const int yy = e / ww, xx = e - yy * ww;
+        s += (double)__ldg(img + (int64_t)(y0 + yy) * W + x0 + xx);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[(int64_t)b * gh * gw + cell] = (float)(s / (double)n);
+}
+
+}  // namespace
+
+int launch_safe_softmax(const float* logits, int B, int N, float eps, float* out, cudaStream_t st) {
+    safe_softmax_kernel<<<B, kRowThreads, 0, st>>>(logits, N, eps, out);
+    return check_launch("safe_softmax_kernel");
+}
+
+int launch_mix_with_uniform(const float* p, int B, int N, float alpha, float* out, cudaStream_t st) {
+    const int64_t total = (int64_t)B * N;
+    // (1 - alpha) and alpha / N are Python floats (float64) cast to the tensor dtype by torch
+    const float c1 = (float)(1.0 - (double)alpha), c2 = (float)((double)alpha / (double)N);
+    mix_with_uniform_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total, c1, c2,
+                                                                             alpha <= 0.f, out);
+    return check_launch("mix_with_uniform_kernel");
+}
+
+int launch_cdf_from_density(const float* p, int B, int N, float* F, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)kRowThreads + N);
+    if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "cdf_from_density: N=%d too long", N);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(cdf_from_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cdf_from_density_kernel<<<B, kRowThreads, smem, st>>>(p, N, F);
+    return check_launch("cdf_from_density_kernel");
+}
+
+int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,
+                                  float* x, cudaStream_t st) {
+    upsample_right_inverse_kernel<<<dim3((L_in + 127) / 128, B), 128, sizeof(float) * L_out, st>>>(
+        y, M, L_out, L_in, x);
+    return check_launch("upsample_right_inverse_kernel");
+}
+
+int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
+                               cudaStream_t st) {
+    const int warps_per_cta = 8;
+    adaptive_avg_pool2d_kernel<<<dim3((gh * gw + warps_per_cta - 1) / warps_per_cta, B),
+                                 warps_per_cta * 32, 0, st>>>(A, H, W, gh, gw, out);
+    return check_launch("adaptive_avg_pool2d_kernel");
+}
+
+}  // namespace aw

@@ -1,0 +1,211 @@
+"""Device-resident batched operators over the C ABI (torch tensors in, torch tensors out).
+
+These are the siblings SURVEY.md section 8(b) asks for next to the NumPy-signature drop-ins:
+inputs stay in HBM, outputs are allocated with torch's caching allocator, all work is enqueued
+on the current CUDA stream, nothing synchronises.  torch is plumbing only (memory + streams);
+every arithmetic step runs in libattwarp_sm100.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (LAYOUT_CHW, LAYOUT_HWC, TORCH_DTYPE_IDS, check, current_stream, load,
+                   make_transform, ptr, require_cuda)
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """A reusable uint8 scratch tensor of at least ``nbytes`` on ``device`` (stream-ordered
+    reuse is safe because all kernels of this package run on the caller's current stream)."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _tp(transform, exp_scale, exp_divisor, apply_inverse):
+    if isinstance(transform, _lib.TransformParams):
+        return transform
+    return make_transform(transform, exp_scale, exp_divisor, apply_inverse)
+
+
+# --------------------------------------------------------------------------------------------
+# stage 1
+# --------------------------------------------------------------------------------------------
+def aggregate_attention(attn: torch.Tensor, tok_start: torch.Tensor | None = None,
+                        num_tokens: int | None = None, out: torch.Tensor | None = None,
+                        accumulate: bool = False, out_scale: float = 1.0,
+                        eps: float = 1e-12) -> torch.Tensor:
+    """attn [B, L, Hh, K] (bf16/fp16/fp32, last dim contiguous, other dims arbitrarily strided)
+    -> float32 [B, T]:  mean over L and Hh of  a[..., st:st+T] / (sum + eps).
+    Reference: llava.py:94-132, 385-411 (L = hooked steps)."""
+    lib = load()
+    require_cuda(attn, tok_start, out)
+    assert attn.dim() == 4, "attn must be [B, L, Hh, K]"
+    if attn.stride(3) != 1:
+        raise ValueError("attention rows must be contiguous along the token axis")
+    B, L, Hh, K = attn.shape
+    T = K if num_tokens is None else int(num_tokens)
+    if tok_start is not None:
+        tok_start = tok_start.to(device=attn.device, dtype=torch.int32).contiguous()
+    if out is None:
+        out = torch.empty(B, T, dtype=torch.float32, device=attn.device)
+        accumulate = False
+    wsb = lib.attwarp_aggregate_workspace_bytes(B, L, Hh, T)
+    ws = _workspace(wsb, attn.device)
+    with torch.cuda.device(attn.device):
+        check(lib.attwarp_aggregate_attention(
+            ptr(attn), TORCH_DTYPE_IDS[attn.dtype], B, L, Hh, T, attn.stride(0), attn.stride(1),
+            attn.stride(2), ptr(tok_start), eps, ptr(ws), ws.numel(), ptr(out),
+            1 if accumulate else 0, float(out_scale), current_stream(attn.device)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# stages 2b-4
+# --------------------------------------------------------------------------------------------
+def maps_from_attention(att: torch.Tensor, out_size, transform="identity", exp_scale=1.0,
+                        exp_divisor=1.0, apply_inverse=False):
+    """att [B,H,W] (uint8/float32/float64) -> (map_x [B,Wo], map_y [B,Ho]) float32.
+    Reference: new_method.py:207-261."""
+    lib = load()
+    require_cuda(att)
+    att = att.contiguous()
+    B, H, W = att.shape
+    Ho, Wo = out_size
+    tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=att.device)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=att.device)
+    wsb = lib.attwarp_maps_workspace_bytes(B, H, W)
+    ws = _workspace(wsb, att.device)
+    with torch.cuda.device(att.device):
+        check(lib.attwarp_maps_from_attention(ptr(att), TORCH_DTYPE_IDS[att.dtype], B, H, W, Wo, Ho,
+                                              C.byref(tp), ptr(ws), ws.numel(), ptr(map_x),
+                                              ptr(map_y), current_stream(att.device)))
+    return map_x, map_y
+
+
+def maps_from_tokens(tok: torch.Tensor, image_size, out_size=None, transform="identity",
+                     exp_scale=1.0, exp_divisor=1.0, apply_inverse=False):
+    """tok [B,gh,gw] float32, index-upsampled on the fly to image_size=(H,W)."""
+    lib = load()
+    require_cuda(tok)
+    tok = tok.contiguous().float()
+    B, gh, gw = tok.shape
+    H, W = image_size
+    Ho, Wo = (H, W) if out_size is None else out_size
+    tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=tok.device)
+    with torch.cuda.device(tok.device):
+        check(lib.attwarp_maps_from_tokens(ptr(tok), B, gh, gw, H, W, Wo, Ho, C.byref(tp),
+                                           ptr(map_x), ptr(map_y), current_stream(tok.device)))
+    return map_x, map_y
+
+
+def maps_from_cdf(Fx: torch.Tensor, Fy: torch.Tensor, out_size=None):
+    """Fx [B,W], Fy [B,H] float32 CDFs -> (map_x [B,Wo], map_y [B,Ho]).
+    Reference: checkpoint_utils.py:157-189."""
+    lib = load()
+    require_cuda(Fx, Fy)
+    Fx = Fx.contiguous().float()
+    Fy = Fy.contiguous().float()
+    B, W = Fx.shape
+    H = Fy.shape[1]
+    Ho, Wo = (H, W) if out_size is None else out_size
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=Fx.device)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=Fx.device)
+    with torch.cuda.device(Fx.device):
+        check(lib.attwarp_maps_from_cdf(ptr(Fx), ptr(Fy), B, H, W, Wo, Ho, ptr(map_x), ptr(map_y),
+                                        current_stream(Fx.device)))
+    return map_x, map_y
+
+
+# --------------------------------------------------------------------------------------------
+# stage 5
+# --------------------------------------------------------------------------------------------
+def remap_bilinear(img: torch.Tensor, map_x: torch.Tensor, map_y: torch.Tensor,
+                   layout: str = "hwc", out: torch.Tensor | None = None) -> torch.Tensor:
+    """img [B,H,W,C] (layout 'hwc') or [B,C,H,W] ('chw'), uint8/float32; maps [B,Wo], [B,Ho].
+    cv2.remap(INTER_LINEAR, BORDER_REPLICATE) semantics (new_method.py:268-271)."""
+    lib = load()
+    require_cuda(img, map_x, map_y, out)
+    img = img.contiguous()
+    map_x = map_x.contiguous().float()
+    map_y = map_y.contiguous().float()
+    if layout == "hwc":
+        B, H, W, Cc = img.shape
+        lay = LAYOUT_HWC
+    elif layout == "chw":
+        B, Cc, H, W = img.shape
+        lay = LAYOUT_CHW
+    else:
+        raise ValueError(f"layout must be 'hwc' or 'chw', got {layout!r}")
+    Wo, Ho = map_x.shape[1], map_y.shape[1]
+    assert map_x.shape[0] == B and map_y.shape[0] == B
+    shape = (B, Ho, Wo, Cc) if layout == "hwc" else (B, Cc, Ho, Wo)
+    if out is None:
+        out = torch.empty(shape, dtype=img.dtype, device=img.device)
+    else:
+        assert tuple(out.shape) == shape and out.dtype == img.dtype and out.is_contiguous()
+    with torch.cuda.device(img.device):
+        check(lib.attwarp_remap_bilinear(ptr(img), ptr(out), TORCH_DTYPE_IDS[img.dtype], lay, B, Cc,
+                                         H, W, Ho, Wo, ptr(map_x), ptr(map_y),
+                                         current_stream(img.device)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# fused batch driver (BASELINE configs[1]/[2])
+# --------------------------------------------------------------------------------------------
+def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw, out_size=None,
+                               layout: str = "hwc", tok_start: torch.Tensor | None = None,
+                               transform="identity", exp_scale=1.0, exp_divisor=1.0,
+                               apply_inverse=False, out: torch.Tensor | None = None,
+                               return_aux: bool = False):
+    """Stages 1-5 for a uniform batch in one host call:
+    attn [B,L,Hh,K] -> token map [B,gh*gw] -> separable maps -> warped images."""
+    lib = load()
+    require_cuda(attn, images, tok_start, out)
+    assert attn.dim() == 4 and attn.stride(3) == 1
+    images = images.contiguous()
+    B, L, Hh, K = attn.shape
+    gh, gw = grid_hw
+    if tok_start is None:
+        assert K == gh * gw, "attention row length must equal gh*gw unless tok_start is given"
+    else:
+        tok_start = tok_start.to(device=attn.device, dtype=torch.int32).contiguous()
+    if layout == "hwc":
+        Bi, H, W, Cc = images.shape
+        lay = LAYOUT_HWC
+    else:
+        Bi, Cc, H, W = images.shape
+        lay = LAYOUT_CHW
+    assert Bi == B
+    Ho, Wo = (H, W) if out_size is None else out_size
+    shape = (B, Ho, Wo, Cc) if layout == "hwc" else (B, Cc, Ho, Wo)
+    if out is None:
+        out = torch.empty(shape, dtype=images.dtype, device=images.device)
+    dev = images.device
+    tok = torch.empty(B, gh * gw, dtype=torch.float32, device=dev)
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=dev)
+    tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
+    wsb = lib.attwarp_aggregate_workspace_bytes(B, L, Hh, gh * gw)
+    ws = _workspace(wsb, dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_warp_from_attention_tokens(
+            ptr(attn), TORCH_DTYPE_IDS[attn.dtype], B, L, Hh, attn.stride(0), attn.stride(1),
+            attn.stride(2), ptr(tok_start), gh, gw, ptr(images), ptr(out),
+            TORCH_DTYPE_IDS[images.dtype], lay, Cc, H, W, Ho, Wo, C.byref(tp), ptr(ws), ws.numel(),
+            ptr(tok), ptr(map_x), ptr(map_y), current_stream(dev)))
+    if return_aux:
+        return out, tok.view(B, gh, gw), map_x, map_y
+    return out

@@ -1,0 +1,102 @@
+"""GPU parity of the fused batch driver (stages 1-5, BASELINE configs[1]/[2] shapes) and
+size-independent properties at full benchmark sizes."""
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, need_gpu, rel_err
+from oracle import aggregate as OA
+from oracle import numpy_path as ON
+
+pytestmark = pytest.mark.gpu
+
+
+def _attention(B, L, Hh, T, dtype, seed):
+    gen = torch.Generator().manual_seed(seed)
+    a = torch.softmax(torch.randn(B, L, Hh, T + 124, generator=gen) * 2, dim=-1)[..., :T]
+    return a.contiguous().to(dtype)
+
+
+@pytest.mark.parametrize("B,L,Hh,gh,H,Ho,layout,transform", [
+    (6, 32, 32, 24, 336, 336, "hwc", "identity"),
+    (3, 4, 8, 24, 336, 500, "hwc", "sqrt"),
+    (2, 2, 4, 48, 1344, 1344, "hwc", "identity"),
+    (3, 4, 8, 24, 336, 336, "chw", "identity"),
+])
+def test_fused_batch_vs_oracle(B, L, Hh, gh, H, Ho, layout, transform):
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(B * 7 + H)
+    attn = _attention(B, L, Hh, gh * gh, torch.bfloat16, seed=H + B)
+    imgs = rng.integers(0, 256, (B, H, H, 3), dtype=np.uint8)
+    src = dev(imgs if layout == "hwc" else np.transpose(imgs, (0, 3, 1, 2)))
+    out, tok, mx, my = ops.warp_from_attention_tokens(attn.cuda(), src, (gh, gh), (Ho, Ho), layout,
+                                                      transform=transform, return_aux=True)
+    out = out.cpu().numpy()
+    if layout == "chw":
+        out = np.transpose(out, (0, 2, 3, 1))
+    tok = tok.cpu().numpy()
+    tok_ref = OA.aggregate_attention(attn.float().numpy())
+    assert rel_err(tok.reshape(B, -1), tok_ref, floor=1e-12) <= 1e-5
+    for b in range(B):
+        # stage-wise: stages 2-5 fed with the GPU's own token map (fp32), float64 oracle after
+        full = ON.upsample_tokens_nearest(tok[b], H, H)
+        ref, rx, ry = ON.warp_image_by_attention(imgs[b], full, Ho, Ho, transform, return_maps=True)
+        assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4
+        diff = np.abs(out[b].astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] at full size (256 x 336^2, [256,32,32,576] bf16): properties that do
+    not need the CPU oracle on every image + oracle spot checks."""
+    need_gpu()
+    from attwarp_b200 import ops
+    B, L, Hh, g, H = 256, 32, 32, 24, 336
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    attn = torch.softmax(torch.randn(B, L, Hh, g * g, device="cuda", generator=gen) * 2, -1).to(torch.bfloat16)
+    imgs = torch.randint(0, 256, (B, H, H, 3), device="cuda", dtype=torch.uint8, generator=gen)
+    out, tok, mx, my = ops.warp_from_attention_tokens(attn, imgs, (g, g), transform="identity",
+                                                      return_aux=True)
+    # token maps are probability maps: every row of stage 1 sums to 1 -> so does the mean
+    assert torch.allclose(tok.reshape(B, -1).sum(1), torch.ones(B, device="cuda"), atol=1e-4)
+    # maps are monotone non-decreasing and inside [0, W]
+    assert (mx[:, 1:] >= mx[:, :-1]).all() and (my[:, 1:] >= my[:, :-1]).all()
+    assert mx.min() >= 0 and mx.max() <= H and my.min() >= 0 and my.max() <= H
+    # determinism: a second run is bitwise identical
+    out2 = ops.warp_from_attention_tokens(attn, imgs, (g, g), transform="identity")
+    assert torch.equal(out, out2)
+    # uniform attention + same output size is the identity warp
+    uni = torch.full((B, 2, 2, g * g), 1.0 / (g * g), device="cuda", dtype=torch.bfloat16)
+    ident = ops.warp_from_attention_tokens(uni, imgs, (g, g), transform="identity")
+    assert torch.equal(ident, imgs)
+    # oracle spot checks on a few images of the big batch
+    for b in (0, 77, 255):
+        full = ON.upsample_tokens_nearest(tok[b].cpu().numpy(), H, H)
+        ref = ON.warp_image_by_attention(imgs[b].cpu().numpy(), full, H, H, "identity")
+        diff = np.abs(out[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1
+
+
+def test_full_size_properties_c3():
+    """BASELINE configs[2]: 64 x 1344^2 with a 48x48 token map."""
+    need_gpu()
+    from attwarp_b200 import ops
+    B, g, H = 64, 48, 1344
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    tok = torch.rand(B, g, g, device="cuda", generator=gen) ** 3
+    tok = tok / tok.sum(dim=(1, 2), keepdim=True)
+    imgs = torch.randint(0, 256, (B, H, H, 3), device="cuda", dtype=torch.uint8, generator=gen)
+    mx, my = ops.maps_from_tokens(tok, (H, H), transform="identity")
+    out = ops.remap_bilinear(imgs, mx, my, "hwc")
+    assert (mx[:, 1:] >= mx[:, :-1]).all() and (my[:, 1:] >= my[:, :-1]).all()
+    uni = torch.full_like(tok, 1.0 / (g * g))
+    ux, uy = ops.maps_from_tokens(uni, (H, H), transform="identity")
+    assert torch.equal(ops.remap_bilinear(imgs, ux, uy, "hwc"), imgs)
+    for b in (0, 63):
+        full = ON.upsample_tokens_nearest(tok[b].cpu().numpy(), H, H)
+        ref = ON.warp_image_by_attention(imgs[b].cpu().numpy(), full, H, H, "identity")
+        diff = np.abs(out[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1

@@ -1,0 +1,115 @@
+"""GPU parity, NumPy path (stages 2b-5): CUDA kernels vs golden vectors recorded from the real
+reference and vs the oracle.  Tolerances: BASELINE.md section 4 -- maps <= 1e-4 px, uint8 remap
+given identical maps 0 LSB, end-to-end uint8 +-1 LSB (we assert 0 where the reference's own
+maps are used and +-1 end to end)."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import numpy_case_names
+from gpu_util import dev, hwc, need_gpu
+from oracle import numpy_path as ON
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", numpy_case_names())
+def test_remap_given_reference_maps_is_bit_equal(golden_numpy, name):
+    need_gpu()
+    from attwarp_b200 import ops
+    c = golden_numpy.case(name)
+    img = hwc(c["image"])
+    out = ops.remap_bilinear(dev(img)[None], dev(c["map_x"])[None], dev(c["map_y"])[None], "hwc")
+    got = out[0].cpu().numpy()
+    assert np.array_equal(got, hwc(c["out"]))
+
+
+@pytest.mark.parametrize("name", numpy_case_names())
+def test_maps_and_end_to_end(golden_numpy, name):
+    need_gpu()
+    from attwarp_b200 import ops, new_method
+    c = golden_numpy.case(name)
+    tname = ON.resolve_transform(c["transform"])
+    att = c["att"]
+    att_t = dev(att if att.dtype in (np.uint8, np.float32, np.float64) else att.astype(np.float64))
+    mx, my = ops.maps_from_attention(att_t[None], (c["new_h"], c["new_w"]), tname, c["exp_scale"],
+                                     c["exp_divisor"], c["apply_inverse"])
+    assert np.abs(mx[0].cpu().numpy() - c["map_x"]).max() <= 1e-4
+    assert np.abs(my[0].cpu().numpy() - c["map_y"]).max() <= 1e-4
+    # the drop-in NumPy entry point (host buffers in / out), module-level transform state
+    new_method.set_transform_function(c["transform"], c["exp_scale"], c["exp_divisor"],
+                                      c["apply_inverse"])
+    out = new_method.warp_image_by_attention(c["image"], att, c["new_w"], c["new_h"])
+    assert out.shape == c["out"].shape and out.dtype == c["out"].dtype
+    diff = np.abs(out.astype(np.int32) - c["out"].astype(np.int32))
+    assert diff.max() <= 1, f"max LSB diff {diff.max()}"
+    assert (diff != 0).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("layout", ["hwc", "chw"])
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_remap_random_maps_vs_oracle(layout, dtype, C):
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(100 + C)
+    B, H, W, Ho, Wo = 3, 45, 67, 52, 71
+    img = (rng.integers(0, 256, (B, H, W, C)).astype(np.uint8) if dtype == np.uint8
+           else rng.random((B, H, W, C)).astype(np.float32))
+    mx = np.sort(rng.random((B, Wo)) * (W + 4) - 2, axis=1).astype(np.float32)
+    my = np.sort(rng.random((B, Ho)) * (H + 4) - 2, axis=1).astype(np.float32)
+    mx[:, :3] = [0.0, 1.0 / 64, 3.0 / 64]            # exact rounding ties
+    src = dev(img if layout == "hwc" else np.transpose(img, (0, 3, 1, 2)))
+    out = ops.remap_bilinear(src, dev(mx), dev(my), layout).cpu().numpy()
+    if layout == "chw":
+        out = np.transpose(out, (0, 2, 3, 1))
+    for b in range(B):
+        ref = hwc(ON.remap(img[b], mx[b], my[b]))
+        assert np.array_equal(out[b], ref)
+
+
+@pytest.mark.parametrize("gh,gw,H,W,Ho,Wo,transform", [
+    (24, 24, 336, 336, 336, 336, "identity"), (24, 24, 336, 336, 500, 500, "sqrt"),
+    (48, 48, 1344, 1344, 1344, 1344, "identity"), (24, 24, 100, 130, 90, 140, "square"),
+    (7, 5, 97, 53, 64, 200, "exp")])
+def test_maps_from_tokens_vs_oracle(gh, gw, H, W, Ho, Wo, transform):
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(gh * 1000 + W)
+    B = 3
+    tok = (rng.random((B, gh, gw)) ** 3).astype(np.float32)
+    tok /= tok.sum(axis=(1, 2), keepdims=True)
+    mx, my = ops.maps_from_tokens(dev(tok), (H, W), (Ho, Wo), transform, 2.0, 3.0)
+    for b in range(B):
+        full = ON.upsample_tokens_nearest(tok[b], H, W)
+        rx, ry, _, _ = ON.inverse_maps(full, Wo, Ho, transform, 2.0, 3.0)
+        assert np.abs(mx[b].cpu().numpy() - rx.astype(np.float32)).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry.astype(np.float32)).max() <= 1e-4
+
+
+def test_large_image_end_to_end_vs_oracle():
+    """1344x1344 (BASELINE configs[2] size) and a non-square large case, noise images."""
+    need_gpu()
+    from attwarp_b200 import new_method
+    rng = np.random.default_rng(5)
+    for (h, w, nh, nw) in [(1344, 1344, 1344, 1344), (700, 2048, 900, 1500)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        att = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out = new_method.warp_image_by_attention(img, att, nw, nh, transform="identity")
+        ref = ON.warp_image_by_attention(img, att, nw, nh, "identity")
+        diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+
+
+def test_error_behaviour():
+    need_gpu()
+    from attwarp_b200 import new_method
+    img = np.zeros((8, 9, 3), np.uint8)
+    with pytest.raises(ValueError):
+        new_method.warp_image_by_attention(img, np.zeros((8, 8), np.float32), 9, 8)
+    with pytest.raises(TypeError):
+        new_method.warp_image_by_attention(img.astype(np.int32), np.zeros((8, 9)), 9, 8)
+    assert new_method.set_transform_function("nope") == "identity"
+    assert new_method.save_warped_image("/nonexistent.png", np.zeros((4, 4)), None, None,
+                                        "/tmp/x.png") is False
