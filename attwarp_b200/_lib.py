@@ -59,7 +59,7 @@ SIGNATURES = {
     "attwarp_remap_bilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "attwarp_warp_from_attention_tokens": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _i,
                                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _tp, _vp,
-                                                _sz, _vp, _vp, _vp, _vp]),
+                                                _sz, _vp, _vp, _vp, C.POINTER(_vp), _vp]),
     "attwarp_warp_image_host": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _tp, _vp,
                                      C.POINTER(_i)]),
     "attwarp_safe_softmax": (_i, [_vp, _i, _i, _f, _vp, _vp]),

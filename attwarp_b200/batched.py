@@ -1,0 +1,66 @@
+"""Host-buffer batch pipeline: the call a user with NumPy/pinned-host data makes.
+
+``HostBatchPipeline.run(attn_host, images_host, out_host)`` takes a whole batch living in
+(pinned) host memory, splits it into chunks and drives, per chunk and on alternating CUDA
+streams:  H2D(attention) -> H2D(images) -> fused stages 1-5 -> D2H(warped images), so the copy
+engines and the SMs overlap.  Device buffers are allocated once and reused; nothing runs on the
+CPU except the enqueueing.  This is what ``bench.py`` reports as ``e2e``.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class HostBatchPipeline:
+    def __init__(self, chunk: int, L: int, Hh: int, grid_hw, image_hwc, out_hw=None,
+                 attn_dtype=torch.bfloat16, img_dtype=torch.uint8, transform="identity",
+                 n_streams: int = 2, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.chunk, self.L, self.Hh = chunk, L, Hh
+        self.gh, self.gw = grid_hw
+        self.H, self.W, self.C = image_hwc
+        self.Ho, self.Wo = (self.H, self.W) if out_hw is None else out_hw
+        self.transform = transform
+        T = self.gh * self.gw
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self.slots = []
+        for _ in range(n_streams):
+            self.slots.append(dict(
+                attn=torch.empty(chunk, L, Hh, T, dtype=attn_dtype, device=self.device),
+                img=torch.empty(chunk, self.H, self.W, self.C, dtype=img_dtype, device=self.device),
+                out=torch.empty(chunk, self.Ho, self.Wo, self.C, dtype=img_dtype, device=self.device),
+                aux=(torch.empty(chunk, T, dtype=torch.float32, device=self.device),
+                     torch.empty(chunk, self.Wo, dtype=torch.float32, device=self.device),
+                     torch.empty(chunk, self.Ho, dtype=torch.float32, device=self.device))))
+        self.kernel_launches = 0
+
+    def run(self, attn_host: torch.Tensor, images_host: torch.Tensor, out_host: torch.Tensor):
+        """attn_host [B,L,Hh,T], images_host [B,H,W,C], out_host [B,Ho,Wo,C]: host tensors
+        (pinned for real overlap).  Returns after everything is enqueued; call ``sync()``."""
+        B = attn_host.shape[0]
+        caller = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(caller)
+        k = 0
+        for lo in range(0, B, self.chunk):
+            hi = min(lo + self.chunk, B)
+            n = hi - lo
+            slot, st = self.slots[k % len(self.slots)], self.streams[k % len(self.streams)]
+            with torch.cuda.stream(st):
+                slot["attn"][:n].copy_(attn_host[lo:hi], non_blocking=True)
+                slot["img"][:n].copy_(images_host[lo:hi], non_blocking=True)
+                ops.warp_from_attention_tokens(
+                    slot["attn"][:n], slot["img"][:n], (self.gh, self.gw), (self.Ho, self.Wo), "hwc",
+                    transform=self.transform, out=slot["out"][:n],
+                    aux=tuple(a[:n] for a in slot["aux"]))
+                out_host[lo:hi].copy_(slot["out"][:n], non_blocking=True)
+            self.kernel_launches += 3
+            k += 1
+        for s in self.streams:
+            caller.wait_stream(s)
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()

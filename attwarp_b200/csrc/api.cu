@@ -210,7 +210,8 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
                                        void* dst, int img_dtype, int layout, int C, int H, int W,
                                        int Ho, int Wo, const attwarp_transform_params* tp,
                                        void* workspace, size_t workspace_bytes, float* tok_out,
-                                       float* map_x, float* map_y, void* stream) {
+                                       float* map_x, float* map_y, void* const* stage_events,
+                                       void* stream) {
     AW_REQUIRE(attn && src && dst && tok_out && map_x && map_y, "warp_from_attention_tokens: NULL pointer");
     AW_REQUIRE(B > 0 && L > 0 && Hh > 0 && gh > 0 && gw > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0,
                "warp_from_attention_tokens: sizes must be positive");
@@ -224,14 +225,24 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
     cudaStream_t st = as_stream(stream);
     const int nsplit = aggregate_nsplit(B, L, Hh);
     float* partial = static_cast<float*>(workspace);
+    auto mark = [&](int i) -> int {
+        if (stage_events == nullptr) return ATTWARP_OK;
+        AW_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st));
+        return ATTWARP_OK;
+    };
+    if ((rc = mark(0)) != ATTWARP_OK) return rc;
     rc = launch_aggregate_partial(attn, attn_dtype, B, L, Hh, T, stride_b, stride_l, stride_h, tok_start,
                                   1e-12f, partial, nsplit, st);
     if (rc != ATTWARP_OK) return rc;
+    if ((rc = mark(1)) != ATTWARP_OK) return rc;
     // stage-1 finalize is fused into the maps kernel (it sums the split partials in order)
     rc = launch_maps_from_tokens(partial, nsplit, 1.0f / ((float)L * (float)Hh), tok_out, B, gh, gw, H, W,
                                  Wo, Ho, *tp, map_x, map_y, nullptr, st);
     if (rc != ATTWARP_OK) return rc;
-    return launch_remap(src, dst, img_dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
+    if ((rc = mark(2)) != ATTWARP_OK) return rc;
+    rc = launch_remap(src, dst, img_dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
+    if (rc != ATTWARP_OK) return rc;
+    return mark(3);
 }
 
 int attwarp_warp_image_host(const void* image_host, int img_dtype, int C, int H, int W,

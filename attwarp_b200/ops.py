@@ -47,14 +47,14 @@ def aggregate_attention(attn: torch.Tensor, tok_start: torch.Tensor | None = Non
     -> float32 [B, T]:  mean over L and Hh of  a[..., st:st+T] / (sum + eps).
     Reference: llava.py:94-132, 385-411 (L = hooked steps)."""
     lib = load()
-    require_cuda(attn, tok_start, out)
+    require_cuda(attn, out)
     assert attn.dim() == 4, "attn must be [B, L, Hh, K]"
     if attn.stride(3) != 1:
         raise ValueError("attention rows must be contiguous along the token axis")
     B, L, Hh, K = attn.shape
     T = K if num_tokens is None else int(num_tokens)
-    if tok_start is not None:
-        tok_start = tok_start.to(device=attn.device, dtype=torch.int32).contiguous()
+    if tok_start is not None:          # list / CPU tensor / CUDA tensor of per-sample offsets
+        tok_start = torch.as_tensor(tok_start).to(device=attn.device, dtype=torch.int32).contiguous()
     if out is None:
         out = torch.empty(B, T, dtype=torch.float32, device=attn.device)
         accumulate = False
@@ -93,7 +93,7 @@ def maps_from_attention(att: torch.Tensor, out_size, transform="identity", exp_s
 
 
 def maps_from_tokens(tok: torch.Tensor, image_size, out_size=None, transform="identity",
-                     exp_scale=1.0, exp_divisor=1.0, apply_inverse=False):
+                     exp_scale=1.0, exp_divisor=1.0, apply_inverse=False, out=None):
     """tok [B,gh,gw] float32, index-upsampled on the fly to image_size=(H,W)."""
     lib = load()
     require_cuda(tok)
@@ -102,8 +102,12 @@ def maps_from_tokens(tok: torch.Tensor, image_size, out_size=None, transform="id
     H, W = image_size
     Ho, Wo = (H, W) if out_size is None else out_size
     tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
-    map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)
-    map_y = torch.empty(B, Ho, dtype=torch.float32, device=tok.device)
+    if out is not None:
+        map_x, map_y = out
+        assert tuple(map_x.shape) == (B, Wo) and tuple(map_y.shape) == (B, Ho)
+    else:
+        map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)
+        map_y = torch.empty(B, Ho, dtype=torch.float32, device=tok.device)
     with torch.cuda.device(tok.device):
         check(lib.attwarp_maps_from_tokens(ptr(tok), B, gh, gw, H, W, Wo, Ho, C.byref(tp),
                                            ptr(map_x), ptr(map_y), current_stream(tok.device)))
@@ -169,11 +173,12 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
                                layout: str = "hwc", tok_start: torch.Tensor | None = None,
                                transform="identity", exp_scale=1.0, exp_divisor=1.0,
                                apply_inverse=False, out: torch.Tensor | None = None,
-                               return_aux: bool = False):
+                               return_aux: bool = False, aux: tuple | None = None,
+                               stage_events=None):
     """Stages 1-5 for a uniform batch in one host call:
     attn [B,L,Hh,K] -> token map [B,gh*gw] -> separable maps -> warped images."""
     lib = load()
-    require_cuda(attn, images, tok_start, out)
+    require_cuda(attn, images, out)
     assert attn.dim() == 4 and attn.stride(3) == 1
     images = images.contiguous()
     B, L, Hh, K = attn.shape
@@ -181,7 +186,7 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
     if tok_start is None:
         assert K == gh * gw, "attention row length must equal gh*gw unless tok_start is given"
     else:
-        tok_start = tok_start.to(device=attn.device, dtype=torch.int32).contiguous()
+        tok_start = torch.as_tensor(tok_start).to(device=attn.device, dtype=torch.int32).contiguous()
     if layout == "hwc":
         Bi, H, W, Cc = images.shape
         lay = LAYOUT_HWC
@@ -194,9 +199,15 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
     if out is None:
         out = torch.empty(shape, dtype=images.dtype, device=images.device)
     dev = images.device
-    tok = torch.empty(B, gh * gw, dtype=torch.float32, device=dev)
-    map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)
-    map_y = torch.empty(B, Ho, dtype=torch.float32, device=dev)
+    if aux is not None:                      # caller-provided (tok, map_x, map_y) buffers
+        tok, map_x, map_y = aux
+    else:
+        tok = torch.empty(B, gh * gw, dtype=torch.float32, device=dev)
+        map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)
+        map_y = torch.empty(B, Ho, dtype=torch.float32, device=dev)
+    ev = None
+    if stage_events is not None:             # 4 recorded torch.cuda.Event(enable_timing=True)
+        ev = (C.c_void_p * 4)(*[e.cuda_event for e in stage_events])
     tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
     wsb = lib.attwarp_aggregate_workspace_bytes(B, L, Hh, gh * gw)
     ws = _workspace(wsb, dev)
@@ -205,7 +216,7 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
             ptr(attn), TORCH_DTYPE_IDS[attn.dtype], B, L, Hh, attn.stride(0), attn.stride(1),
             attn.stride(2), ptr(tok_start), gh, gw, ptr(images), ptr(out),
             TORCH_DTYPE_IDS[images.dtype], lay, Cc, H, W, Ho, Wo, C.byref(tp), ptr(ws), ws.numel(),
-            ptr(tok), ptr(map_x), ptr(map_y), current_stream(dev)))
+            ptr(tok), ptr(map_x), ptr(map_y), ev, current_stream(dev)))
     if return_aux:
         return out, tok.view(B, gh, gw), map_x, map_y
     return out

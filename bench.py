@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- warped images/s of the attention-guided warp hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  c2 (default; BASELINE.json configs[1]): 256 x 336^2 RGB uint8 + bf16 attention
+      [256, 32, 32, 576]  -> stage 1 aggregation -> 24x24 token map -> marginals / CDF /
+      inverse-CDF maps -> bilinear resample (cv2.remap semantics) to 336^2.
+  c3 (configs[2]): 64 x 1344^2 RGB uint8 + 48x48 token maps -> maps -> resample.
+For N > 1 (launched under torchrun, one rank per GPU) every rank processes its own batch
+(weak scaling, images sharded by index, no data-path collective); NCCL only gathers timings and
+checksums.  Rank 0 prints ONE JSON line.
+
+`value`  : whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same metric through the host-buffer pipeline (pinned host -> H2D -> kernels -> D2H).
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured
+            HBM copy peak (MEASURED_PEAKS.json).
+`cpu_baseline`: the oracle port of the reference CPU path on this box's host cores (bounded sample).
+`--impl reference`: only the CPU arm, same metric/config, `"impl": "reference"`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "warped_images_per_sec"
+UNIT = "images/s"
+
+WORKLOADS = {
+    "c2": dict(name="c2: LLaVA-1.5 batch 256x336^2 RGB u8 + bf16 attention [256,32,32,576] "
+                    "aggregation + 24x24 token map -> inverse-CDF warp -> 336^2",
+               B=256, L=32, Hh=32, grid=24, side=336, C=3, has_attention=True),
+    "c3": dict(name="c3: Qwen-VL-style batch 64x1344^2 RGB u8 + 48x48 token map upsample + "
+                    "inverse-CDF warp -> 1344^2",
+               B=64, L=0, Hh=0, grid=48, side=1344, C=3, has_attention=False),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(kernel, workload):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "50"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for k, nm in enumerate(names):
+                    if f[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference)
+# ------------------------------------------------------------------------------------------
+def cpu_arm(wl_key, steps, warmup, budget_s, full_steps):
+    """Times the oracle port on the host cores.  Each step = one pass over a bounded sample of
+    the workload (the full batch when it is cheap enough)."""
+    from oracle import cpu_baseline as CB
+    wl = WORKLOADS[wl_key]
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # calibrate on a couple of images, single process
+    if wl["has_attention"]:
+        attn, imgs = CB.make_c2_sample(2, wl["L"], wl["Hh"], wl["grid"], wl["side"])
+        tok = None
+    else:
+        tok, imgs = CB.make_c3_sample(2, wl["grid"], wl["side"])
+        attn = None
+    r = CB.CpuRunner(attn, tok, imgs, wl["grid"], (wl["side"], wl["side"]), workers=1)
+    r.step()
+    t1, _ = r.step()
+    per_img = t1 / 2
+    r.close()
+    total_steps = steps + warmup
+    # images per step so that the whole run fits the budget (assume ~70 % parallel efficiency)
+    n = int(budget_s / max(total_steps, 1) / per_img * avail * 0.7)
+    n = max(min(n, wl["B"]), min(avail, wl["B"]), 1)
+    if wl["has_attention"]:
+        attn, imgs = CB.make_c2_sample(n, wl["L"], wl["Hh"], wl["grid"], wl["side"])
+    else:
+        tok, imgs = CB.make_c3_sample(n, wl["grid"], wl["side"])
+    runner = CB.CpuRunner(attn, tok, imgs, wl["grid"], (wl["side"], wl["side"]))
+    for _ in range(warmup):
+        runner.step()
+    t = 0.0
+    for _ in range(steps):
+        dt, _ = runner.step()
+        t += dt
+    runner.close()
+    value = n * steps / t
+    import cv2
+    import numpy
+    info = {"value": value, "unit": UNIT, "cores": runner.workers, "kind": "port",
+            "sample": f"{n} of {wl['B']} images per step x {steps} steps ({warmup} warm-up), "
+                      f"{runner.workers} fork()ed workers x 1 image at a time, cv2.setNumThreads(1); "
+                      f"single-process cost {per_img * 1e3:.2f} ms/image; numpy {numpy.__version__}, "
+                      f"cv2 {cv2.__version__}; host cpus visible {avail}"}
+    return info, t / steps * 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    info, ms_per_step = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0,
+                                full_steps=True)
+    line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "timing": "wall clock around each CPU step"},
+            "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    wl = WORKLOADS[args.workload]
+    cpu_info = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised (the pool forks)
+        cpu_info, _ = cpu_arm(args.workload, steps=3, warmup=1, budget_s=20.0, full_steps=False)
+
+    import torch
+    import torch.distributed as dist
+
+    from attwarp_b200 import ops, sharding
+    from attwarp_b200.batched import HostBatchPipeline
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, side, C, grid = wl["B"], wl["side"], wl["C"], wl["grid"]
+    L, Hh, T = wl["L"], wl["Hh"], wl["grid"] ** 2
+    R = args.rotate
+    gen = torch.Generator(device=dev).manual_seed(1235 + rank)
+    sets = []
+    for _ in range(R):
+        s = {}
+        if wl["has_attention"]:
+            chunks = []
+            for lo in range(0, B, 64):                 # bounded fp32 temporaries
+                z = torch.randn(min(64, B - lo), L, Hh, T, device=dev, generator=gen) * 2
+                chunks.append(torch.softmax(z, -1).to(torch.bfloat16))
+            s["attn"] = torch.cat(chunks)
+            del chunks, z
+        else:
+            tok = torch.rand(B, grid, grid, device=dev, generator=gen) ** 3
+            s["tok"] = (tok / tok.sum(dim=(1, 2), keepdim=True)).contiguous()
+        s["img"] = torch.randint(0, 256, (B, side, side, C), device=dev, dtype=torch.uint8, generator=gen)
+        s["out"] = torch.empty(B, side, side, C, device=dev, dtype=torch.uint8)
+        s["aux"] = (torch.empty(B, T, device=dev), torch.empty(B, side, device=dev),
+                    torch.empty(B, side, device=dev))
+        sets.append(s)
+
+    n_steps_total = args.warmup + args.steps
+    use_ev = wl["has_attention"] and not args.no_stage_events
+    stage_ev = None
+    if use_ev:
+        stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        for evs in stage_ev:
+            for e in evs:
+                e.record()                              # materialise the cudaEvent_t handles
+
+    def step(i, evs=None):
+        s = sets[i % R]
+        if wl["has_attention"]:
+            ops.warp_from_attention_tokens(s["attn"], s["img"], (grid, grid), None, "hwc",
+                                           transform="identity", out=s["out"], aux=s["aux"],
+                                           stage_events=evs)
+            return 3
+        mx, my = s["aux"][1], s["aux"][2]
+        ops.maps_from_tokens(s["tok"], (side, side), None, "identity", out=(mx, my))
+        ops.remap_bilinear(s["img"], mx, my, "hwc", out=s["out"])
+        return 2
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ev0.record()
+    for i in range(args.steps):
+        launches += step(args.warmup + i, stage_ev[i] if use_ev else None)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+
+    chk = sharding.checksum64(sets[(n_steps_total - 1) % R]["out"][:8])
+    stats = sharding.gather_stats(elapsed_ms, B * args.steps, chk, dev)
+    value = sharding.aggregate_throughput(stats)
+    worst_ms = max(s[0] for s in stats)
+
+    # ---- per-kernel durations (CUDA events recorded by the library between the stages) -------
+    peak, peak_src = measured_peak()
+    kernels = {}
+    if use_ev:
+        names = ["aggregate_rows_vec_kernel", "maps_from_tokens_kernel", "remap_kernel"]
+        byts = [B * (L * Hh * T * 2 + T * 4), B * (T * 4 + 2 * side * 4), B * side * side * C * 2]
+        for k, (nm, by) in enumerate(zip(names, byts)):
+            ms = sum(evs[k].elapsed_time(evs[k + 1]) for evs in stage_ev) / args.steps
+            kernels[nm] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
+                           "frac": by / ms / 1e6 / peak}
+    else:
+        # c3: time the resample kernel alone with events around it
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for i in range(args.steps):
+            s = sets[i % R]
+            e0.record()
+            ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"])
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        by = B * side * side * C * 2
+        ms = tot / args.steps
+        kernels["remap_kernel"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
+                                   "frac": by / ms / 1e6 / peak}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.workload),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+                "kernel_ms": kernels[dom]["ms"]}
+
+    # ---- e2e: pinned host buffers -> H2D -> kernels -> D2H, per step -----------------------------
+    e2e = None
+    if wl["has_attention"] and not args.no_e2e:
+        h_attn = torch.empty(B, L, Hh, T, dtype=torch.bfloat16).pin_memory()
+        h_img = torch.empty(B, side, side, C, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(B, side, side, C, dtype=torch.uint8).pin_memory()
+        h_attn.copy_(sets[0]["attn"])
+        h_img.copy_(sets[0]["img"])
+        pipe = HostBatchPipeline(args.e2e_chunk, L, Hh, (grid, grid), (side, side, C), device=dev)
+        for _ in range(2):
+            pipe.run(h_attn, h_img, h_out)
+        pipe.sync()
+        ke = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ke):
+            pipe.run(h_attn, h_img, h_out)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ems = e0.elapsed_time(e1)
+        est = sharding.gather_stats(ems, B * ke, int(h_out[:4].to(torch.int64).sum()), dev)
+        e2e = {"value": sharding.aggregate_throughput(est), "unit": UNIT,
+               "h2d_bytes_per_step": h_attn.numel() * 2 + h_img.numel(),
+               "d2h_bytes_per_step": h_out.numel(), "steps": ke, "chunk": args.e2e_chunk,
+               "ms_per_step": max(s[0] for s in est) / ke,
+               "api": "attwarp_b200.batched.HostBatchPipeline.run (pinned host in/out)"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16->fp32 (stage 1), f64 (stages 2-4), u8 fixed-point (stage 5)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "images_per_step_per_gpu": B,
+                       "l2_policy": f"inputs rotate over {R} resident buffer sets; one batch "
+                                    f"(attention+images) is {sum(t.numel() * t.element_size() for t in sets[0].values() if hasattr(t, 'numel')) / 1e6:.0f} MB > 126 MB L2",
+                       "parallelism": f"images sharded by index over {world} GPU(s), no data-path collective",
+                       "transform": "identity", "stage_events_in_timed_region": bool(use_ev)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_info,
+            "per_rank_ms": [s[0] for s in stats]}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rotate", type=int, default=3, help="resident input buffer sets to rotate over")
+    ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage-events", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running 1 rank",
+              file=sys.stderr)
+    return run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

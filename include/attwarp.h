@@ -157,7 +157,9 @@ int attwarp_remap_bilinear(const void* src, void* dst, int dtype, int layout, in
  * attwarp_warp_from_attention_tokens: stages 1-5 for a uniform batch (BASELINE configs[1]):
  *   attention [B,L,Hh,*] -> token map [B,gh*gw] -> maps -> warped uint8/float32 images.
  * tok_out / map_x / map_y are outputs the caller may inspect (required, not optional).
- * workspace: attwarp_aggregate_workspace_bytes(B,L,Hh,gh*gw). */
+ * workspace: attwarp_aggregate_workspace_bytes(B,L,Hh,gh*gw).
+ * stage_events: NULL, or 4 cudaEvent_t handles recorded on `stream` before stage 1, after
+ *   stage 1, after stages 2-4 and after stage 5 (per-kernel timing for the roofline report). */
 int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, int L, int Hh,
                                        int64_t stride_b, int64_t stride_l, int64_t stride_h,
                                        const int32_t* tok_start, int gh, int gw,
@@ -165,7 +167,7 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
                                        int C, int H, int W, int Ho, int Wo,
                                        const attwarp_transform_params* tp, void* workspace,
                                        size_t workspace_bytes, float* tok_out, float* map_x,
-                                       float* map_y, void* stream);
+                                       float* map_y, void* const* stage_events, void* stream);
 
 /* attwarp_warp_image_host: the whole of warp_image_by_attention (AGW/new_method.py:198-283) for
  * ONE image with HOST buffers, as the NumPy signature implies: H2D, stages 2b-5 on the device,
