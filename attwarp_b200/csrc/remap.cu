@@ -9,6 +9,9 @@
 //   remap_direct_kernel   any dtype / layout / channel count; one thread per output pixel,
 //                         taps gathered straight from global memory through L1/L2.  Baseline and
 //                         fallback for shapes the tiled kernel does not cover.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace aw {
@@ -76,10 +79,29 @@ int launch_direct(const void* src, void* dst, int layout, int B, int C, int H, i
 
 }  // namespace
 
+int launch_remap_u8_tiled(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
+                          const float* map_x, const float* map_y, int map_div, cudaStream_t st);
+
+// ATTWARP_REMAP=direct forces the baseline gather kernel (A/B comparisons, debugging).
+static bool force_direct() {
+    static const bool v = [] {
+        const char* e = getenv("ATTWARP_REMAP");
+        return e != nullptr && strcmp(e, "direct") == 0;
+    }();
+    return v;
+}
+
 int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C, int H, int W,
                  int Ho, int Wo, const float* map_x, const float* map_y, cudaStream_t st) {
     if (Ho > 65535 || B > 65535)
         return fail(ATTWARP_ERR_UNSUPPORTED, "remap: Ho=%d / B=%d exceed the grid limits", Ho, B);
+    if (dtype == ATTWARP_U8 && !force_direct()) {
+        // HWC with 1/3/4 interleaved channels, or planar = B*C single-channel images
+        if (layout == ATTWARP_LAYOUT_HWC && (C == 1 || C == 3 || C == 4))
+            return launch_remap_u8_tiled(src, dst, B, C, H, W, Ho, Wo, map_x, map_y, 1, st);
+        if (layout == ATTWARP_LAYOUT_CHW && (int64_t)B * C <= 65535)
+            return launch_remap_u8_tiled(src, dst, B * C, 1, H, W, Ho, Wo, map_x, map_y, C, st);
+    }
     if (dtype == ATTWARP_U8)
         return launch_direct<uint8_t>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
     if (dtype == ATTWARP_F32)
