@@ -95,7 +95,7 @@ int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C
                  int Ho, int Wo, const float* map_x, const float* map_y, cudaStream_t st) {
     if (Ho > 65535 || B > 65535)
         return fail(ATTWARP_ERR_UNSUPPORTED, "remap: Ho=%d / B=%d exceed the grid limits", Ho, B);
-    if (dtype == ATTWARP_U8 && !force_direct()) {
+    if (dtype == ATTWARP_U8 && !force_direct() && H >= 2 && W >= 2) {
         // HWC with 1/3/4 interleaved channels, or planar = B*C single-channel images
         if (layout == ATTWARP_LAYOUT_HWC && (C == 1 || C == 3 || C == 4))
             return launch_remap_u8_tiled(src, dst, B, C, H, W, Ho, Wo, map_x, map_y, 1, st);

@@ -1,0 +1,114 @@
+"""GPU parity, stage 5 edge cases: the tiled uint8 resample kernel against the oracle's restatement
+of cv2.remap(INTER_LINEAR, BORDER_REPLICATE) (itself pinned to the real cv2 in
+test_oracle_vs_golden.py).  Bit-exact (0 LSB) given identical float32 maps.
+
+Covers what the attention-derived maps of the benchmark never produce but the C ABI accepts:
+non-monotone maps (per-row path), strong minification (source rows skipped / pass splitting /
+direct-row path), strong magnification (many output rows per source row pair), constant and
+out-of-range maps (border replicate on every tap), degenerate 1-pixel axes, odd pitches that make
+every row start at a different 16-byte phase."""
+
+import numpy as np
+import pytest
+
+from gpu_util import dev, hwc, need_gpu
+from oracle import numpy_path as ON
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(img, mx, my, layout="hwc"):
+    from attwarp_b200 import ops
+    B = img.shape[0]
+    src = dev(img if layout == "hwc" else np.ascontiguousarray(np.transpose(img, (0, 3, 1, 2))))
+    out = ops.remap_bilinear(src, dev(mx), dev(my), layout).cpu().numpy()
+    if layout == "chw":
+        out = np.transpose(out, (0, 2, 3, 1))
+    for b in range(B):
+        ref = hwc(ON.remap(img[b], mx[b], my[b]))
+        assert np.array_equal(out[b], ref), f"image {b}: {np.abs(out[b].astype(int) - ref.astype(int)).max()} LSB"
+
+
+@pytest.mark.parametrize("layout", ["hwc", "chw"])
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_unsorted_maps(layout, C):
+    need_gpu()
+    rng = np.random.default_rng(7 + C)
+    B, H, W, Ho, Wo = 2, 61, 83, 70, 97
+    img = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    mx = (rng.random((B, Wo)) * (W + 6) - 3).astype(np.float32)
+    my = (rng.random((B, Ho)) * (H + 6) - 3).astype(np.float32)
+    _check(img, mx, my, layout)
+
+
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_strong_minification(C):
+    """2048 -> 40 rows/cols: source rows between taps are skipped, spans exceed the arena."""
+    need_gpu()
+    rng = np.random.default_rng(17 + C)
+    B, H, W, Ho, Wo = 1, 1500, 1700, 40, 45
+    img = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    mx = np.sort(rng.random((B, Wo)) * W, axis=1).astype(np.float32)
+    my = np.sort(rng.random((B, Ho)) * H, axis=1).astype(np.float32)
+    _check(img, mx, my)
+    # moderate vertical minification only (3.7x): rows are skipped but the pass still fits
+    my2 = (np.arange(400, dtype=np.float32) * 3.7)[None]
+    mx2 = (np.arange(500, dtype=np.float32) * 1.01 + 0.3)[None]
+    _check(img, mx2, my2)
+
+
+@pytest.mark.parametrize("C", [1, 3])
+def test_strong_magnification(C):
+    """12 source pixels stretched over 700 outputs: many output rows share one slot pair."""
+    need_gpu()
+    rng = np.random.default_rng(27 + C)
+    B, H, W, Ho, Wo = 2, 12, 13, 700, 650
+    img = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    mx = np.tile(np.linspace(-0.5, W - 0.4, Wo, dtype=np.float32), (B, 1))
+    my = np.tile(np.linspace(-0.5, H - 0.4, Ho, dtype=np.float32), (B, 1))
+    _check(img, mx, my)
+
+
+def test_constant_and_out_of_range_maps():
+    need_gpu()
+    rng = np.random.default_rng(3)
+    B, H, W, Ho, Wo = 3, 33, 47, 50, 60
+    img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    mx = np.stack([np.full(Wo, -7.3), np.full(Wo, W + 100.0), np.full(Wo, 11.49)]).astype(np.float32)
+    my = np.stack([np.full(Ho, H + 9.0), np.full(Ho, -1e6), np.full(Ho, 5.5)]).astype(np.float32)
+    _check(img, mx, my)
+    # decreasing maps (a flip)
+    mx = np.tile(np.linspace(W - 1, 0, Wo, dtype=np.float32), (B, 1))
+    my = np.tile(np.linspace(H - 1, 0, Ho, dtype=np.float32), (B, 1))
+    _check(img, mx, my)
+
+
+@pytest.mark.parametrize("H,W", [(1, 50), (50, 1), (1, 1), (2, 2)])
+def test_degenerate_axes(H, W):
+    need_gpu()
+    rng = np.random.default_rng(H * 100 + W)
+    img = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    mx = np.sort(rng.random((2, 37)) * (W + 2) - 1, axis=1).astype(np.float32)
+    my = np.sort(rng.random((2, 29)) * (H + 2) - 1, axis=1).astype(np.float32)
+    _check(img, mx, my)
+    _check(img, mx, my, "chw")
+
+
+@pytest.mark.parametrize("W,Wo", [(333, 335), (500, 501), (1021, 777)])
+def test_odd_pitches(W, Wo):
+    """Row pitches that are not multiples of 4 / 16 bytes: every staged row has its own phase."""
+    need_gpu()
+    rng = np.random.default_rng(W)
+    H, Ho = 77, 91
+    img = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    mx = np.sort(rng.random((2, Wo)) * W, axis=1).astype(np.float32)
+    my = np.sort(rng.random((2, Ho)) * H, axis=1).astype(np.float32)
+    _check(img, mx, my)
+    # a view with a non-zero storage offset: the image base itself is misaligned
+    from attwarp_b200 import ops
+    import torch
+    flat = torch.zeros(img[0].size + 5, dtype=torch.uint8, device="cuda")
+    flat[5:] = torch.from_numpy(img[0]).cuda().reshape(-1)
+    view = flat[5:].view(1, H, W, 3)
+    out = ops.remap_bilinear(view, dev(mx[:1]), dev(my[:1]), "hwc")[0].cpu().numpy()
+    assert np.array_equal(out, ON.remap(img[0], mx[0], my[0]))
