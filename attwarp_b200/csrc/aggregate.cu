@@ -13,6 +13,8 @@
 //   * warps of a CTA are combined through shared memory in warp order, CTAs of an image through
 //     a [B][nsplit][T] fp32 partial buffer that the consumer (finalize kernel or the fused
 //     maps-from-tokens kernel) sums in split order -> bitwise deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aw {
@@ -243,13 +245,23 @@ int dispatch(const void* attn, int B, int L, int Hh, int Tlen, int64_t sb, int64
 
 }  // namespace
 
-// Number of CTAs per image: enough CTAs to fill the machine a few times over, but never fewer
-// than 2 rows per warp.
+bool aggregate_tma_applicable(const void* attn, int dtype, int L, int Hh, int T, int64_t sb, int64_t sl,
+                              int64_t sh, const int32_t* tok_start);
+int launch_aggregate_tma(const void* attn, int dtype, int B, int L, int Hh, int T, int64_t sb, float eps,
+                         float* partial, int nsplit, cudaStream_t st);
+
+// Number of CTAs per image.  The kernel is a pure stream, so the best launch is ONE resident
+// wave of equal, long-lived CTAs (pipeline fill and the per-CTA epilogue are paid once per CTA,
+// and equal slabs finish together whatever SM they landed on): as many CTAs per image as still
+// fit the resident set (4 per SM), never fewer than 2 rows per warp.
 int aggregate_nsplit(int B, int L, int Hh) {
+    static const int forced = [] {
+        const char* e = getenv("ATTWARP_AGG_NSPLIT");
+        return e ? atoi(e) : 0;
+    }();
     const int n_rows = L * Hh;
-    const int target_ctas = 4 * sm_count();
-    int nsplit = (target_ctas + B - 1) / B;
     const int max_split = (n_rows + 2 * kAggWarps - 1) / (2 * kAggWarps);
+    int nsplit = forced > 0 ? forced : (4 * sm_count()) / (B > 0 ? B : 1);
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;
     return nsplit;
@@ -258,6 +270,10 @@ int aggregate_nsplit(int B, int L, int Hh) {
 int launch_aggregate_partial(const void* attn, int dtype, int B, int L, int Hh, int T, int64_t sb,
                              int64_t sl, int64_t sh, const int32_t* tok_start, float eps,
                              float* partial, int nsplit, cudaStream_t st) {
+    if (aggregate_tma_applicable(attn, dtype, L, Hh, T, sb, sl, sh, tok_start)) {
+        const int rc = launch_aggregate_tma(attn, dtype, B, L, Hh, T, sb, eps, partial, nsplit, st);
+        if (rc != ATTWARP_ERR_UNSUPPORTED) return rc;
+    }
     switch (dtype) {
         case ATTWARP_BF16:
             return dispatch<__nv_bfloat16>(attn, B, L, Hh, T, sb, sl, sh, tok_start, eps, partial, nsplit, st);

@@ -135,6 +135,59 @@ __device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* r
     __syncthreads();
 }
 
+// ---- thread groups: a contiguous run of warps of a CTA that synchronises on its own named barrier ----
+// (lets the x axis and the y axis of one image be processed concurrently by the two halves of a CTA)
+struct Group {
+    int tid;  // thread index inside the group
+    int nt;   // threads in the group (multiple of 32)
+    int bar;  // hardware barrier id (1..15; 0 is __syncthreads)
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory");
+    }
+};
+
+// Group-wide sum, result broadcast to every thread of the group.  `red` holds >= nt/32 elements and
+// is private to the group.  Deterministic (shuffle tree per warp, warp partials added in warp order).
+template <typename T>
+__device__ __forceinline__ T group_sum(const Group& g, T v, T* red) {
+    const int lane = g.tid & 31, wid = g.tid >> 5, nw = g.nt >> 5;
+    v = warp_sum(v);
+    g.sync();  // protect `red` from a previous use
+    if (lane == 0) red[wid] = v;
+    g.sync();
+    T tot = (T)0;
+    for (int i = 0; i < nw; ++i) tot += red[i];
+    return tot;
+}
+
+// In-place inclusive scan of a[0..n) (shared memory, double) by one group.  Each thread scans a
+// contiguous chunk, every warp shuffle-scans its 32 chunk totals, warp totals are added in warp
+// order.  `red` holds >= nt/32 doubles.  Deterministic.
+__device__ __forceinline__ void group_inclusive_scan(const Group& g, double* a, int n, double* red) {
+    const int lane = g.tid & 31, wid = g.tid >> 5;
+    const int per = (n + g.nt - 1) / g.nt;
+    const int beg = min(g.tid * per, n), end = min(beg + per, n);
+    double run = 0.0;
+    for (int i = beg; i < end; ++i) {
+        run += a[i];
+        a[i] = run;
+    }
+    double inc = run;                                   // inclusive scan of the chunk totals in the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    g.sync();                                           // protect `red` from a previous use
+    if (lane == 31) red[wid] = inc;
+    g.sync();
+    double off = inc - run;                             // chunks before mine in my warp
+    for (int w = 0; w < wid; ++w) off += red[w];        // warps before mine, in order
+    if (off != 0.0)
+        for (int i = beg; i < end; ++i) a[i] += off;
+    g.sync();
+}
+
 // ---- loads ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
     uint4 r;

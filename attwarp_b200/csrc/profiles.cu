@@ -29,62 +29,68 @@ struct TransformArgs {
 
 // -------------------------------------------------------------------------------------------
 // Shared tail: profiles (shared memory) -> knots -> inverse maps for one image.
+// The CTA is two groups of kProfThreads threads: group 0 inverts the x axis while group 1 inverts
+// the y axis (the two chains of scan -> knots -> search are independent and latency-bound).
 //   prof_x[W], prof_y[H]: raw marginal sums of the biased map (new_method.py:215-216)
-//   knots: scratch of max(W,H)+1 doubles; red: >= blockDim.x doubles
+//   knots: 2 x (max(W,H)+1) doubles; red: 2 x 32 doubles; xchg: 4 doubles
 // -------------------------------------------------------------------------------------------
-__device__ void invert_axis(double* prof, int n, double total, int n_out, double* knots,
+constexpr int kTailRed = 32;       // doubles of reduction scratch per group
+constexpr int kTailXchg = 4;       // totals exchanged between the groups
+
+__device__ void invert_axis(const Group& g, double* prof, int n, double total, int n_out, double* knots,
                             double* red, float* __restrict__ out_map) {
-    block_inclusive_scan(prof, n, red);                       // np.cumsum            :242,248
-    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+    group_inclusive_scan(g, prof, n, red);                    // np.cumsum            :242,248
+    for (int i = g.tid; i <= n; i += g.nt) {
         double k;
         if (i == 0) k = 0.0;
         else if (i == n) k = (double)n_out;                   // forced last knot      :254-255
         else k = dmul_nofma(ddiv_exact(prof[i - 1], total), (double)n_out);  //       :243-245
         knots[i] = k;
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < n_out; j += blockDim.x)     // np.interp + f32 cast :260-265
+    g.sync();
+    for (int j = g.tid; j < n_out; j += g.nt)                 // np.interp + f32 cast :260-265
         out_map[j] = (float)interp_index((double)j, knots, n + 1);
-    __syncthreads();
 }
 
+// Called by all 2 * kProfThreads threads of the CTA.
 __device__ void profiles_to_maps(double* prof_x, double* prof_y, int W, int H, int Wo, int Ho,
-                                 const TransformArgs& ta, double* knots, double* red,
+                                 const TransformArgs& ta, double* knots, double* red, double* xchg,
                                  float* __restrict__ map_x, float* __restrict__ map_y,
                                  int* __restrict__ fallback_flag) {
-    // sum of the biased map (needed by the fallback's np.mean) = sum of raw row sums
-    double part = 0.0;
-    for (int i = threadIdx.x; i < H; i += blockDim.x) part += prof_y[i];
-    const double sum_biased = block_sum(part, red);
+    const int axis = threadIdx.x >= kProfThreads ? 1 : 0;     // group 0: x (columns), group 1: y (rows)
+    const Group g = {(int)threadIdx.x - axis * kProfThreads, kProfThreads, 1 + axis};
+    double* prof = axis ? prof_y : prof_x;
+    const int n = axis ? H : W, n_other = axis ? W : H, n_out = axis ? Ho : Wo;
+    double* my_red = red + axis * kTailRed;
+    double* my_knots = knots + axis * (max(W, H) + 1);
 
-    if (ta.apply_inverse) {                                   // :219-226
-        const double bx = kBaseAttention * (double)H, by = kBaseAttention * (double)W;
-        for (int i = threadIdx.x; i < W; i += blockDim.x)
-            prof_x[i] = transform_inv(prof_x[i] - bx, ta.transform, ta.exp_scale, ta.exp_divisor) + bx;
-        for (int i = threadIdx.x; i < H; i += blockDim.x)
-            prof_y[i] = transform_inv(prof_y[i] - by, ta.transform, ta.exp_scale, ta.exp_divisor) + by;
-        __syncthreads();
+    // sum of the biased map (needed by the fallback's np.mean) = sum of the raw row sums
+    if (axis == 1) {
+        double part = 0.0;
+        for (int i = g.tid; i < H; i += g.nt) part += prof_y[i];
+        const double sum_biased = group_sum(g, part, my_red);
+        if (g.tid == 0) xchg[2] = sum_biased;
     }
-    part = 0.0;
-    for (int i = threadIdx.x; i < W; i += blockDim.x) part += prof_x[i];
-    double total_x = block_sum(part, red);                    // :228
-    part = 0.0;
-    for (int i = threadIdx.x; i < H; i += blockDim.x) part += prof_y[i];
-    double total_y = block_sum(part, red);                    // :229
-
-    const bool fallback = (total_x < kEpsilon) || (total_y < kEpsilon);   // :231
+    if (ta.apply_inverse) {                                   // :219-226
+        const double bias = kBaseAttention * (double)n_other;
+        for (int i = g.tid; i < n; i += g.nt)
+            prof[i] = transform_inv(prof[i] - bias, ta.transform, ta.exp_scale, ta.exp_divisor) + bias;
+        g.sync();
+    }
+    double part = 0.0;
+    for (int i = g.tid; i < n; i += g.nt) part += prof[i];
+    double total = group_sum(g, part, my_red);                // :228-229
+    if (g.tid == 0) xchg[axis] = total;
+    __syncthreads();
+    const bool fallback = (xchg[0] < kEpsilon) || (xchg[1] < kEpsilon);   // :231
     if (fallback) {                                           // :233-239
-        for (int i = threadIdx.x; i < W; i += blockDim.x) prof_x[i] = 1.0;
-        for (int i = threadIdx.x; i < H; i += blockDim.x) prof_y[i] = 1.0;
-        const double mean = sum_biased / ((double)H * (double)W);
-        total_x = fmax((double)W * (mean * (double)H), kEpsilon);
-        total_y = fmax((double)H * (mean * (double)W), kEpsilon);
-        __syncthreads();
+        for (int i = g.tid; i < n; i += g.nt) prof[i] = 1.0;
+        const double mean = xchg[2] / ((double)H * (double)W);
+        total = fmax((double)n * (mean * (double)n_other), kEpsilon);
+        g.sync();
     }
     if (fallback_flag != nullptr && threadIdx.x == 0) *fallback_flag = fallback ? 1 : 0;
-
-    invert_axis(prof_x, W, total_x, Wo, knots, red, map_x);
-    invert_axis(prof_y, H, total_y, Ho, knots, red, map_y);
+    invert_axis(g, prof, n, total, n_out, my_knots, my_red, axis ? map_y : map_x);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -92,7 +98,7 @@ __device__ void profiles_to_maps(double* prof_x, double* prof_y, int W, int H, i
 //   tok[b][gh*gw] given either final (nsplit==1, scale==1) or as stage-1 partials
 //   [b][nsplit][gh*gw] to be summed in split order and scaled (fused stage-1 finalize).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kProfThreads)
+__global__ void __launch_bounds__(2 * kProfThreads)
 maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
                         float* __restrict__ tok_out, int gh, int gw, int H, int W, int Wo, int Ho,
                         TransformArgs ta, float* __restrict__ map_x, float* __restrict__ map_y,
@@ -100,13 +106,14 @@ maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
     extern __shared__ double smem[];
     const int b = blockIdx.x;
     const int G = gh * gw;
-    double* red = smem;                       // kProfThreads
-    double* grid = red + kProfThreads;        // G   transformed + biased token values
+    double* red = smem;                       // 2 * kTailRed
+    double* xchg = red + 2 * kTailRed;        // kTailXchg
+    double* grid = xchg + kTailXchg;          // G   transformed + biased token values
     double* csum = grid + G;                  // gw  column sums over the full-res rows
     double* rsum = csum + gw;                 // gh
     double* prof_x = rsum + gh;               // W
     double* prof_y = prof_x + W;              // H
-    double* knots = prof_y + H;               // max(W,H)+1
+    double* knots = prof_y + H;               // 2 * (max(W,H)+1)
 
     const float* src = tok + (int64_t)b * nsplit * G;
     for (int i = threadIdx.x; i < G; i += blockDim.x) {
@@ -123,28 +130,38 @@ maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
         grid[i] = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;  // :210-212
     }
     __syncthreads();
-    // number of full-res rows (cols) that index-map to grid row i (col c): floor-partition sizes
-    for (int c = threadIdx.x; c < gw; c += blockDim.x) {
-        double s = 0.0;
-        for (int i = 0; i < gh; ++i) {
-            const int y0 = (int)(((int64_t)i * H + gh - 1) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
-            s += (double)(y1 - y0) * grid[i * gw + c];
+    // number of full-res rows (cols) that index-map to grid row i (col c): the index upsample
+    // att[y][x] = tok[(y*gh)/H][(x*gw)/W] gives row i the rows [ceil(i*H/gh), ceil((i+1)*H/gh)).
+    // (sizes fit 32 bits: H, W < 65536 and gh, gw <= 8192)
+    double* cnt_y = knots;                    // gh   (knots are not live yet)
+    double* cnt_x = knots + gh;               // gw
+    for (int i = threadIdx.x; i < gh + gw; i += blockDim.x) {
+        if (i < gh) {
+            cnt_y[i] = (double)(((i + 1) * H + gh - 1) / gh - (i * H + gh - 1) / gh);
+        } else {
+            const int c = i - gh;
+            cnt_x[c] = (double)(((c + 1) * W + gw - 1) / gw - (c * W + gw - 1) / gw);
         }
-        csum[c] = s;
-    }
-    for (int i = threadIdx.x; i < gh; i += blockDim.x) {
-        double s = 0.0;
-        for (int c = 0; c < gw; ++c) {
-            const int x0 = (int)(((int64_t)c * W + gw - 1) / gw), x1 = (int)(((int64_t)(c + 1) * W + gw - 1) / gw);
-            s += (double)(x1 - x0) * grid[i * gw + c];
-        }
-        rsum[i] = s;
     }
     __syncthreads();
-    for (int x = threadIdx.x; x < W; x += blockDim.x) prof_x[x] = csum[(int)(((int64_t)x * gw) / W)];
-    for (int y = threadIdx.x; y < H; y += blockDim.x) prof_y[y] = rsum[(int)(((int64_t)y * gh) / H)];
+    if (threadIdx.x < kProfThreads) {                                       // first group: column sums
+        for (int c = threadIdx.x; c < gw; c += kProfThreads) {
+            double s = 0.0;
+            for (int i = 0; i < gh; ++i) s += cnt_y[i] * grid[i * gw + c];
+            csum[c] = s;
+        }
+    } else {                                                                // second group: row sums
+        for (int i = threadIdx.x - kProfThreads; i < gh; i += kProfThreads) {
+            double s = 0.0;
+            for (int c = 0; c < gw; ++c) s += cnt_x[c] * grid[i * gw + c];
+            rsum[i] = s;
+        }
+    }
     __syncthreads();
-    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, map_x + (int64_t)b * Wo,
+    for (int x = threadIdx.x; x < W; x += blockDim.x) prof_x[x] = csum[(x * gw) / W];
+    for (int y = threadIdx.x; y < H; y += blockDim.x) prof_y[y] = rsum[(y * gh) / H];
+    __syncthreads();
+    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, xchg, map_x + (int64_t)b * Wo,
                      map_y + (int64_t)b * Ho, fallback_flags ? fallback_flags + b : nullptr);
 }
 
@@ -203,17 +220,18 @@ marginals_partial_kernel(const T* __restrict__ att, int H, int W, TransformArgs 
 }
 
 // (P3) finish: sum the partials in fixed order, then the shared tail.
-__global__ void __launch_bounds__(kProfThreads)
+__global__ void __launch_bounds__(2 * kProfThreads)
 maps_from_partials_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
                           int n_row_chunks, int n_col_tiles, int H, int W, int Wo, int Ho,
                           TransformArgs ta, float* __restrict__ map_x, float* __restrict__ map_y,
                           int* __restrict__ fallback_flags) {
     extern __shared__ double smem[];
     const int b = blockIdx.x;
-    double* red = smem;
-    double* prof_x = red + kProfThreads;
+    double* red = smem;                       // 2 * kTailRed
+    double* xchg = red + 2 * kTailRed;        // kTailXchg
+    double* prof_x = xchg + kTailXchg;
     double* prof_y = prof_x + W;
-    double* knots = prof_y + H;
+    double* knots = prof_y + H;               // 2 * (max(W,H)+1)
     const double* cp = colpart + (int64_t)b * n_row_chunks * W;
     const double* rp = rowpart + (int64_t)b * n_col_tiles * H;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
@@ -227,7 +245,7 @@ maps_from_partials_kernel(const double* __restrict__ colpart, const double* __re
         prof_y[y] = s;
     }
     __syncthreads();
-    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, map_x + (int64_t)b * Wo,
+    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, xchg, map_x + (int64_t)b * Wo,
                      map_y + (int64_t)b * Ho, fallback_flags ? fallback_flags + b : nullptr);
 }
 
@@ -295,7 +313,8 @@ maps_from_cdf_kernel(const float* __restrict__ Fx, const float* __restrict__ Fy,
 }
 
 size_t maps_smem_bytes(int extra_doubles, int H, int W) {
-    return sizeof(double) * ((size_t)kProfThreads + extra_doubles + W + H + (size_t)max(W, H) + 1);
+    return sizeof(double) * ((size_t)2 * kTailRed + kTailXchg + extra_doubles + W + H +
+                             2 * ((size_t)max(W, H) + 1));
 }
 
 template <typename K>
@@ -331,7 +350,7 @@ int launch_maps_from_tokens(const float* tok, int nsplit, float scale, float* to
     const size_t smem = maps_smem_bytes(gh * gw + gw + gh, H, W);
     int rc = opt_in_smem(maps_from_tokens_kernel, smem, "maps_from_tokens");
     if (rc != ATTWARP_OK) return rc;
-    maps_from_tokens_kernel<<<B, kProfThreads, smem, st>>>(tok, nsplit, scale, tok_out, gh, gw, H, W,
+    maps_from_tokens_kernel<<<B, 2 * kProfThreads, smem, st>>>(tok, nsplit, scale, tok_out, gh, gw, H, W,
                                                            Wo, Ho, to_args(tp), map_x, map_y,
                                                            fallback_flags);
     return check_launch("maps_from_tokens_kernel");
@@ -375,7 +394,7 @@ int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int
     const size_t smem = maps_smem_bytes(0, H, W);
     rc = opt_in_smem(maps_from_partials_kernel, smem, "maps_from_attention");
     if (rc != ATTWARP_OK) return rc;
-    maps_from_partials_kernel<<<B, kProfThreads, smem, st>>>(colpart, rowpart, nrc, nct, H, W, Wo, Ho,
+    maps_from_partials_kernel<<<B, 2 * kProfThreads, smem, st>>>(colpart, rowpart, nrc, nct, H, W, Wo, Ho,
                                                              ta, map_x, map_y, fallback_flags);
     return check_launch("maps_from_partials_kernel");
 }
