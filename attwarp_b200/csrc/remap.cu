@@ -82,13 +82,25 @@ int launch_direct(const void* src, void* dst, int layout, int B, int C, int H, i
 int launch_remap_u8_tiled(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
                           const float* map_x, const float* map_y, int map_div, cudaStream_t st);
 
-// ATTWARP_REMAP=direct forces the baseline gather kernel (A/B comparisons, debugging).
-static bool force_direct() {
-    static const bool v = [] {
+int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
+                           const float* map_x, const float* map_y, int map_div, cudaStream_t st);
+
+// ATTWARP_REMAP=direct forces the baseline gather kernel, ATTWARP_REMAP=tiled the pass-synchronous
+// tiled kernel (A/B comparisons, debugging); default is the streaming kernel.
+static int remap_impl() {
+    static const int v = [] {
         const char* e = getenv("ATTWARP_REMAP");
-        return e != nullptr && strcmp(e, "direct") == 0;
+        if (e != nullptr && strcmp(e, "direct") == 0) return 0;
+        if (e != nullptr && strcmp(e, "tiled") == 0) return 1;
+        return 2;
     }();
     return v;
+}
+static bool force_direct() { return remap_impl() == 0; }
+static int launch_u8_fast(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
+                          const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
+    if (remap_impl() == 1) return launch_remap_u8_tiled(src, dst, n_img, C, H, W, Ho, Wo, map_x, map_y, map_div, st);
+    return launch_remap_u8_stream(src, dst, n_img, C, H, W, Ho, Wo, map_x, map_y, map_div, st);
 }
 
 int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C, int H, int W,
@@ -98,9 +110,9 @@ int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C
     if (dtype == ATTWARP_U8 && !force_direct() && H >= 2 && W >= 2) {
         // HWC with 1/3/4 interleaved channels, or planar = B*C single-channel images
         if (layout == ATTWARP_LAYOUT_HWC && (C == 1 || C == 3 || C == 4))
-            return launch_remap_u8_tiled(src, dst, B, C, H, W, Ho, Wo, map_x, map_y, 1, st);
+            return launch_u8_fast(src, dst, B, C, H, W, Ho, Wo, map_x, map_y, 1, st);
         if (layout == ATTWARP_LAYOUT_CHW && (int64_t)B * C <= 65535)
-            return launch_remap_u8_tiled(src, dst, B * C, 1, H, W, Ho, Wo, map_x, map_y, C, st);
+            return launch_u8_fast(src, dst, B * C, 1, H, W, Ho, Wo, map_x, map_y, C, st);
     }
     if (dtype == ATTWARP_U8)
         return launch_direct<uint8_t>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);

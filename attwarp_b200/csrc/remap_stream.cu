@@ -1,0 +1,720 @@
+// remap_stream.cu -- stage 5 for uint8 images: persistent, warp-specialised, streaming resample.
+//
+// Same arithmetic as remap_direct_kernel (cv2.remap INTER_LINEAR + BORDER_REPLICATE, see
+// warp_math.h; reference call sites "Attention Guided Warping/new_method.py:268-271",
+// "model/marginalnet_full_dataset/checkpoint_utils.py:195-198").  A gather-resample of 3-byte
+// pixels runs out of issue slots long before it runs out of HBM bandwidth, so the kernel is
+// organised around instructions per output pixel and around never making a warp wait for another:
+//
+//   * work = column strips (<= 352 output columns) of images, cut into tiles of kRows output rows;
+//     the grid is persistent (three CTAs per SM) and every CTA walks a contiguous range of tiles.
+//     Consecutive tiles of one strip form a SEGMENT that is streamed top to bottom in CHUNKS of
+//     <= kRows output rows through a ring of shared-memory source stages and a ring of output tiles;
+//   * the PRODUCER warp plans a chunk -- the contiguous range of source rows its output rows tap,
+//     minus the (at most two) rows whose horizontal blends the consumers still hold in registers
+//     from the previous chunk -- writes the chunk's row table and fetches the rows with
+//     cp.async.bulk (TMA bulk copy, global -> shared): ONE copy for the whole range when the strip
+//     spans full image rows that are multiples of 16 bytes, else one copy per row (the 16-byte
+//     aligned span around the strip's source columns); completion lands on the stage's `full`
+//     mbarrier.  Planning costs ~60 dependent instructions per chunk: the single producer warp
+//     must stay well ahead of eleven consumer warps;
+//   * CONSUMER warps own 32 output columns each, one per lane.  The warp map is separable, so the
+//     horizontal blend of a source row is computed ONCE per (row, output column) -- a funnel-shifted
+//     8-byte window and dp4a with byte-positioned weights -- and kept packed with the previous
+//     row's blend as the two 16-bit halves of one register; each output row is then ONE dp2a
+//     (vertical blend + rounding constant) and a shift per channel.  The packed pair is carried
+//     across chunks, so no source row is fetched or blended twice.  Consumer warps never
+//     synchronise with each other: a warp that finishes a chunk arrives on the chunk's mbarriers
+//     and moves on to the next one;
+//   * the STORE warp waits until every consumer warp has written a chunk's output tile, ships it
+//     with cp.async.bulk (shared -> global; byte stores for ragged row ends) and frees the tile
+//     once it has been read.
+//
+// Maps need not be monotone: a chunk ends before the first output row that taps an earlier
+// source row than its predecessor, so arbitrary maps degrade to one-row chunks (same arithmetic).
+// A strip whose source span does not fit two rows of a stage is gathered straight from global
+// memory by the consumers, so the kernel is total.
+#include <stdlib.h>
+
+#include "bulk_ptx.cuh"
+#include "common.cuh"
+
+namespace aw {
+namespace {
+
+using namespace ptx;
+
+constexpr int kSrcStages = 4;          // source-row stages (chunks whose loads are in flight) per CTA
+constexpr int kOutStages = 3;          // output tiles per CTA
+constexpr int kMaxCols = 352;          // consumer threads (= output columns per strip): 11 + 2 warps x 3 CTAs keep 48 registers
+constexpr int kRoleThreads = 64;       // producer warp + store warp
+
+// Keeps a loop-invariant value in a register (stops the compiler from rematerialising it).
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
+}
+// Shared memory is addressed as byte offsets from the one dynamic array below.
+extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ uint32_t ld32(int off) { return *reinterpret_cast<const uint32_t*>(smem + off); }
+__device__ __forceinline__ uint4 ld128(int off) { return *reinterpret_cast<const uint4*>(smem + off); }
+__device__ __forceinline__ void st32(int off, uint32_t v) { *reinterpret_cast<uint32_t*>(smem + off) = v; }
+__device__ __forceinline__ void st128(int off, uint4 v) { *reinterpret_cast<uint4*>(smem + off) = v; }
+__device__ __forceinline__ void st8(int off, uint32_t v) { smem[off] = (uint8_t)v; }
+
+// ---- per-stage chunk table (byte offsets), written by the producer, read by consumers + store warp
+//   +0   uint4 {n_rows, n_slots | flags << 16, slot_pitch, phase of slot 0 (global address & 15)}
+//              n_rows 0: output row y0 takes the direct path; -1: stop
+//   +16  uint4 {img, x_first, y0, c_lo}
+//   +32  uint4 row[R + 1]:  x = dp2a weight word  wa | (32 - wa) << 8  (upper row, lower row)
+//                           y = byte offset of the row inside the output tile
+//                               (i * out_pitch + (dst address & 15))
+//                           z = slot after which the row is emitted (= slot of its LOWER tap);
+//                               0xffffffff: both taps are the carried pair, emit before slot 0;
+//                               entry n_rows is a sentinel (z = kRowSentinel)
+//   +32 + 16 (R + 1)  uint32 slot_base[2 R]:  slot * slot_pitch + (global address of its first byte & 15)
+constexpr int kTabRows = 32;
+constexpr uint32_t kRowSentinel = 0x7fffffffu;
+template <int R> constexpr int tab_slots() { return kTabRows + 16 * (R + 1); }
+template <int R> constexpr int tab_bytes() { return tab_slots<R>() + 4 * 2 * R; }
+constexpr uint32_t kFlagNewStrip = 1u;
+constexpr int kNoCarry = -(1 << 29);
+
+// base source column and tap weights of one output column (border replicate folded into weights)
+__device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, int& w1) {
+    const int sx = quantise_coord(m);
+    const int ix = sx >> 5, ax = sx & 31;
+    if (ix < 0) { xb = 0; w0 = 32; w1 = 0; }
+    else if (ix >= W - 1) { xb = W - 2; w0 = 0; w1 = 32; }
+    else { xb = ix; w0 = 32 - ax; w1 = ax; }
+}
+
+// Horizontal blend of the C channels of one output column on one staged source row (generic C).
+template <int C>
+__device__ __forceinline__ void hblend_row(int wp, uint32_t sh, const uint32_t* wA, const uint32_t* wB,
+                                           uint32_t* h) {
+    const uint32_t lo = ld32(wp), mid = ld32(wp + 4);
+    const uint32_t A = __funnelshift_r(lo, mid, sh);
+    if (C == 1) {
+        h[0] = __dp4a(A, wA[0], 0u);
+    } else {
+        const uint32_t hi = ld32(wp + 8);
+        const uint32_t Bv = __funnelshift_r(mid, hi, sh);
+        if (C == 3) {
+            h[0] = __dp4a(A, wA[0], 0u);
+            h[1] = __dp4a(Bv, wB[1], __dp4a(A, wA[1], 0u));
+            h[2] = __dp4a(Bv, wB[2], __dp4a(A, wA[2], 0u));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __dp4a(Bv, wB[k], __dp4a(A, wA[k], 0u));
+        }
+    }
+}
+template <int C>
+__device__ __forceinline__ void vblend_store(const uint32_t* PQ, uint32_t wy, int o) {
+    if (C == 4) {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pk |= (__dp2a_lo(PQ[k], wy, 512u) >> 10) << (8 * k);
+        if ((o & 3) == 0) {
+            st32(o, pk);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st8(o + k, pk >> (8 * k));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) st8(o + k, __dp2a_lo(PQ[k], wy, 512u) >> 10);
+    }
+}
+
+// ---- the sweep over one chunk, hand-scheduled in PTX ---------------------------------------------
+// The table-driven loops branch on values loaded from shared memory.  They are uniform over the
+// warp, but the compiler cannot prove it and would wrap every branch in reconvergence bookkeeping;
+// PTX with `bra.uni` and explicit shared-space addresses avoids that.
+//   P*        : packed (previous row blend | this row blend << 16) per channel, carried across chunks
+//   cur/arena : shared-space address of the window (U: word holding its first byte in slot 0;
+//               !U: start of the staged span + this column's window offset)
+//   sh        : U only, 8 * (window byte offset inside its word)
+//   sp        : !U only, shared-space address of slot_base[0]
+//   rp        : shared-space address of row[0];  ocol: of this column inside the output tile
+// Order: rows with z == -1 (no new slot), then per slot: blend, shift into P, emit its rows.
+#define AW_SW_ROWCTL_BEGIN                                      \
+    "setp.ne.u32 q, ez, s;\n"                                   \
+    "@q bra.uni NEXT;\n"                                        \
+    "ROW:\n"
+#define AW_SW_ROWCTL_END(NSLOTS)                                \
+    "add.u32 rp, rp, 16;\n"                                     \
+    "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp];\n"                \
+    "setp.eq.u32 q, ez, s;\n"                                   \
+    "@q bra.uni ROW;\n"                                         \
+    "NEXT:\n"                                                   \
+    "add.s32 s, s, 1;\n"                                        \
+    "setp.lt.s32 p, s, " NSLOTS ";\n"
+// rows whose two taps are the carried pair: emitted before the first slot of the chunk
+#define AW_SW_PRE_BEGIN                                         \
+    "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp];\n"                \
+    "setp.ne.u32 q, ez, 0xffffffff;\n"                          \
+    "@q bra.uni PRE_DONE;\n"                                    \
+    "PRE_ROW:\n"
+#define AW_SW_PRE_END(NSLOTS)                                   \
+    "add.u32 rp, rp, 16;\n"                                     \
+    "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp];\n"                \
+    "setp.eq.u32 q, ez, 0xffffffff;\n"                          \
+    "@q bra.uni PRE_ROW;\n"                                     \
+    "PRE_DONE:\n"                                               \
+    "mov.b32 s, 0;\n"                                           \
+    "setp.lt.s32 p, s, " NSLOTS ";\n"                           \
+    "@!p bra.uni DONE;\n"
+#define AW_SW_WINDOW_U                                          \
+    "ld.shared.b32 lo, [cur];\n"                                \
+    "ld.shared.b32 mid, [cur+4];\n"
+#define AW_SW_WINDOW_T(ARENA)                                   \
+    "ld.shared.b32 t, [sp];\n"                                  \
+    "add.u32 t, t, " ARENA ";\n"                                \
+    "and.b32 cur, t, 0xfffffffc;\n"                             \
+    "shl.b32 sh, t, 3;\n"                                       \
+    "add.u32 sp, sp, 4;\n"                                      \
+    "ld.shared.b32 lo, [cur];\n"                                \
+    "ld.shared.b32 mid, [cur+4];\n"
+#define AW_SW_EMIT3                                             \
+    "dp2a.lo.u32.u32 r0, %0, ex, %14;\n"                        \
+    "dp2a.lo.u32.u32 r1, %1, ex, %14;\n"                        \
+    "dp2a.lo.u32.u32 r2, %2, ex, %14;\n"                        \
+    "add.u32 o, ey, %8;\n"                                      \
+    "shr.u32 r0, r0, 10;\n shr.u32 r1, r1, 10;\n shr.u32 r2, r2, 10;\n" \
+    "st.shared.u8 [o], r0;\n st.shared.u8 [o+1], r1;\n st.shared.u8 [o+2], r2;\n"
+#define AW_SW_BLEND3(SH)                                        \
+    "ld.shared.b32 hi, [cur+8];\n"                              \
+    "shf.r.wrap.b32 A, lo, mid, " SH ";\n"                      \
+    "shf.r.wrap.b32 B, mid, hi, " SH ";\n"                      \
+    "dp4a.u32.u32 h0, A, %9, 0;\n"                              \
+    "dp4a.u32.u32 t, A, %10, 0;\n"                              \
+    "dp4a.u32.u32 h1, B, %12, t;\n"                             \
+    "dp4a.u32.u32 t, A, %11, 0;\n"                              \
+    "dp4a.u32.u32 h2, B, %13, t;\n"                             \
+    "prmt.b32 %0, %0, h0, 0x5432;\n"                            \
+    "prmt.b32 %1, %1, h1, 0x5432;\n"                            \
+    "prmt.b32 %2, %2, h2, 0x5432;\n"
+#define AW_SW_EMIT1                                             \
+    "dp2a.lo.u32.u32 r0, %0, ex, %8;\n"                         \
+    "add.u32 o, ey, %6;\n"                                      \
+    "shr.u32 r0, r0, 10;\n"                                     \
+    "st.shared.u8 [o], r0;\n"
+#define AW_SW_BLEND1(SH)                                        \
+    "shf.r.wrap.b32 A, lo, mid, " SH ";\n"                      \
+    "dp4a.u32.u32 h0, A, %7, 0;\n"                              \
+    "prmt.b32 %0, %0, h0, 0x5432;\n"
+
+template <bool U>
+__device__ __forceinline__ void sweep_c3(uint32_t* P, int n_slots, uint32_t cur_or_arena, uint32_t sh_or_sp,
+                                         uint32_t pitch, uint32_t rp, uint32_t ocol, const uint32_t* wA,
+                                         const uint32_t* wB, uint32_t rnd) {
+    if (U) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            ".reg .b32 s, lo, mid, hi, A, B, h0, h1, h2, t, r0, r1, r2, o, cur, rp, ex, ey, ez, ew;\n"
+            "mov.b32 cur, %4;\n mov.b32 rp, %7;\n" AW_SW_PRE_BEGIN AW_SW_EMIT3 AW_SW_PRE_END("%3")
+            "SLOT:\n" AW_SW_WINDOW_U AW_SW_BLEND3("%5")
+            "add.u32 cur, cur, %6;\n" AW_SW_ROWCTL_BEGIN AW_SW_EMIT3 AW_SW_ROWCTL_END("%3")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1]), "+r"(P[2])
+            : "r"(n_slots), "r"(cur_or_arena), "r"(sh_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(wA[0]),
+              "r"(wA[1]), "r"(wA[2]), "r"(wB[1]), "r"(wB[2]), "r"(rnd)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            ".reg .b32 s, lo, mid, hi, A, B, h0, h1, h2, t, r0, r1, r2, o, cur, sh, sp, rp, ex, ey, ez, ew;\n"
+            "mov.b32 sp, %5;\n mov.b32 rp, %7;\n" AW_SW_PRE_BEGIN AW_SW_EMIT3 AW_SW_PRE_END("%3")
+            "SLOT:\n" AW_SW_WINDOW_T("%4") AW_SW_BLEND3("sh") AW_SW_ROWCTL_BEGIN AW_SW_EMIT3 AW_SW_ROWCTL_END("%3")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1]), "+r"(P[2])
+            : "r"(n_slots), "r"(cur_or_arena), "r"(sh_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(wA[0]),
+              "r"(wA[1]), "r"(wA[2]), "r"(wB[1]), "r"(wB[2]), "r"(rnd)
+            : "memory");
+    }
+}
+
+template <bool U>
+__device__ __forceinline__ void sweep_c1(uint32_t* P, int n_slots, uint32_t cur_or_arena, uint32_t sh_or_sp,
+                                         uint32_t pitch, uint32_t rp, uint32_t ocol, const uint32_t* wA,
+                                         uint32_t rnd) {
+    if (U) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            ".reg .b32 s, lo, mid, A, h0, t, r0, o, cur, rp, ex, ey, ez, ew;\n"
+            "mov.b32 cur, %2;\n mov.b32 rp, %5;\n" AW_SW_PRE_BEGIN AW_SW_EMIT1 AW_SW_PRE_END("%1")
+            "SLOT:\n" AW_SW_WINDOW_U AW_SW_BLEND1("%3")
+            "add.u32 cur, cur, %4;\n" AW_SW_ROWCTL_BEGIN AW_SW_EMIT1 AW_SW_ROWCTL_END("%1")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0])
+            : "r"(n_slots), "r"(cur_or_arena), "r"(sh_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(wA[0]), "r"(rnd)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            ".reg .b32 s, lo, mid, A, h0, t, r0, o, cur, sh, sp, rp, ex, ey, ez, ew;\n"
+            "mov.b32 sp, %3;\n mov.b32 rp, %5;\n" AW_SW_PRE_BEGIN AW_SW_EMIT1 AW_SW_PRE_END("%1")
+            "SLOT:\n" AW_SW_WINDOW_T("%2") AW_SW_BLEND1("sh") AW_SW_ROWCTL_BEGIN AW_SW_EMIT1 AW_SW_ROWCTL_END("%1")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0])
+            : "r"(n_slots), "r"(cur_or_arena), "r"(sh_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(wA[0]), "r"(rnd)
+            : "memory");
+    }
+}
+
+struct StreamArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    const float* map_x;
+    const float* map_y;
+    int H, W, Ho, Wo;
+    int map_div;             // CHW planes share their image's maps
+    int n_strips, n_rowtiles, total_tiles;
+    int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
+    int out_pitch;           // bytes per row of an output tile
+    int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
+};
+
+// Requires H >= 2 and W >= 2 (the launcher routes degenerate images to the direct kernel).
+// blockDim.x = Wt consumer threads + 32 producer threads + 32 store threads.
+// U ("uniform phase"): W*C is a multiple of 16, so every staged row starts at the same 16-byte
+// phase and slot k sits at k * slot_pitch + phase -- the sweep advances by one add per slot.
+//
+// Shared memory: [kSrcStages source arenas][kOutStages output tiles][kSrcStages chunk tables]
+//                [kOutStages tile headers][mbarriers].
+// Chunk c lives in source stage c % kSrcStages and output tile c % kOutStages.  mbarriers:
+//   full[s]  producer -> consumers   table written, source rows landed (transaction bytes)
+//   sfree[s] consumers -> producer   every consumer warp is done with the stage's rows and table
+//   odone[o] consumers -> store warp every consumer warp has written its columns of the tile
+//   ofree[o] store warp -> consumers the tile has been read out of shared memory
+// The two rings are decoupled so that the loads of chunk c + kSrcStages start as soon as the
+// consumers leave chunk c, without waiting for its tile to be shipped.
+template <int C, int R, bool U>
+__global__ void __launch_bounds__(kMaxCols + kRoleThreads, 3)
+remap_u8_stream_kernel(const StreamArgs a) {
+    const int Wt = (int)blockDim.x - kRoleThreads;
+    const int tid = threadIdx.x;
+    const int out_bytes = R * a.out_pitch;
+    const int out_off0 = kSrcStages * a.stage_bytes;
+    const int tab_off0 = out_off0 + kOutStages * out_bytes;
+    const int ohdr_off0 = tab_off0 + kSrcStages * tab_bytes<R>();
+    const int bar_off0 = ohdr_off0 + kOutStages * 16;
+    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t full_s = smem_s + (uint32_t)bar_off0;
+    const uint32_t sfree_s = full_s + 8u * kSrcStages;
+    const uint32_t odone_s = sfree_s + 8u * kSrcStages;
+    const uint32_t ofree_s = odone_s + 8u * kOutStages;
+    const int H = a.H, W = a.W, Ho = a.Ho, Wo = a.Wo;
+    const int n_cons_warps = Wt >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < kSrcStages; ++s) {
+            mbar_init(full_s + 8u * s, 1);
+            mbar_init(sfree_s + 8u * s, n_cons_warps);
+        }
+        for (int s = 0; s < kOutStages; ++s) {
+            mbar_init(odone_s + 8u * s, n_cons_warps);
+            mbar_init(ofree_s + 8u * s, 1);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    // contiguous, balanced range of tiles for this CTA
+    const int t0 = (int)(((int64_t)a.total_tiles * blockIdx.x) / gridDim.x);
+    const int t1 = (int)(((int64_t)a.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+    // warp-uniform role split (the shuffle tells the compiler the branch does not diverge)
+    const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+
+    // Role split nested under ONE warp-uniform branch: with two sibling branches ptxas stops treating
+    // the consumers' table-driven control flow as uniform and wraps every sweep branch in BSSY/BSYNC.
+    if (warp_idx >= n_cons_warps) {
+        if (warp_idx == n_cons_warps) {
+            // =========================== producer warp =========================================
+            const unsigned lt_mask = (1u << lane) - 1u;
+            int st = 0;
+            uint32_t ph = 0;                 // parity of the stage's current use
+            int t = t0;
+            while (t < t1) {
+                // ---- segment: the tiles [t, t_end) of one (image, strip) ----------------------
+                const int rt = t % a.n_rowtiles;
+                const int q = t / a.n_rowtiles;
+                const int strip = q % a.n_strips, img = q / a.n_strips;
+                const int t_end = min(t1, (q + 1) * a.n_rowtiles);
+                const int y_end = min(Ho, (rt + (t_end - t)) * R);
+                const int mrow = img / a.map_div;
+                const int x_first = strip * Wt;
+                const int ncols = min(Wt, Wo - x_first);
+                const uint8_t* simg = a.src + (int64_t)img * H * W * C;
+                const uintptr_t dimg = reinterpret_cast<uintptr_t>(a.dst) + (uintptr_t)((int64_t)img * Ho * Wo * C);
+                const float* my = a.map_y + (int64_t)mrow * Ho;
+                // source column span of the strip
+                int c_lo, row_bytes, slot_pitch, max_slots;
+                {
+                    int lo = 0x7fffffff, hi = -1;
+                    const float* mx = a.map_x + (int64_t)mrow * Wo + x_first;
+                    for (int x = lane; x < ncols; x += 32) {
+                        int xb, w0, w1;
+                        column_taps(__ldg(mx + x), W, xb, w0, w1);
+                        lo = min(lo, xb);
+                        hi = max(hi, xb);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                    }
+                    c_lo = lo;
+                    const int c_hi = min(hi + 1, W - 1);
+                    row_bytes = (c_hi - c_lo + 1) * C;
+                    slot_pitch = ((row_bytes + 15 + 15) & ~15) + 16;   // alignment head + window over-read
+                    max_slots = min(a.stage_bytes / slot_pitch, 2 * R);
+                }
+                const uint8_t* scol = simg + (int64_t)c_lo * C;
+                const int64_t row_pitch = (int64_t)W * C;
+                // phase of the staged rows (U: identical for every row of every image)
+                const int phase = (int)(reinterpret_cast<uintptr_t>(scol) & 15);
+                // Full-width strip of an image whose rows are multiples of 16 bytes: consecutive source
+                // rows are contiguous in global memory, so a whole chunk is ONE bulk copy (slot pitch =
+                // row pitch).  Otherwise one copy per source row, issued by the lane that owns the slot.
+                const bool one_copy = U && row_bytes == W * C;
+                if (one_copy) {
+                    slot_pitch = W * C;
+                    max_slots = min((a.stage_bytes - 32) / slot_pitch, 2 * R);
+                }
+                uint32_t strip_flag = kFlagNewStrip;
+                int carry_row = kNoCarry;    // source row whose blend sits in the upper half of P
+                int y_cur = rt * R;
+                // map_y is read through a register window of 2 x 32 rows (lane i holds rows y_win + i
+                // and y_win + 32 + i) refilled 32 rows ahead of use: a global-load latency per chunk
+                // on the planning path would cap the whole CTA at one chunk per microsecond.
+                int y_win = y_cur;
+                int sy_cur = quantise_coord(__ldg(my + min(y_win + lane, Ho - 1)));
+                int sy_nxt = quantise_coord(__ldg(my + min(y_win + 32 + lane, Ho - 1)));
+                while (y_cur < y_end) {
+                    const int tab = tab_off0 + st * tab_bytes<R>();
+                    const uint32_t stage_s = smem_s + (uint32_t)(st * a.stage_bytes);
+                    if (y_cur - y_win >= 32) {
+                        y_win += 32;
+                        sy_cur = sy_nxt;
+                        sy_nxt = quantise_coord(__ldg(my + min(y_win + 32 + lane, Ho - 1)));
+                    }
+                    // ---- plan: lane i <-> output row y_cur + i --------------------------------
+                    const int y = y_cur + lane;
+                    const bool live = y < y_end && lane < R;
+                    const int wsel = y - y_win;                       // 0 .. 31 + R - 1
+                    const int sy_a = __shfl_sync(0xffffffffu, sy_cur, wsel & 31);
+                    const int sy_b = __shfl_sync(0xffffffffu, sy_nxt, wsel & 31);
+                    int ra = 0x3fffffff, wa = 32;       // upper source row (lower = ra + 1), its weight
+                    if (live) {
+                        const int sy = wsel < 32 ? sy_a : sy_b;
+                        const int iy = sy >> 5, ay = sy & 31;
+                        if (iy < 0) { ra = 0; wa = 32; }
+                        else if (iy >= H - 1) { ra = H - 2; wa = 0; }
+                        else { ra = iy; wa = 32 - ay; }
+                    }
+                    // The chunk stages the CONTIGUOUS source rows r_lo .. ra(last) + 1 and takes output
+                    // rows while they run in non-decreasing source order and the range fits the stage.
+                    // When its first row starts inside the pair (carry_row - 1, carry_row) whose blends
+                    // the consumers still hold, staging continues after that pair.
+                    const int prev_ra = __shfl_up_sync(0xffffffffu, ra, 1);
+                    const int r0 = __shfl_sync(0xffffffffu, ra, 0);
+                    const int r_lo = (r0 == carry_row - 1 || r0 == carry_row) ? carry_row + 1 : r0;
+                    const int need = ra + 2 - r_lo;                  // slots up to and including this row's taps
+                    const unsigned bad = __ballot_sync(0xffffffffu, !live || (lane > 0 && ra < prev_ra) || need > max_slots);
+                    const int n_rows = max_slots >= 2 ? (bad ? (__ffs(bad) - 1) : 32) : 0;
+                    const int ra_last = __shfl_sync(0xffffffffu, ra, max(n_rows - 1, 0));
+                    const int n_slots = n_rows > 0 ? ra_last + 2 - r_lo : 0;
+                    // lane j stages source row r_lo + j into slot j
+                    const uint8_t* p = scol + (int64_t)(r_lo + lane) * row_pitch;
+                    const int off = (int)(reinterpret_cast<uintptr_t>(p) & 15);
+                    const uint32_t bytes = lane < n_slots ? (uint32_t)((off + row_bytes + 15) & ~15) : 0u;
+                    const uint32_t tx = one_copy ? (uint32_t)((phase + n_slots * slot_pitch + 15) & ~15)
+                                                 : __reduce_add_sync(0xffffffffu, bytes);
+
+                    mbar_wait(sfree_s + 8u * st, ph ^ 1u);             // stage free again
+                    if (lane < n_rows) {
+                        const uintptr_t gd = dimg + (uintptr_t)(((int64_t)y * Wo + x_first) * C);
+                        st128(tab + kTabRows + 16 * lane,
+                              make_uint4((uint32_t)wa | ((uint32_t)(32 - wa) << 8),
+                                         (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 15),
+                                         (uint32_t)(ra + 1 - r_lo), 0u));
+                    } else if (lane == n_rows) {
+                        st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, kRowSentinel, 0u));
+                    }
+                    if (!U && lane < n_slots) st32(tab + tab_slots<R>() + 4 * lane, (uint32_t)(lane * slot_pitch + off));
+                    if (lane == 0) {
+                        st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (strip_flag << 16),
+                                              (uint32_t)slot_pitch, (uint32_t)phase));
+                        st128(tab + 16, make_uint4((uint32_t)img, (uint32_t)x_first, (uint32_t)y_cur, (uint32_t)c_lo));
+                    }
+                    strip_flag = 0u;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (n_slots > 0) mbar_arrive_expect_tx(full_s + 8u * st, tx);
+                        else mbar_arrive(full_s + 8u * st);
+                    }
+                    __syncwarp();
+                    if (one_copy) {
+                        if (lane == 0 && n_slots > 0) bulk_g2s(stage_s, p - off, tx, full_s + 8u * st);
+                    } else if (lane < n_slots) {
+                        bulk_g2s(stage_s + (uint32_t)(lane * slot_pitch), p - off, bytes, full_s + 8u * st);
+                    }
+                    // the pair the consumers hold after this chunk: rows (carry_row - 1, carry_row)
+                    carry_row = n_rows > 0 ? ra_last + 1 : kNoCarry;
+                    y_cur += max(n_rows, 1);
+                    if (++st == kSrcStages) { st = 0; ph ^= 1u; }
+                }
+                t = t_end;
+            }
+            // terminator
+            mbar_wait(sfree_s + 8u * st, ph ^ 1u);
+            if (lane == 0) {
+                st128(tab_off0 + st * tab_bytes<R>(), make_uint4(0xffffffffu, 0u, 0u, 0u));
+                mbar_arrive(full_s + 8u * st);
+            }
+        } else {
+            // =============================== store warp ======================================
+            int ot = 0;
+            uint32_t ph = 0;
+            const bool rows_aligned = ((Wo * C) & 15) == 0;
+            for (;;) {
+                mbar_wait(odone_s + 8u * ot, ph);                      // every consumer warp is through
+                const uint4 hd = ld128(ohdr_off0 + 16 * ot);           // {n_rows, img, x_first, y0}
+                const int n_rows = (int)hd.x;
+                if (n_rows < 0) break;
+                if (n_rows > 0 && !(a.dbg & 2)) {
+                    // ---- ship the rows: bulk store for the 16-byte aligned interior, bytes for the ends
+                    const int img = (int)hd.y, x_first = (int)hd.z, y0 = (int)hd.w;
+                    const int len = min(Wt, Wo - x_first) * C;
+                    const int obuf = out_off0 + ot * out_bytes;
+                    uint8_t* g0 = a.dst + ((int64_t)img * Ho * Wo + (int64_t)y0 * Wo + x_first) * C;
+                    const bool ragged = !rows_aligned || ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len) & 15) != 0;
+                    if (lane < n_rows) {
+                        uint8_t* g = g0 + (int64_t)lane * Wo * C;
+                        const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+                        const int head = (16 - off) & 15;
+                        const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
+                        if (body > 0)
+                            bulk_s2g(g + head, smem_s + (uint32_t)(obuf + lane * a.out_pitch + off + head), (uint32_t)body);
+                    }
+                    bulk_commit();
+                    if (ragged) {
+                        // <= 15 head bytes and <= 15 tail bytes per row, one lane per byte
+                        for (int i = 0; i < n_rows; ++i) {
+                            uint8_t* g = g0 + (int64_t)i * Wo * C;
+                            const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+                            const int head = min((16 - off) & 15, len);
+                            const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
+                            const int s = obuf + i * a.out_pitch + off;
+                            if (lane < 16) {
+                                if (lane < head) g[lane] = smem[s + lane];
+                            } else {
+                                const int qq = head + body + (lane - 16);
+                                if (qq < len) g[qq] = smem[s + qq];
+                            }
+                        }
+                    }
+                    bulk_wait_read0();                                 // the tile has left shared memory
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ofree_s + 8u * ot);        // tile free for the consumers
+                if (++ot == kOutStages) { ot = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // =============================== consumer warps ==============================================
+    const int xl = tid;
+    int wo = 0;                       // byte offset of this column's window inside a staged row span
+    bool xvalid = false;
+    uint32_t wA[C], wB[C], P[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) wA[k] = wB[k] = P[k] = 0u;
+    const int out_col = xl * C;
+    const uint32_t rnd = pin(512u);
+
+    for (int it = 0;; ++it) {
+        const int st = it % kSrcStages, ot = it % kOutStages;
+        const int tab = tab_off0 + st * tab_bytes<R>();
+        mbar_wait(full_s + 8u * st, (uint32_t)(it / kSrcStages) & 1u);
+        const uint4 h0 = ld128(tab);
+        const int n_rows = (int)h0.x;
+        mbar_wait(ofree_s + 8u * ot, ((uint32_t)(it / kOutStages) & 1u) ^ 1u);   // tile shipped and free
+        if (n_rows < 0) {                                                        // pass the stop on
+            if (tid == 0) st128(ohdr_off0 + 16 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(odone_s + 8u * ot);
+            break;
+        }
+        if (h0.y & (kFlagNewStrip << 16)) {                  // new strip: per-column taps and weights
+            const uint4 h1 = ld128(tab + 16);
+            const int img = (int)h1.x, x_first = (int)h1.y;
+            const int mrow = img / a.map_div;
+            xvalid = xl < min(Wt, Wo - x_first);
+            int w0 = 32, w1 = 0, xb = (int)h1.w;
+            if (xvalid) column_taps(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl), W, xb, w0, w1);
+            wo = (xb - (int)h1.w) * C;
+            // dp4a weight words: tap0 of channel k at byte k of the 8-byte window, tap1 at byte k+C
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                wA[k] = (uint32_t)w0 << (8 * k);
+                wB[k] = 0u;
+                if (k + C < 4) wA[k] |= (uint32_t)w1 << (8 * (k + C));
+                else wB[k] = (uint32_t)w1 << (8 * (k + C - 4));
+            }
+        }
+        if (tid == 0) {                                      // what the store warp needs to ship the tile
+            const uint4 h1 = ld128(tab + 16);
+            st128(ohdr_off0 + 16 * ot, make_uint4(h0.x, h1.x, h1.y, h1.z));
+        }
+        if (n_rows == 0) {
+            // ---- direct path for one output row whose source span does not fit a stage ----------
+            if (xvalid) {
+                const uint4 h1 = ld128(tab + 16);
+                const int img = (int)h1.x, x_first = (int)h1.y, y0 = (int)h1.z;
+                const int mrow = img / a.map_div;
+                const uint8_t* simg = a.src + (int64_t)img * H * W * C;
+                uint8_t* dimg = a.dst + (int64_t)img * Ho * Wo * C;
+                const int sy = quantise_coord(__ldg(a.map_y + (int64_t)mrow * Ho + y0));
+                const int ay = sy & 31;
+                const int ya = clampi(sy >> 5, 0, H - 1), yb = clampi((sy >> 5) + 1, 0, H - 1);
+                const int sx = quantise_coord(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl));
+                const int ax = sx & 31;
+                const int x0 = clampi(sx >> 5, 0, W - 1), x1 = clampi((sx >> 5) + 1, 0, W - 1);
+                uint8_t* o = dimg + ((int64_t)y0 * Wo + x_first + xl) * C;
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                    o[k] = bilinear_u8(__ldg(simg + ((int64_t)ya * W + x0) * C + k),
+                                       __ldg(simg + ((int64_t)ya * W + x1) * C + k),
+                                       __ldg(simg + ((int64_t)yb * W + x0) * C + k),
+                                       __ldg(simg + ((int64_t)yb * W + x1) * C + k), ax, ay);
+            }
+        } else if (xvalid && !(a.dbg & 1)) {
+            const int n_slots = (int)(h0.y & 0xffffu);
+            const int arena = st * a.stage_bytes + wo;
+            const int ocol = out_off0 + ot * out_bytes + out_col;
+            const uint32_t ocol_s = smem_s + (uint32_t)ocol;
+            const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
+            const int slot_tab = tab + tab_slots<R>();
+            const int win0 = arena + (U ? (int)h0.w : 0);
+            if (C == 3) {
+                if (U) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
+                else sweep_c3<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, wB, rnd);
+            } else if (C == 1) {
+                if (U) sweep_c1<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, rnd);
+                else sweep_c1<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, rnd);
+            } else {
+                int rp = tab + kTabRows;
+                uint4 re = ld128(rp);
+                for (int s = -1; s < n_slots; ++s) {
+                    if (s >= 0) {
+                        uint32_t h[C];
+                        const int win = U ? win0 + s * (int)h0.z : arena + (int)ld32(slot_tab + 4 * s);
+                        hblend_row<C>(win & ~3, (uint32_t)win << 3, wA, wB, h);
+#pragma unroll
+                        for (int k = 0; k < C; ++k) P[k] = __byte_perm(P[k], h[k], 0x5432);
+                    }
+                    while (re.z == (uint32_t)s) {
+                        vblend_store<C>(P, re.x, ocol + (int)re.y);
+                        rp += 16;
+                        re = ld128(rp);
+                    }
+                }
+            }
+        }
+        // publish this warp's part of the tile to the async proxy, then count the warp in
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(sfree_s + 8u * st);
+            mbar_arrive(odone_s + 8u * ot);
+        }
+    }
+}
+
+template <int C, int R>
+int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int Ho, int Wo,
+                  const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
+    // one consumer thread per output column; strips as wide as possible up to kMaxCols
+    const int n_strips = (Wo + kMaxCols - 1) / kMaxCols;
+    int Wt = ((Wo + n_strips - 1) / n_strips + 31) & ~31;
+    if (Wt < 32) Wt = 32;
+    StreamArgs a;
+    a.src = src; a.dst = dst; a.map_x = map_x; a.map_y = map_y;
+    a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.map_div = map_div;
+    a.n_strips = (Wo + Wt - 1) / Wt;
+    a.n_rowtiles = (Ho + R - 1) / R;
+    const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
+    if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
+    a.total_tiles = (int)total;
+    {
+        const char* e = getenv("ATTWARP_REMAP_DBG");
+        a.dbg = e ? atoi(e) : 0;
+    }
+    const int cols_t = Wo < Wt ? Wo : Wt;                    // widest strip actually processed
+    a.out_pitch = (cols_t * C + 15 + 15) & ~15;
+    // an arena holds R + 2 source rows at unit scale (first chunk of a segment: R + 1)
+    const int unit_pitch = (((cols_t + 1) * C + 30) & ~15) + 16;
+    a.stage_bytes = ((R + 2) * unit_pitch + 127) & ~127;
+    const size_t smem_bytes = (size_t)kSrcStages * (a.stage_bytes + tab_bytes<R>()) +
+                              (size_t)kOutStages * ((size_t)R * a.out_pitch + 16) +
+                              2 * (kSrcStages + kOutStages) * sizeof(uint64_t);
+    // uniform phase: every source row of every image starts at the same 16-byte phase
+    const bool uniform = ((W * C) & 15) == 0 && (((int64_t)H * W * C) & 15) == 0;
+    auto kern = uniform ? remap_u8_stream_kernel<C, R, true> : remap_u8_stream_kernel<C, R, false>;
+    const int threads = Wt + kRoleThreads;
+    // the opt-in and the occupancy query cost microseconds of host time: once per configuration
+    struct Cfg { size_t smem; int threads, dev, occ; };
+    static thread_local Cfg cache[2] = {{0, 0, -1, 0}, {0, 0, -1, 0}};
+    Cfg& c = cache[uniform ? 1 : 0];
+    int dev = 0;
+    AW_CUDA(cudaGetDevice(&dev));
+    if (c.smem != smem_bytes || c.threads != threads || c.dev != dev) {
+        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int o = 0;
+        AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
+        c = Cfg{smem_bytes, threads, dev, o};
+    }
+    const int occ = c.occ;
+    if (occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
+    const int64_t cap = (int64_t)sm_count() * occ;
+    const int grid = (int)(total < cap ? total : cap);
+    kern<<<grid, threads, smem_bytes, st>>>(a);
+    return check_launch("remap_u8_stream_kernel");
+}
+
+}  // namespace
+
+// uint8 images with H, W >= 2: HWC with C in {1,3,4} or planar (n_img = B*C single-channel planes,
+// map_div = C).
+int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
+                           const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    switch (C) {
+        case 1: return launch_stream<1, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 3: return launch_stream<3, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 4: return launch_stream<4, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        default: return fail(ATTWARP_ERR_UNSUPPORTED, "remap supports C in {1,3,4} (got %d)", C);
+    }
+}
+
+}  // namespace aw
