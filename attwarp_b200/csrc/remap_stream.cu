@@ -6,7 +6,7 @@
 // pixels runs out of issue slots long before it runs out of HBM bandwidth, so the kernel is
 // organised around instructions per output pixel and around never making a warp wait for another:
 //
-//   * work = column strips (<= 352 output columns) of images, cut into tiles of kRows output rows;
+//   * work = column strips (<= 384 output columns) of images, cut into tiles of kRows output rows;
 //     the grid is persistent (three CTAs per SM) and every CTA walks a contiguous range of tiles.
 //     Consecutive tiles of one strip form a SEGMENT that is streamed top to bottom in CHUNKS of
 //     <= kRows output rows through a ring of shared-memory source stages and a ring of output tiles;
@@ -46,14 +46,11 @@ using namespace ptx;
 
 constexpr int kSrcStages = 4;          // source-row stages (chunks whose loads are in flight) per CTA
 constexpr int kOutStages = 3;          // output tiles per CTA
-constexpr int kMaxCols = 352;          // consumer threads (= output columns per strip): 11 + 2 warps x 3 CTAs keep 48 registers
+// output columns per strip: 352 at one column per thread (11 + 2 warps x 3 CTAs keep 48 registers),
+// 384 at two columns per thread (6 + 2 warps)
+constexpr int max_cols(int cpt) { return cpt == 2 ? 384 : 352; }
 constexpr int kRoleThreads = 64;       // producer warp + store warp
 
-// Keeps a loop-invariant value in a register (stops the compiler from rematerialising it).
-__device__ __forceinline__ uint32_t pin(uint32_t v) {
-    asm volatile("mov.b32 %0, %0;" : "+r"(v));
-    return v;
-}
 // Shared memory is addressed as byte offsets from the one dynamic array below.
 extern __shared__ __align__(128) uint8_t smem[];
 __device__ __forceinline__ uint32_t ld32(int off) { return *reinterpret_cast<const uint32_t*>(smem + off); }
@@ -276,6 +273,103 @@ __device__ __forceinline__ void sweep_c1(uint32_t* P, int n_slots, uint32_t cur_
     }
 }
 
+// Two output columns per thread (C = 3), half a strip apart so that a warp's accesses to shared
+// memory keep the conflict-free 3-byte lane stride: the table loads and the loop control (a third of
+// the one-column sweep) are shared by both columns and each thread carries two independent chains.
+//   bdelta : byte distance of column b from column a inside an output row;  bvalid: column b exists
+//   ca/cb : window addresses of column a / b (as cur/arena above);  sha/shb: their shift amounts (U)
+#define AW_SW2_BLEND(SHA, SHB)                                  \
+    "ld.shared.b32 loa, [ca];\n"                                \
+    "ld.shared.b32 mida, [ca+4];\n"                             \
+    "ld.shared.b32 hia, [ca+8];\n"                              \
+    "ld.shared.b32 lob, [cb];\n"                                \
+    "ld.shared.b32 midb, [cb+4];\n"                             \
+    "ld.shared.b32 hib, [cb+8];\n"                              \
+    "shf.r.wrap.b32 Aa, loa, mida, " SHA ";\n"                  \
+    "shf.r.wrap.b32 Ba, mida, hia, " SHA ";\n"                  \
+    "shf.r.wrap.b32 Ab, lob, midb, " SHB ";\n"                  \
+    "shf.r.wrap.b32 Bb, midb, hib, " SHB ";\n"                  \
+    "dp4a.u32.u32 h0, Aa, %14, 0;\n"                            \
+    "dp4a.u32.u32 t, Aa, %15, 0;\n"                             \
+    "dp4a.u32.u32 h1, Ba, %17, t;\n"                            \
+    "dp4a.u32.u32 t, Aa, %16, 0;\n"                             \
+    "dp4a.u32.u32 h2, Ba, %18, t;\n"                            \
+    "dp4a.u32.u32 h3, Ab, %19, 0;\n"                            \
+    "dp4a.u32.u32 t, Ab, %20, 0;\n"                             \
+    "dp4a.u32.u32 h4, Bb, %22, t;\n"                            \
+    "dp4a.u32.u32 t, Ab, %21, 0;\n"                             \
+    "dp4a.u32.u32 h5, Bb, %23, t;\n"                            \
+    "prmt.b32 %0, %0, h0, 0x5432;\n"                            \
+    "prmt.b32 %1, %1, h1, 0x5432;\n"                            \
+    "prmt.b32 %2, %2, h2, 0x5432;\n"                            \
+    "prmt.b32 %3, %3, h3, 0x5432;\n"                            \
+    "prmt.b32 %4, %4, h4, 0x5432;\n"                            \
+    "prmt.b32 %5, %5, h5, 0x5432;\n"
+#define AW_SW2_EMIT                                             \
+    "dp2a.lo.u32.u32 r0, %0, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r1, %1, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r2, %2, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r3, %3, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r4, %4, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r5, %5, ex, %13;\n"                        \
+    "add.u32 o, ey, %12;\n"                                     \
+    "add.u32 o2, o, %25;\n"                                     \
+    "shr.u32 r0, r0, 10;\n shr.u32 r1, r1, 10;\n shr.u32 r2, r2, 10;\n" \
+    "shr.u32 r3, r3, 10;\n shr.u32 r4, r4, 10;\n shr.u32 r5, r5, 10;\n" \
+    "st.shared.u8 [o], r0;\n st.shared.u8 [o+1], r1;\n st.shared.u8 [o+2], r2;\n" \
+    "@pb st.shared.u8 [o2], r3;\n @pb st.shared.u8 [o2+1], r4;\n @pb st.shared.u8 [o2+2], r5;\n"
+
+template <bool U>
+__device__ __forceinline__ void sweep_c3x2(uint32_t* P, int n_slots, uint32_t ca, uint32_t cb, uint32_t sha_or_sp,
+                                           uint32_t shb, uint32_t pitch, uint32_t rp, uint32_t ocol,
+                                           const uint32_t* wA, const uint32_t* wB, uint32_t rnd,
+                                           uint32_t bdelta, uint32_t bvalid) {
+    if (U) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q, pb;\n"
+            ".reg .b32 s, loa, mida, hia, lob, midb, hib, Aa, Ba, Ab, Bb, h0, h1, h2, h3, h4, h5, t;\n"
+            ".reg .b32 r0, r1, r2, r3, r4, r5, o, o2, ca, cb, rp, ex, ey, ez, ew;\n"
+            "setp.ne.u32 pb, %26, 0;\n"
+            "mov.b32 ca, %7;\n mov.b32 cb, %8;\n mov.b32 rp, %11;\n" AW_SW_PRE_BEGIN AW_SW2_EMIT AW_SW_PRE_END("%6")
+            "SLOT:\n" AW_SW2_BLEND("%9", "%24")
+            "add.u32 ca, ca, %10;\n add.u32 cb, cb, %10;\n" AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1]), "+r"(P[2]), "+r"(P[3]), "+r"(P[4]), "+r"(P[5])
+            : "r"(n_slots), "r"(ca), "r"(cb), "r"(sha_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(rnd),
+              "r"(wA[0]), "r"(wA[1]), "r"(wA[2]), "r"(wB[1]), "r"(wB[2]),
+              "r"(wA[3]), "r"(wA[4]), "r"(wA[5]), "r"(wB[4]), "r"(wB[5]), "r"(shb), "r"(bdelta), "r"(bvalid)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q, pb;\n"
+            ".reg .b32 s, loa, mida, hia, lob, midb, hib, Aa, Ba, Ab, Bb, h0, h1, h2, h3, h4, h5, t, ta, tb, sha, shb;\n"
+            ".reg .b32 r0, r1, r2, r3, r4, r5, o, o2, ca, cb, sp, rp, ex, ey, ez, ew;\n"
+            "setp.ne.u32 pb, %26, 0;\n"
+            "mov.b32 sp, %9;\n mov.b32 rp, %11;\n" AW_SW_PRE_BEGIN AW_SW2_EMIT AW_SW_PRE_END("%6")
+            "SLOT:\n"
+            "ld.shared.b32 t, [sp];\n"
+            "add.u32 sp, sp, 4;\n"
+            "add.u32 ta, t, %7;\n"
+            "add.u32 tb, t, %8;\n"
+            "and.b32 ca, ta, 0xfffffffc;\n"
+            "and.b32 cb, tb, 0xfffffffc;\n"
+            "shl.b32 sha, ta, 3;\n"
+            "shl.b32 shb, tb, 3;\n" AW_SW2_BLEND("sha", "shb") AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1]), "+r"(P[2]), "+r"(P[3]), "+r"(P[4]), "+r"(P[5])
+            : "r"(n_slots), "r"(ca), "r"(cb), "r"(sha_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(rnd),
+              "r"(wA[0]), "r"(wA[1]), "r"(wA[2]), "r"(wB[1]), "r"(wB[2]),
+              "r"(wA[3]), "r"(wA[4]), "r"(wA[5]), "r"(wB[4]), "r"(wB[5]), "r"(shb), "r"(bdelta), "r"(bvalid)
+            : "memory");
+    }
+}
+
 struct StreamArgs {
     const uint8_t* src;
     uint8_t* dst;
@@ -284,13 +378,17 @@ struct StreamArgs {
     int H, W, Ho, Wo;
     int map_div;             // CHW planes share their image's maps
     int n_strips, n_rowtiles, total_tiles;
+    int strip_cols;          // output columns per strip (<= consumer threads x CPT)
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int out_pitch;           // bytes per row of an output tile
+    int rnd;                 // 512, the rounding constant of the vertical blend (kept out of the
+                             // instruction stream: as a literal it is rematerialised inside the row loop)
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
 };
 
 // Requires H >= 2 and W >= 2 (the launcher routes degenerate images to the direct kernel).
-// blockDim.x = Wt consumer threads + 32 producer threads + 32 store threads.
+// blockDim.x = Wt / CPT consumer threads (CPT adjacent output columns each) + 32 producer threads +
+// 32 store threads.
 // U ("uniform phase"): W*C is a multiple of 16, so every staged row starts at the same 16-byte
 // phase and slot k sits at k * slot_pitch + phase -- the sweep advances by one add per slot.
 //
@@ -303,10 +401,11 @@ struct StreamArgs {
 //   ofree[o] store warp -> consumers the tile has been read out of shared memory
 // The two rings are decoupled so that the loads of chunk c + kSrcStages start as soon as the
 // consumers leave chunk c, without waiting for its tile to be shipped.
-template <int C, int R, bool U>
-__global__ void __launch_bounds__(kMaxCols + kRoleThreads, 3)
+template <int C, int R, bool U, int CPT>
+__global__ void __launch_bounds__(max_cols(CPT) / CPT + kRoleThreads, 3)
 remap_u8_stream_kernel(const StreamArgs a) {
-    const int Wt = (int)blockDim.x - kRoleThreads;
+    static_assert(CPT == 1 || (CPT == 2 && C == 3), "two columns per thread are implemented for C = 3");
+    const int Wt = ((int)blockDim.x - kRoleThreads) * CPT;
     const int tid = threadIdx.x;
     const int out_bytes = R * a.out_pitch;
     const int out_off0 = kSrcStages * a.stage_bytes;
@@ -319,7 +418,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
     const uint32_t odone_s = sfree_s + 8u * kSrcStages;
     const uint32_t ofree_s = odone_s + 8u * kOutStages;
     const int H = a.H, W = a.W, Ho = a.Ho, Wo = a.Wo;
-    const int n_cons_warps = Wt >> 5;
+    const int n_cons_warps = ((int)blockDim.x - kRoleThreads) >> 5;
 
     if (tid == 0) {
         for (int s = 0; s < kSrcStages; ++s) {
@@ -347,7 +446,6 @@ remap_u8_stream_kernel(const StreamArgs a) {
     if (warp_idx >= n_cons_warps) {
         if (warp_idx == n_cons_warps) {
             // =========================== producer warp =========================================
-            const unsigned lt_mask = (1u << lane) - 1u;
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
             int t = t0;
@@ -359,8 +457,8 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 const int t_end = min(t1, (q + 1) * a.n_rowtiles);
                 const int y_end = min(Ho, (rt + (t_end - t)) * R);
                 const int mrow = img / a.map_div;
-                const int x_first = strip * Wt;
-                const int ncols = min(Wt, Wo - x_first);
+                const int x_first = strip * a.strip_cols;
+                const int ncols = min(a.strip_cols, Wo - x_first);
                 const uint8_t* simg = a.src + (int64_t)img * H * W * C;
                 const uintptr_t dimg = reinterpret_cast<uintptr_t>(a.dst) + (uintptr_t)((int64_t)img * Ho * Wo * C);
                 const float* my = a.map_y + (int64_t)mrow * Ho;
@@ -502,7 +600,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 if (n_rows > 0 && !(a.dbg & 2)) {
                     // ---- ship the rows: bulk store for the 16-byte aligned interior, bytes for the ends
                     const int img = (int)hd.y, x_first = (int)hd.z, y0 = (int)hd.w;
-                    const int len = min(Wt, Wo - x_first) * C;
+                    const int len = min(a.strip_cols, Wo - x_first) * C;
                     const int obuf = out_off0 + ot * out_bytes;
                     uint8_t* g0 = a.dst + ((int64_t)img * Ho * Wo + (int64_t)y0 * Wo + x_first) * C;
                     const bool ragged = !rows_aligned || ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len) & 15) != 0;
@@ -542,14 +640,19 @@ remap_u8_stream_kernel(const StreamArgs a) {
     }
 
     // =============================== consumer warps ==============================================
+    // this thread's output columns inside the strip: xl, and for CPT = 2 also xl + Wt / 2
     const int xl = tid;
-    int wo = 0;                       // byte offset of this column's window inside a staged row span
+    const int xstep = Wt / CPT;
+    int wo[CPT];                      // byte offset of each column's window inside a staged row span
     bool xvalid = false;
-    uint32_t wA[C], wB[C], P[C];
+    uint32_t bvalid = 0u;             // CPT = 2: the second column exists in this strip
+    uint32_t wA[C * CPT], wB[C * CPT], P[C * CPT];
 #pragma unroll
-    for (int k = 0; k < C; ++k) wA[k] = wB[k] = P[k] = 0u;
+    for (int k = 0; k < C * CPT; ++k) wA[k] = wB[k] = P[k] = 0u;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) wo[j] = 0;
     const int out_col = xl * C;
-    const uint32_t rnd = pin(512u);
+    const uint32_t rnd = (uint32_t)a.rnd;
 
     for (int it = 0;; ++it) {
         const int st = it % kSrcStages, ot = it % kOutStages;
@@ -568,17 +671,25 @@ remap_u8_stream_kernel(const StreamArgs a) {
             const uint4 h1 = ld128(tab + 16);
             const int img = (int)h1.x, x_first = (int)h1.y;
             const int mrow = img / a.map_div;
-            xvalid = xl < min(Wt, Wo - x_first);
-            int w0 = 32, w1 = 0, xb = (int)h1.w;
-            if (xvalid) column_taps(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl), W, xb, w0, w1);
-            wo = (xb - (int)h1.w) * C;
-            // dp4a weight words: tap0 of channel k at byte k of the 8-byte window, tap1 at byte k+C
+            const int ncols = min(a.strip_cols, Wo - x_first);
+            xvalid = xl < ncols;
+            bvalid = (CPT == 2 && xl + xstep < ncols) ? 1u : 0u;
+            int xb = (int)h1.w;
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                wA[k] = (uint32_t)w0 << (8 * k);
-                wB[k] = 0u;
-                if (k + C < 4) wA[k] |= (uint32_t)w1 << (8 * (k + C));
-                else wB[k] = (uint32_t)w1 << (8 * (k + C - 4));
+            for (int j = 0; j < CPT; ++j) {
+                // a column past the strip's end keeps the first column's window and gets zero weights
+                int w0 = j == 0 ? 32 : 0, w1 = 0;
+                if (xl + j * xstep < ncols)
+                    column_taps(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl + j * xstep), W, xb, w0, w1);
+                wo[j] = (xb - (int)h1.w) * C;
+                // dp4a weight words: tap0 of channel k at byte k of the 8-byte window, tap1 at byte k+C
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    wA[j * C + k] = (uint32_t)w0 << (8 * k);
+                    wB[j * C + k] = 0u;
+                    if (k + C < 4) wA[j * C + k] |= (uint32_t)w1 << (8 * (k + C));
+                    else wB[j * C + k] = (uint32_t)w1 << (8 * (k + C - 4));
+                }
             }
         }
         if (tid == 0) {                                      // what the store warp needs to ship the tile
@@ -591,31 +702,38 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 const uint4 h1 = ld128(tab + 16);
                 const int img = (int)h1.x, x_first = (int)h1.y, y0 = (int)h1.z;
                 const int mrow = img / a.map_div;
+                const int ncols = min(a.strip_cols, Wo - x_first);
                 const uint8_t* simg = a.src + (int64_t)img * H * W * C;
                 uint8_t* dimg = a.dst + (int64_t)img * Ho * Wo * C;
                 const int sy = quantise_coord(__ldg(a.map_y + (int64_t)mrow * Ho + y0));
                 const int ay = sy & 31;
                 const int ya = clampi(sy >> 5, 0, H - 1), yb = clampi((sy >> 5) + 1, 0, H - 1);
-                const int sx = quantise_coord(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl));
-                const int ax = sx & 31;
-                const int x0 = clampi(sx >> 5, 0, W - 1), x1 = clampi((sx >> 5) + 1, 0, W - 1);
-                uint8_t* o = dimg + ((int64_t)y0 * Wo + x_first + xl) * C;
+                for (int j = 0; j < CPT && xl + j * xstep < ncols; ++j) {
+                    const int sx = quantise_coord(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl + j * xstep));
+                    const int ax = sx & 31;
+                    const int x0 = clampi(sx >> 5, 0, W - 1), x1 = clampi((sx >> 5) + 1, 0, W - 1);
+                    uint8_t* o = dimg + ((int64_t)y0 * Wo + x_first + xl + j * xstep) * C;
 #pragma unroll
-                for (int k = 0; k < C; ++k)
-                    o[k] = bilinear_u8(__ldg(simg + ((int64_t)ya * W + x0) * C + k),
-                                       __ldg(simg + ((int64_t)ya * W + x1) * C + k),
-                                       __ldg(simg + ((int64_t)yb * W + x0) * C + k),
-                                       __ldg(simg + ((int64_t)yb * W + x1) * C + k), ax, ay);
+                    for (int k = 0; k < C; ++k)
+                        o[k] = bilinear_u8(__ldg(simg + ((int64_t)ya * W + x0) * C + k),
+                                           __ldg(simg + ((int64_t)ya * W + x1) * C + k),
+                                           __ldg(simg + ((int64_t)yb * W + x0) * C + k),
+                                           __ldg(simg + ((int64_t)yb * W + x1) * C + k), ax, ay);
+                }
             }
         } else if (xvalid && !(a.dbg & 1)) {
             const int n_slots = (int)(h0.y & 0xffffu);
-            const int arena = st * a.stage_bytes + wo;
+            const int arena = st * a.stage_bytes + wo[0];
             const int ocol = out_off0 + ot * out_bytes + out_col;
             const uint32_t ocol_s = smem_s + (uint32_t)ocol;
             const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
             const int slot_tab = tab + tab_slots<R>();
             const int win0 = arena + (U ? (int)h0.w : 0);
-            if (C == 3) {
+            if (CPT == 2) {
+                const int win1 = st * a.stage_bytes + wo[CPT - 1] + (U ? (int)h0.w : 0);
+                if (U) sweep_c3x2<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), smem_s + (uint32_t)(win1 & ~3), (uint32_t)win0 << 3, (uint32_t)win1 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
+                else sweep_c3x2<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)win1, smem_s + (uint32_t)slot_tab, 0u, 0u, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
+            } else if (C == 3) {
                 if (U) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
                 else sweep_c3<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, wB, rnd);
             } else if (C == 1) {
@@ -650,27 +768,30 @@ remap_u8_stream_kernel(const StreamArgs a) {
     }
 }
 
-template <int C, int R>
+template <int C, int R, int CPT>
 int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int Ho, int Wo,
                   const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
-    // one consumer thread per output column; strips as wide as possible up to kMaxCols
-    const int n_strips = (Wo + kMaxCols - 1) / kMaxCols;
-    int Wt = ((Wo + n_strips - 1) / n_strips + 31) & ~31;
-    if (Wt < 32) Wt = 32;
+    // CPT output columns per consumer thread; as few, equal strips as possible
+    constexpr int kMaxCols = max_cols(CPT);
     StreamArgs a;
+    a.n_strips = (Wo + kMaxCols - 1) / kMaxCols;
+    // equal strips, a multiple of 16 columns so that strip boundaries keep the 16-byte phase of a row
+    a.strip_cols = (((Wo + a.n_strips - 1) / a.n_strips) + 15) & ~15;
+    a.n_strips = (Wo + a.strip_cols - 1) / a.strip_cols;
+    const int Wt = (a.strip_cols + 32 * CPT - 1) / (32 * CPT) * (32 * CPT);   // columns covered by the consumer threads
     a.src = src; a.dst = dst; a.map_x = map_x; a.map_y = map_y;
     a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.map_div = map_div;
-    a.n_strips = (Wo + Wt - 1) / Wt;
     a.n_rowtiles = (Ho + R - 1) / R;
     const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
     if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
     a.total_tiles = (int)total;
+    a.rnd = 512;
     {
         const char* e = getenv("ATTWARP_REMAP_DBG");
         a.dbg = e ? atoi(e) : 0;
     }
-    const int cols_t = Wo < Wt ? Wo : Wt;                    // widest strip actually processed
-    a.out_pitch = (cols_t * C + 15 + 15) & ~15;
+    const int cols_t = Wo < a.strip_cols ? Wo : a.strip_cols;   // widest strip actually processed
+    a.out_pitch = (cols_t * C + 15 + 15) & ~15;            // + the 16-byte phase of the destination
     // an arena holds R + 2 source rows at unit scale (first chunk of a segment: R + 1)
     const int unit_pitch = (((cols_t + 1) * C + 30) & ~15) + 16;
     a.stage_bytes = ((R + 2) * unit_pitch + 127) & ~127;
@@ -679,8 +800,8 @@ int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int
                               2 * (kSrcStages + kOutStages) * sizeof(uint64_t);
     // uniform phase: every source row of every image starts at the same 16-byte phase
     const bool uniform = ((W * C) & 15) == 0 && (((int64_t)H * W * C) & 15) == 0;
-    auto kern = uniform ? remap_u8_stream_kernel<C, R, true> : remap_u8_stream_kernel<C, R, false>;
-    const int threads = Wt + kRoleThreads;
+    auto kern = uniform ? remap_u8_stream_kernel<C, R, true, CPT> : remap_u8_stream_kernel<C, R, false, CPT>;
+    const int threads = Wt / CPT + kRoleThreads;
     // the opt-in and the occupancy query cost microseconds of host time: once per configuration
     struct Cfg { size_t smem; int threads, dev, occ; };
     static thread_local Cfg cache[2] = {{0, 0, -1, 0}, {0, 0, -1, 0}};
@@ -701,6 +822,15 @@ int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int
     return check_launch("remap_u8_stream_kernel");
 }
 
+// ATTWARP_REMAP_CPT=1 forces one column per thread for C = 3 (A/B comparisons).
+int columns_per_thread_c3() {
+    static const int v = [] {
+        const char* e = getenv("ATTWARP_REMAP_CPT");
+        return (e && atoi(e) == 1) ? 1 : 2;
+    }();
+    return v;
+}
+
 }  // namespace
 
 // uint8 images with H, W >= 2: HWC with C in {1,3,4} or planar (n_img = B*C single-channel planes,
@@ -710,9 +840,11 @@ int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, 
     const uint8_t* s = static_cast<const uint8_t*>(src);
     uint8_t* d = static_cast<uint8_t*>(dst);
     switch (C) {
-        case 1: return launch_stream<1, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
-        case 3: return launch_stream<3, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
-        case 4: return launch_stream<4, 8>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 1: return launch_stream<1, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 3:
+            if (columns_per_thread_c3() == 2) return launch_stream<3, 8, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+            return launch_stream<3, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 4: return launch_stream<4, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
         default: return fail(ATTWARP_ERR_UNSUPPORTED, "remap supports C in {1,3,4} (got %d)", C);
     }
 }
