@@ -76,7 +76,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
+            extra = os.environ.get("ATTWARP_NVCC_EXTRA", "").split()   # tuning experiments (-D...)
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

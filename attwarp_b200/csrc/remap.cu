@@ -8,7 +8,7 @@
 // Kernels
 //   remap_direct_kernel   any dtype / layout / channel count; one thread per output pixel,
 //                         taps gathered straight from global memory through L1/L2.  Baseline and
-//                         fallback for shapes the tiled kernel does not cover.
+//                         fallback for shapes the streaming kernel (remap_stream.cu) does not cover.
 #include <stdlib.h>
 #include <string.h>
 
@@ -79,27 +79,20 @@ int launch_direct(const void* src, void* dst, int layout, int B, int C, int H, i
 
 }  // namespace
 
-int launch_remap_u8_tiled(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
-                          const float* map_x, const float* map_y, int map_div, cudaStream_t st);
-
 int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
                            const float* map_x, const float* map_y, int map_div, cudaStream_t st);
 
-// ATTWARP_REMAP=direct forces the baseline gather kernel, ATTWARP_REMAP=tiled the pass-synchronous
-// tiled kernel (A/B comparisons, debugging); default is the streaming kernel.
-static int remap_impl() {
-    static const int v = [] {
+// ATTWARP_REMAP=direct forces the baseline gather kernel (A/B comparisons, debugging); default is the
+// streaming kernel (remap_stream.cu).
+static bool force_direct() {
+    static const bool v = [] {
         const char* e = getenv("ATTWARP_REMAP");
-        if (e != nullptr && strcmp(e, "direct") == 0) return 0;
-        if (e != nullptr && strcmp(e, "tiled") == 0) return 1;
-        return 2;
+        return e != nullptr && strcmp(e, "direct") == 0;
     }();
     return v;
 }
-static bool force_direct() { return remap_impl() == 0; }
 static int launch_u8_fast(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
                           const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
-    if (remap_impl() == 1) return launch_remap_u8_tiled(src, dst, n_img, C, H, W, Ho, Wo, map_x, map_y, map_div, st);
     return launch_remap_u8_stream(src, dst, n_img, C, H, W, Ho, Wo, map_x, map_y, map_div, st);
 }
 

@@ -44,8 +44,22 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kSrcStages = 4;          // source-row stages (chunks whose loads are in flight) per CTA
-constexpr int kOutStages = 3;          // output tiles per CTA
+// Tuned on B200 at 336^2 and 1344^2 (profiles/run_tune.sh): 3 source stages x 12 rows, 2 output tiles,
+// 3 CTAs per SM; 4-5 smaller CTAs per SM or deeper rings of smaller chunks are 3-20 % slower.
+#ifndef AW_SRC_STAGES
+#define AW_SRC_STAGES 3
+#endif
+#ifndef AW_OUT_STAGES
+#define AW_OUT_STAGES 2
+#endif
+#ifndef AW_ROWS
+#define AW_ROWS 12
+#endif
+#ifndef AW_MIN_CTAS
+#define AW_MIN_CTAS 3
+#endif
+constexpr int kSrcStages = AW_SRC_STAGES;          // source-row stages (chunks whose loads are in flight) per CTA
+constexpr int kOutStages = AW_OUT_STAGES;          // output tiles per CTA
 // output columns per strip: 352 at one column per thread (11 + 2 warps x 3 CTAs keep 48 registers),
 // 384 at two columns per thread (6 + 2 warps)
 constexpr int max_cols(int cpt) { return cpt == 2 ? 384 : 352; }
@@ -402,7 +416,7 @@ struct StreamArgs {
 // The two rings are decoupled so that the loads of chunk c + kSrcStages start as soon as the
 // consumers leave chunk c, without waiting for its tile to be shipped.
 template <int C, int R, bool U, int CPT>
-__global__ void __launch_bounds__(max_cols(CPT) / CPT + kRoleThreads, 3)
+__global__ void __launch_bounds__(max_cols(CPT) / CPT + kRoleThreads, CPT == 2 ? AW_MIN_CTAS : 3)
 remap_u8_stream_kernel(const StreamArgs a) {
     static_assert(CPT == 1 || (CPT == 2 && C == 3), "two columns per thread are implemented for C = 3");
     const int Wt = ((int)blockDim.x - kRoleThreads) * CPT;
@@ -840,11 +854,11 @@ int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, 
     const uint8_t* s = static_cast<const uint8_t*>(src);
     uint8_t* d = static_cast<uint8_t*>(dst);
     switch (C) {
-        case 1: return launch_stream<1, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 1: return launch_stream<1, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
         case 3:
-            if (columns_per_thread_c3() == 2) return launch_stream<3, 8, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
-            return launch_stream<3, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
-        case 4: return launch_stream<4, 8, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+            if (columns_per_thread_c3() == 2) return launch_stream<3, AW_ROWS, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+            return launch_stream<3, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 4: return launch_stream<4, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
         default: return fail(ATTWARP_ERR_UNSUPPORTED, "remap supports C in {1,3,4} (got %d)", C);
     }
 }

@@ -1,4 +1,4 @@
-"""GPU parity, stage 5 edge cases: the tiled uint8 resample kernel against the oracle's restatement
+"""GPU parity, stage 5 edge cases: the streaming uint8 resample kernel against the oracle's restatement
 of cv2.remap(INTER_LINEAR, BORDER_REPLICATE) (itself pinned to the real cv2 in
 test_oracle_vs_golden.py).  Bit-exact (0 LSB) given identical float32 maps.
 
