@@ -36,6 +36,12 @@ class TransformParams(C.Structure):
                 ("exp_scale", C.c_double), ("exp_divisor", C.c_double)]
 
 
+class RaggedImage(C.Structure):
+    """attwarp_ragged_image: one image of a ragged batch (device pointers, dense HWC uint8)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32),
+                ("Ho", C.c_int32), ("Wo", C.c_int32)]
+
+
 def make_transform(name="identity", exp_scale=1.0, exp_divisor=1.0, apply_inverse=False):
     return TransformParams(TRANSFORM_IDS[name], 1 if apply_inverse else 0,
                            float(exp_scale), float(exp_divisor))
@@ -60,6 +66,8 @@ SIGNATURES = {
     "attwarp_warp_from_attention_tokens": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _i,
                                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _tp, _vp,
                                                 _sz, _vp, _vp, _vp, C.POINTER(_vp), _vp]),
+    "attwarp_ragged_workspace_bytes": (_sz, [_vp, _i]),
+    "attwarp_warp_ragged_from_tokens": (_i, [_vp, _i, _i, _i, _vp, _i, _tp, _vp, _sz, _vp]),
     "attwarp_warp_image_host": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _tp, _vp,
                                      C.POINTER(_i)]),
     "attwarp_safe_softmax": (_i, [_vp, _i, _i, _f, _vp, _vp]),

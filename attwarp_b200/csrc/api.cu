@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace aw {
@@ -243,6 +245,73 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
     rc = launch_remap(src, dst, img_dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
     if (rc != ATTWARP_OK) return rc;
     return mark(3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ragged batch: descriptor table (n + 1 entries) followed by the map rows of every image.
+static size_t ragged_table_bytes(int n) { return align_up(sizeof(RaggedImage) * (size_t)(n + 1), 256); }
+
+size_t attwarp_ragged_workspace_bytes(const attwarp_ragged_image* images, int n) {
+    if (images == nullptr || n <= 0) return 0;
+    size_t floats = 0;
+    for (int i = 0; i < n; ++i) floats += (size_t)(images[i].Wo > 0 ? images[i].Wo : 0) + (size_t)(images[i].Ho > 0 ? images[i].Ho : 0);
+    return ragged_table_bytes(n) + align_up(floats * sizeof(float), 256);
+}
+
+int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
+                                    const attwarp_ragged_image* images, int C,
+                                    const attwarp_transform_params* tp, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    AW_REQUIRE(tok && images && workspace, "warp_ragged: NULL pointer");
+    AW_REQUIRE(n > 0 && gh > 0 && gw > 0, "warp_ragged: sizes must be positive");
+    AW_REQUIRE(C == 1 || C == 3 || C == 4, "warp_ragged: C must be 1, 3 or 4 (got %d)", C);
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    const size_t need = attwarp_ragged_workspace_bytes(images, n);
+    if (workspace_bytes < need)
+        return fail(ATTWARP_ERR_WORKSPACE, "warp_ragged: workspace too small (%zu < %zu)", workspace_bytes, need);
+    cudaStream_t st = as_stream(stream);
+    RaggedImage* dev_table = static_cast<RaggedImage*>(workspace);
+    float* pool = reinterpret_cast<float*>(static_cast<char*>(workspace) + ragged_table_bytes(n));
+    static thread_local std::vector<RaggedImage> host;
+    host.assign((size_t)n + 1, RaggedImage{});
+    int max_h = 0, max_w = 0;
+    bool degenerate = false;
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        const attwarp_ragged_image& im = images[i];
+        AW_REQUIRE(im.src && im.dst && im.src != im.dst, "warp_ragged: image %d: bad pointers", i);
+        AW_REQUIRE(im.H > 0 && im.W > 0 && im.Ho > 0 && im.Wo > 0, "warp_ragged: image %d: sizes must be positive", i);
+        AW_REQUIRE(im.H < 65536 && im.W < 65536, "warp_ragged: image %d: H, W must be below 65536", i);
+        RaggedImage& r = host[(size_t)i];
+        r.src = static_cast<const uint8_t*>(im.src);
+        r.dst = static_cast<uint8_t*>(im.dst);
+        r.map_x = pool + off; off += (size_t)im.Wo;
+        r.map_y = pool + off; off += (size_t)im.Ho;
+        r.H = im.H; r.W = im.W; r.Ho = im.Ho; r.Wo = im.Wo;
+        max_h = im.H > max_h ? im.H : max_h;
+        max_w = im.W > max_w ? im.W : max_w;
+        degenerate = degenerate || im.H < 2 || im.W < 2;
+    }
+    if (degenerate) {
+        // 1-pixel axes go through the per-image entry points (the streaming kernel needs two source rows
+        // and columns); such batches are not a throughput case
+        for (int i = 0; i < n; ++i) {
+            const RaggedImage& r = host[(size_t)i];
+            rc = launch_maps_from_tokens(tok + (size_t)i * gh * gw, 1, 1.0f, nullptr, 1, gh, gw, r.H, r.W, r.Wo, r.Ho,
+                                         *tp, const_cast<float*>(r.map_x), const_cast<float*>(r.map_y), nullptr, st);
+            if (rc != ATTWARP_OK) return rc;
+            rc = launch_remap(r.src, r.dst, ATTWARP_U8, ATTWARP_LAYOUT_HWC, 1, C, r.H, r.W, r.Ho, r.Wo, r.map_x, r.map_y, st);
+            if (rc != ATTWARP_OK) return rc;
+        }
+        return ATTWARP_OK;
+    }
+    // the strip plan of stage 5 is part of the table both kernels read: plan + upload, maps, resample
+    rc = launch_remap_u8_stream_ragged_prepare(host.data(), n, C, dev_table, st);
+    if (rc != ATTWARP_OK) return rc;
+    rc = launch_maps_from_tokens_ragged(tok, n, gh, gw, dev_table, max_h, max_w, *tp, nullptr, st);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
 }
 
 int attwarp_warp_image_host(const void* image_host, int img_dtype, int C, int H, int W,

@@ -32,6 +32,18 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int sm_count();
 
+// ---- one image of a ragged batch (device table built by the launchers in remap_stream.cu / api.cu) ----
+struct RaggedImage {
+    const uint8_t* src;      // HWC uint8, dense
+    uint8_t* dst;            // Ho x Wo x C, dense
+    const float* map_x;      // Wo floats
+    const float* map_y;      // Ho floats
+    int H, W, Ho, Wo;
+    int n_strips, strip_cols, n_rowtiles;   // stage-5 strip plan (filled in by the stage-5 launcher)
+    int tile_begin;          // index of the image's first tile; its tiles are strip-major
+};
+static_assert(sizeof(RaggedImage) == 64, "descriptor layout");
+
 // ---- internal launchers (defined in the .cu files, used by the fused drivers in api.cu) -------
 int launch_aggregate_partial(const void* attn, int dtype, int B, int L, int Hh, int T,
                              int64_t sb, int64_t sl, int64_t sh, const int32_t* tok_start,
@@ -49,6 +61,14 @@ int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int
                                cudaStream_t st);
 int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C, int H, int W,
                  int Ho, int Wo, const float* map_x, const float* map_y, cudaStream_t st);
+// ragged batches: `imgs` is a device table of n entries (dims + map pointers are read per image)
+int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, const RaggedImage* imgs,
+                                   int max_h, int max_w, const attwarp_transform_params& tp,
+                                   int* fallback_flags, cudaStream_t st);
+// stage 5 over a ragged batch, in two steps so that the maps kernel can run in between: `prepare` fills in the
+// strip plan of host_table[0..n] (n + 1 entries) and uploads it to dev_table; `run` launches the kernel
+int launch_remap_u8_stream_ragged_prepare(RaggedImage* host_table, int n, int C, RaggedImage* dev_table, cudaStream_t st);
+int launch_remap_u8_stream_ragged_run(const RaggedImage* host_table, int n, int C, const RaggedImage* dev_table, cudaStream_t st);
 
 #if defined(__CUDACC__)
 // ---- warp / block reductions -----------------------------------------------------------------

@@ -102,10 +102,18 @@ __global__ void __launch_bounds__(2 * kProfThreads)
 maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
                         float* __restrict__ tok_out, int gh, int gw, int H, int W, int Wo, int Ho,
                         TransformArgs ta, float* __restrict__ map_x, float* __restrict__ map_y,
-                        int* __restrict__ fallback_flags) {
+                        int* __restrict__ fallback_flags, const RaggedImage* __restrict__ imgs) {
     extern __shared__ double smem[];
     const int b = blockIdx.x;
     const int G = gh * gw;
+    if (imgs != nullptr) {                    // ragged batch: sizes and map rows per image
+        H = imgs[b].H; W = imgs[b].W; Wo = imgs[b].Wo; Ho = imgs[b].Ho;
+        map_x = const_cast<float*>(imgs[b].map_x);
+        map_y = const_cast<float*>(imgs[b].map_y);
+    } else {
+        map_x += (int64_t)b * Wo;
+        map_y += (int64_t)b * Ho;
+    }
     double* red = smem;                       // 2 * kTailRed
     double* xchg = red + 2 * kTailRed;        // kTailXchg
     double* grid = xchg + kTailXchg;          // G   transformed + biased token values
@@ -161,8 +169,8 @@ maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
     for (int x = threadIdx.x; x < W; x += blockDim.x) prof_x[x] = csum[(x * gw) / W];
     for (int y = threadIdx.x; y < H; y += blockDim.x) prof_y[y] = rsum[(y * gh) / H];
     __syncthreads();
-    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, xchg, map_x + (int64_t)b * Wo,
-                     map_y + (int64_t)b * Ho, fallback_flags ? fallback_flags + b : nullptr);
+    profiles_to_maps(prof_x, prof_y, W, H, Wo, Ho, ta, knots, red, xchg, map_x, map_y,
+                     fallback_flags ? fallback_flags + b : nullptr);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -352,7 +360,19 @@ int launch_maps_from_tokens(const float* tok, int nsplit, float scale, float* to
     if (rc != ATTWARP_OK) return rc;
     maps_from_tokens_kernel<<<B, 2 * kProfThreads, smem, st>>>(tok, nsplit, scale, tok_out, gh, gw, H, W,
                                                            Wo, Ho, to_args(tp), map_x, map_y,
-                                                           fallback_flags);
+                                                           fallback_flags, nullptr);
+    return check_launch("maps_from_tokens_kernel");
+}
+
+int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, const RaggedImage* imgs,
+                                   int max_h, int max_w, const attwarp_transform_params& tp,
+                                   int* fallback_flags, cudaStream_t st) {
+    if (gh * gw > 8192) return fail(ATTWARP_ERR_UNSUPPORTED, "token grid %dx%d too large", gh, gw);
+    const size_t smem = maps_smem_bytes(gh * gw + gw + gh, max_h, max_w);
+    int rc = opt_in_smem(maps_from_tokens_kernel, smem, "maps_from_tokens");
+    if (rc != ATTWARP_OK) return rc;
+    maps_from_tokens_kernel<<<n, 2 * kProfThreads, smem, st>>>(tok, 1, 1.0f, nullptr, gh, gw, 0, 0, 0, 0,
+                                                           to_args(tp), nullptr, nullptr, fallback_flags, imgs);
     return check_launch("maps_from_tokens_kernel");
 }
 

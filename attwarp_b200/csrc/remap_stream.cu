@@ -73,22 +73,19 @@ __device__ __forceinline__ void st32(int off, uint32_t v) { *reinterpret_cast<ui
 __device__ __forceinline__ void st128(int off, uint4 v) { *reinterpret_cast<uint4*>(smem + off) = v; }
 __device__ __forceinline__ void st8(int off, uint32_t v) { smem[off] = (uint8_t)v; }
 
-// ---- per-stage chunk table (byte offsets), written by the producer, read by consumers + store warp
-//   +0   uint4 {n_rows, n_slots | flags << 16, slot_pitch, phase of slot 0 (global address & 15)}
-//              n_rows 0: output row y0 takes the direct path; -1: stop
-//   +16  uint4 {img, x_first, y0, c_lo}
-//   +32  uint4 row[R + 1]:  x = dp2a weight word  wa | (32 - wa) << 8  (upper row, lower row)
-//                           y = byte offset of the row inside the output tile
-//                               (i * out_pitch + (dst address & 15))
-//                           z = slot after which the row is emitted (= slot of its LOWER tap);
-//                               0xffffffff: both taps are the carried pair, emit before slot 0;
-//                               entry n_rows is a sentinel (z = kRowSentinel)
-//   +32 + 16 (R + 1)  uint32 slot_base[2 R]:  slot * slot_pitch + (global address of its first byte & 15)
-constexpr int kTabRows = 32;
+// ---- rows of the per-stage chunk table (the header is described next to the kernel) -----------------
+//   uint4 row[R + 1]:  x = dp2a weight word  wa | (32 - wa) << 8  (upper row, lower row)
+//                      y = byte offset of the row inside the output tile
+//                          (i * out_pitch + (dst address & 15))
+//                      z = slot after which the row is emitted (= slot of its LOWER tap);
+//                          0xffffffff: both taps are the carried pair, emit before slot 0;
+//                          entry n_rows is a sentinel (z = kRowSentinel)
+//   uint32 slot_base[2 R]:  slot * slot_pitch + (global address of its first byte & 15)
+constexpr int kTabRows = 64;
 constexpr uint32_t kRowSentinel = 0x7fffffffu;
 template <int R> constexpr int tab_slots() { return kTabRows + 16 * (R + 1); }
 template <int R> constexpr int tab_bytes() { return tab_slots<R>() + 4 * 2 * R; }
-constexpr uint32_t kFlagNewStrip = 1u;
+constexpr uint32_t kFlagNewStrip = 1u, kFlagUniform = 2u;
 constexpr int kNoCarry = -(1 << 29);
 
 // base source column and tap weights of one output column (border replicate folded into weights)
@@ -385,14 +382,19 @@ __device__ __forceinline__ void sweep_c3x2(uint32_t* P, int n_slots, uint32_t ca
 }
 
 struct StreamArgs {
+    // uniform batch (imgs == nullptr): n_img dense images of one shape, maps [n_img / map_div][..]
     const uint8_t* src;
     uint8_t* dst;
     const float* map_x;
     const float* map_y;
     int H, W, Ho, Wo;
     int map_div;             // CHW planes share their image's maps
-    int n_strips, n_rowtiles, total_tiles;
+    int n_strips, n_rowtiles;
     int strip_cols;          // output columns per strip (<= consumer threads x CPT)
+    // ragged batch: per-image descriptors, n_img + 1 entries (the last one only carries tile_begin)
+    const RaggedImage* imgs;
+    int n_img;
+    int total_tiles;
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int out_pitch;           // bytes per row of an output tile
     int rnd;                 // 512, the rounding constant of the vertical blend (kept out of the
@@ -400,10 +402,54 @@ struct StreamArgs {
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
 };
 
-// Requires H >= 2 and W >= 2 (the launcher routes degenerate images to the direct kernel).
-// blockDim.x = Wt / CPT consumer threads (CPT adjacent output columns each) + 32 producer threads +
+// What the kernel needs to know about one image.
+struct View {
+    const uint8_t* src;
+    uint8_t* dst;
+    const float* mx;
+    const float* my;
+    int H, W, Ho, Wo, n_strips, strip_cols, n_rowtiles, tile_begin;
+};
+template <int C>
+__device__ __forceinline__ View get_view(const StreamArgs& a, int img) {
+    View v;
+    if (a.imgs != nullptr) {
+        const uint4* q = reinterpret_cast<const uint4*>(a.imgs + img);
+        const uint4 p0 = __ldg(q), p1 = __ldg(q + 1), p2 = __ldg(q + 2), p3 = __ldg(q + 3);
+        v.src = reinterpret_cast<const uint8_t*>(((uint64_t)p0.y << 32) | p0.x);
+        v.dst = reinterpret_cast<uint8_t*>(((uint64_t)p0.w << 32) | p0.z);
+        v.mx = reinterpret_cast<const float*>(((uint64_t)p1.y << 32) | p1.x);
+        v.my = reinterpret_cast<const float*>(((uint64_t)p1.w << 32) | p1.z);
+        v.H = (int)p2.x; v.W = (int)p2.y; v.Ho = (int)p2.z; v.Wo = (int)p2.w;
+        v.n_strips = (int)p3.x; v.strip_cols = (int)p3.y; v.n_rowtiles = (int)p3.z; v.tile_begin = (int)p3.w;
+    } else {
+        const int mrow = img / a.map_div;
+        v.src = a.src + (int64_t)img * a.H * a.W * C;
+        v.dst = a.dst + (int64_t)img * a.Ho * a.Wo * C;
+        v.mx = a.map_x + (int64_t)mrow * a.Wo;
+        v.my = a.map_y + (int64_t)mrow * a.Ho;
+        v.H = a.H; v.W = a.W; v.Ho = a.Ho; v.Wo = a.Wo;
+        v.n_strips = a.n_strips; v.strip_cols = a.strip_cols; v.n_rowtiles = a.n_rowtiles;
+        v.tile_begin = img * a.n_strips * a.n_rowtiles;
+    }
+    return v;
+}
+
+// ---- per-stage chunk table (byte offsets), written by the producer, read by the consumers ----------
+//   +0   uint4 {n_rows, n_slots | flags << 16, slot_pitch, phase of slot 0 (global address & 15)}
+//              n_rows 0: output row y0 takes the direct path; -1: stop
+//   +16  uint4 {img, x_first, y0, c_lo}
+//   +32  uint4 {address of the chunk's first output byte (lo, hi), bytes per tile row, Wo * C}
+//              (copied to the tile header for the store warp)
+//   +48  uint4 {address of map_x[x_first] (lo, hi), W, columns in the strip}      (new strip only)
+//   +64  uint4 row[R + 1]: see kTabRows
+//   then uint32 slot_base[2 R]  (non-uniform phase only)
+constexpr int kTabStore = 32, kTabStrip = 48;
+
+// Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
+// blockDim.x = Wt / CPT consumer threads (CPT output columns each) + 32 producer threads +
 // 32 store threads.
-// U ("uniform phase"): W*C is a multiple of 16, so every staged row starts at the same 16-byte
+// Uniform phase (per image): W*C is a multiple of 16, so every staged row starts at the same 16-byte
 // phase and slot k sits at k * slot_pitch + phase -- the sweep advances by one add per slot.
 //
 // Shared memory: [kSrcStages source arenas][kOutStages output tiles][kSrcStages chunk tables]
@@ -415,7 +461,7 @@ struct StreamArgs {
 //   ofree[o] store warp -> consumers the tile has been read out of shared memory
 // The two rings are decoupled so that the loads of chunk c + kSrcStages start as soon as the
 // consumers leave chunk c, without waiting for its tile to be shipped.
-template <int C, int R, bool U, int CPT>
+template <int C, int R, int CPT>
 __global__ void __launch_bounds__(max_cols(CPT) / CPT + kRoleThreads, CPT == 2 ? AW_MIN_CTAS : 3)
 remap_u8_stream_kernel(const StreamArgs a) {
     static_assert(CPT == 1 || (CPT == 2 && C == 3), "two columns per thread are implemented for C = 3");
@@ -425,13 +471,12 @@ remap_u8_stream_kernel(const StreamArgs a) {
     const int out_off0 = kSrcStages * a.stage_bytes;
     const int tab_off0 = out_off0 + kOutStages * out_bytes;
     const int ohdr_off0 = tab_off0 + kSrcStages * tab_bytes<R>();
-    const int bar_off0 = ohdr_off0 + kOutStages * 16;
+    const int bar_off0 = ohdr_off0 + kOutStages * 32;
     const uint32_t smem_s = smem_u32(smem);
     const uint32_t full_s = smem_s + (uint32_t)bar_off0;
     const uint32_t sfree_s = full_s + 8u * kSrcStages;
     const uint32_t odone_s = sfree_s + 8u * kSrcStages;
     const uint32_t ofree_s = odone_s + 8u * kOutStages;
-    const int H = a.H, W = a.W, Ho = a.Ho, Wo = a.Wo;
     const int n_cons_warps = ((int)blockDim.x - kRoleThreads) >> 5;
 
     if (tid == 0) {
@@ -463,24 +508,43 @@ remap_u8_stream_kernel(const StreamArgs a) {
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
             int t = t0;
+            int img = -1;
             while (t < t1) {
                 // ---- segment: the tiles [t, t_end) of one (image, strip) ----------------------
-                const int rt = t % a.n_rowtiles;
-                const int q = t / a.n_rowtiles;
-                const int strip = q % a.n_strips, img = q / a.n_strips;
-                const int t_end = min(t1, (q + 1) * a.n_rowtiles);
+                if (a.imgs == nullptr) {
+                    img = t / (a.n_strips * a.n_rowtiles);
+                } else if (img < 0) {
+                    // first segment: the last image whose first tile is <= t (32-ary search)
+                    int lo = 0, hi = a.n_img;                          // answer in [lo, hi)
+                    while (hi - lo > 1) {
+                        const int step = (hi - lo + 31) / 32;
+                        const int probe = min(lo + (lane + 1) * step, hi);
+                        const bool le = probe < hi && __ldg(&a.imgs[probe].tile_begin) <= t;
+                        const int k = __popc(__ballot_sync(0xffffffffu, le));   // probes are monotone
+                        const int nlo = lo + k * step;
+                        hi = min(lo + (k + 1) * step, hi);
+                        lo = nlo;
+                    }
+                    img = lo;
+                } else {
+                    while (__ldg(&a.imgs[img + 1].tile_begin) <= t) ++img;
+                }
+                const View v = get_view<C>(a, img);
+                const int H = v.H, W = v.W, Ho = v.Ho, Wo = v.Wo;
+                const int local = t - v.tile_begin;
+                const int strip = local / v.n_rowtiles, rt = local % v.n_rowtiles;
+                const int t_end = min(t1, v.tile_begin + (strip + 1) * v.n_rowtiles);
                 const int y_end = min(Ho, (rt + (t_end - t)) * R);
-                const int mrow = img / a.map_div;
-                const int x_first = strip * a.strip_cols;
-                const int ncols = min(a.strip_cols, Wo - x_first);
-                const uint8_t* simg = a.src + (int64_t)img * H * W * C;
-                const uintptr_t dimg = reinterpret_cast<uintptr_t>(a.dst) + (uintptr_t)((int64_t)img * Ho * Wo * C);
-                const float* my = a.map_y + (int64_t)mrow * Ho;
+                const int x_first = strip * v.strip_cols;
+                const int ncols = min(v.strip_cols, Wo - x_first);
+                const uint8_t* simg = v.src;
+                const uintptr_t dimg = reinterpret_cast<uintptr_t>(v.dst);
+                const float* my = v.my;
+                const float* mx = v.mx + x_first;
                 // source column span of the strip
                 int c_lo, row_bytes, slot_pitch, max_slots;
                 {
                     int lo = 0x7fffffff, hi = -1;
-                    const float* mx = a.map_x + (int64_t)mrow * Wo + x_first;
                     for (int x = lane; x < ncols; x += 32) {
                         int xb, w0, w1;
                         column_taps(__ldg(mx + x), W, xb, w0, w1);
@@ -500,17 +564,18 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 }
                 const uint8_t* scol = simg + (int64_t)c_lo * C;
                 const int64_t row_pitch = (int64_t)W * C;
-                // phase of the staged rows (U: identical for every row of every image)
+                // phase of the staged rows (uniform: identical for every row of the image)
                 const int phase = (int)(reinterpret_cast<uintptr_t>(scol) & 15);
+                const bool uni = ((W * C) & 15) == 0;
                 // Full-width strip of an image whose rows are multiples of 16 bytes: consecutive source
                 // rows are contiguous in global memory, so a whole chunk is ONE bulk copy (slot pitch =
                 // row pitch).  Otherwise one copy per source row, issued by the lane that owns the slot.
-                const bool one_copy = U && row_bytes == W * C;
+                const bool one_copy = uni && row_bytes == W * C;
                 if (one_copy) {
                     slot_pitch = W * C;
                     max_slots = min((a.stage_bytes - 32) / slot_pitch, 2 * R);
                 }
-                uint32_t strip_flag = kFlagNewStrip;
+                uint32_t seg_flags = kFlagNewStrip | (uni ? kFlagUniform : 0u);
                 int carry_row = kNoCarry;    // source row whose blend sits in the upper half of P
                 int y_cur = rt * R;
                 // map_y is read through a register window of 2 x 32 rows (lane i holds rows y_win + i
@@ -559,10 +624,10 @@ remap_u8_stream_kernel(const StreamArgs a) {
                     const uint32_t bytes = lane < n_slots ? (uint32_t)((off + row_bytes + 15) & ~15) : 0u;
                     const uint32_t tx = one_copy ? (uint32_t)((phase + n_slots * slot_pitch + 15) & ~15)
                                                  : __reduce_add_sync(0xffffffffu, bytes);
+                    const uintptr_t gd = dimg + (uintptr_t)(((int64_t)y * Wo + x_first) * C);   // this row's first byte
 
                     mbar_wait(sfree_s + 8u * st, ph ^ 1u);             // stage free again
                     if (lane < n_rows) {
-                        const uintptr_t gd = dimg + (uintptr_t)(((int64_t)y * Wo + x_first) * C);
                         st128(tab + kTabRows + 16 * lane,
                               make_uint4((uint32_t)wa | ((uint32_t)(32 - wa) << 8),
                                          (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 15),
@@ -570,13 +635,20 @@ remap_u8_stream_kernel(const StreamArgs a) {
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, kRowSentinel, 0u));
                     }
-                    if (!U && lane < n_slots) st32(tab + tab_slots<R>() + 4 * lane, (uint32_t)(lane * slot_pitch + off));
+                    if (!uni && lane < n_slots) st32(tab + tab_slots<R>() + 4 * lane, (uint32_t)(lane * slot_pitch + off));
                     if (lane == 0) {
-                        st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (strip_flag << 16),
+                        st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (seg_flags << 16),
                                               (uint32_t)slot_pitch, (uint32_t)phase));
                         st128(tab + 16, make_uint4((uint32_t)img, (uint32_t)x_first, (uint32_t)y_cur, (uint32_t)c_lo));
+                        st128(tab + kTabStore, make_uint4((uint32_t)gd, (uint32_t)((uint64_t)gd >> 32),
+                                                          (uint32_t)(ncols * C), (uint32_t)(Wo * C)));
+                        if (seg_flags & kFlagNewStrip) {
+                            const uintptr_t mxa = reinterpret_cast<uintptr_t>(mx);
+                            st128(tab + kTabStrip, make_uint4((uint32_t)mxa, (uint32_t)((uint64_t)mxa >> 32),
+                                                              (uint32_t)W, (uint32_t)ncols));
+                        }
                     }
-                    strip_flag = 0u;
+                    seg_flags &= ~kFlagNewStrip;
                     __syncwarp();
                     if (lane == 0) {
                         if (n_slots > 0) mbar_arrive_expect_tx(full_s + 8u * st, tx);
@@ -605,21 +677,21 @@ remap_u8_stream_kernel(const StreamArgs a) {
             // =============================== store warp ======================================
             int ot = 0;
             uint32_t ph = 0;
-            const bool rows_aligned = ((Wo * C) & 15) == 0;
             for (;;) {
                 mbar_wait(odone_s + 8u * ot, ph);                      // every consumer warp is through
-                const uint4 hd = ld128(ohdr_off0 + 16 * ot);           // {n_rows, img, x_first, y0}
+                const uint4 hd = ld128(ohdr_off0 + 32 * ot);           // {n_rows, -, -, -}
                 const int n_rows = (int)hd.x;
                 if (n_rows < 0) break;
                 if (n_rows > 0 && !(a.dbg & 2)) {
                     // ---- ship the rows: bulk store for the 16-byte aligned interior, bytes for the ends
-                    const int img = (int)hd.y, x_first = (int)hd.z, y0 = (int)hd.w;
-                    const int len = min(a.strip_cols, Wo - x_first) * C;
+                    const uint4 hs = ld128(ohdr_off0 + 32 * ot + 16);  // {dst lo, dst hi, row bytes, dst pitch}
+                    const int len = (int)hs.z;
+                    const int64_t dpitch = (int64_t)hs.w;
                     const int obuf = out_off0 + ot * out_bytes;
-                    uint8_t* g0 = a.dst + ((int64_t)img * Ho * Wo + (int64_t)y0 * Wo + x_first) * C;
-                    const bool ragged = !rows_aligned || ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len) & 15) != 0;
+                    uint8_t* g0 = reinterpret_cast<uint8_t*>(((uint64_t)hs.y << 32) | hs.x);
+                    const bool ragged = ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len | (uintptr_t)dpitch) & 15) != 0;
                     if (lane < n_rows) {
-                        uint8_t* g = g0 + (int64_t)lane * Wo * C;
+                        uint8_t* g = g0 + (int64_t)lane * dpitch;
                         const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                         const int head = (16 - off) & 15;
                         const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
@@ -630,7 +702,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                     if (ragged) {
                         // <= 15 head bytes and <= 15 tail bytes per row, one lane per byte
                         for (int i = 0; i < n_rows; ++i) {
-                            uint8_t* g = g0 + (int64_t)i * Wo * C;
+                            uint8_t* g = g0 + (int64_t)i * dpitch;
                             const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                             const int head = min((16 - off) & 15, len);
                             const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
@@ -676,16 +748,16 @@ remap_u8_stream_kernel(const StreamArgs a) {
         const int n_rows = (int)h0.x;
         mbar_wait(ofree_s + 8u * ot, ((uint32_t)(it / kOutStages) & 1u) ^ 1u);   // tile shipped and free
         if (n_rows < 0) {                                                        // pass the stop on
-            if (tid == 0) st128(ohdr_off0 + 16 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
+            if (tid == 0) st128(ohdr_off0 + 32 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
             __syncwarp();
             if (lane == 0) mbar_arrive(odone_s + 8u * ot);
             break;
         }
         if (h0.y & (kFlagNewStrip << 16)) {                  // new strip: per-column taps and weights
             const uint4 h1 = ld128(tab + 16);
-            const int img = (int)h1.x, x_first = (int)h1.y;
-            const int mrow = img / a.map_div;
-            const int ncols = min(a.strip_cols, Wo - x_first);
+            const uint4 hx = ld128(tab + kTabStrip);
+            const float* mx = reinterpret_cast<const float*>(((uint64_t)hx.y << 32) | hx.x);
+            const int W = (int)hx.z, ncols = (int)hx.w;
             xvalid = xl < ncols;
             bvalid = (CPT == 2 && xl + xstep < ncols) ? 1u : 0u;
             int xb = (int)h1.w;
@@ -693,8 +765,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
             for (int j = 0; j < CPT; ++j) {
                 // a column past the strip's end keeps the first column's window and gets zero weights
                 int w0 = j == 0 ? 32 : 0, w1 = 0;
-                if (xl + j * xstep < ncols)
-                    column_taps(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl + j * xstep), W, xb, w0, w1);
+                if (xl + j * xstep < ncols) column_taps(__ldg(mx + xl + j * xstep), W, xb, w0, w1);
                 wo[j] = (xb - (int)h1.w) * C;
                 // dp4a weight words: tap0 of channel k at byte k of the 8-byte window, tap1 at byte k+C
 #pragma unroll
@@ -707,51 +778,51 @@ remap_u8_stream_kernel(const StreamArgs a) {
             }
         }
         if (tid == 0) {                                      // what the store warp needs to ship the tile
-            const uint4 h1 = ld128(tab + 16);
-            st128(ohdr_off0 + 16 * ot, make_uint4(h0.x, h1.x, h1.y, h1.z));
+            st128(ohdr_off0 + 32 * ot, make_uint4(h0.x, 0u, 0u, 0u));
+            st128(ohdr_off0 + 32 * ot + 16, ld128(tab + kTabStore));
         }
         if (n_rows == 0) {
             // ---- direct path for one output row whose source span does not fit a stage ----------
             if (xvalid) {
                 const uint4 h1 = ld128(tab + 16);
                 const int img = (int)h1.x, x_first = (int)h1.y, y0 = (int)h1.z;
-                const int mrow = img / a.map_div;
-                const int ncols = min(a.strip_cols, Wo - x_first);
-                const uint8_t* simg = a.src + (int64_t)img * H * W * C;
-                uint8_t* dimg = a.dst + (int64_t)img * Ho * Wo * C;
-                const int sy = quantise_coord(__ldg(a.map_y + (int64_t)mrow * Ho + y0));
+                const View v = get_view<C>(a, img);
+                const int H = v.H, W = v.W, Wo = v.Wo;
+                const int ncols = min(v.strip_cols, Wo - x_first);
+                const int sy = quantise_coord(__ldg(v.my + y0));
                 const int ay = sy & 31;
                 const int ya = clampi(sy >> 5, 0, H - 1), yb = clampi((sy >> 5) + 1, 0, H - 1);
                 for (int j = 0; j < CPT && xl + j * xstep < ncols; ++j) {
-                    const int sx = quantise_coord(__ldg(a.map_x + (int64_t)mrow * Wo + x_first + xl + j * xstep));
+                    const int sx = quantise_coord(__ldg(v.mx + x_first + xl + j * xstep));
                     const int ax = sx & 31;
                     const int x0 = clampi(sx >> 5, 0, W - 1), x1 = clampi((sx >> 5) + 1, 0, W - 1);
-                    uint8_t* o = dimg + ((int64_t)y0 * Wo + x_first + xl + j * xstep) * C;
+                    uint8_t* o = v.dst + ((int64_t)y0 * Wo + x_first + xl + j * xstep) * C;
 #pragma unroll
                     for (int k = 0; k < C; ++k)
-                        o[k] = bilinear_u8(__ldg(simg + ((int64_t)ya * W + x0) * C + k),
-                                           __ldg(simg + ((int64_t)ya * W + x1) * C + k),
-                                           __ldg(simg + ((int64_t)yb * W + x0) * C + k),
-                                           __ldg(simg + ((int64_t)yb * W + x1) * C + k), ax, ay);
+                        o[k] = bilinear_u8(__ldg(v.src + ((int64_t)ya * W + x0) * C + k),
+                                           __ldg(v.src + ((int64_t)ya * W + x1) * C + k),
+                                           __ldg(v.src + ((int64_t)yb * W + x0) * C + k),
+                                           __ldg(v.src + ((int64_t)yb * W + x1) * C + k), ax, ay);
                 }
             }
         } else if (xvalid && !(a.dbg & 1)) {
             const int n_slots = (int)(h0.y & 0xffffu);
+            const bool uni = (h0.y & (kFlagUniform << 16)) != 0u;
             const int arena = st * a.stage_bytes + wo[0];
             const int ocol = out_off0 + ot * out_bytes + out_col;
             const uint32_t ocol_s = smem_s + (uint32_t)ocol;
             const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
             const int slot_tab = tab + tab_slots<R>();
-            const int win0 = arena + (U ? (int)h0.w : 0);
+            const int win0 = arena + (uni ? (int)h0.w : 0);
             if (CPT == 2) {
-                const int win1 = st * a.stage_bytes + wo[CPT - 1] + (U ? (int)h0.w : 0);
-                if (U) sweep_c3x2<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), smem_s + (uint32_t)(win1 & ~3), (uint32_t)win0 << 3, (uint32_t)win1 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
+                const int win1 = st * a.stage_bytes + wo[CPT - 1] + (uni ? (int)h0.w : 0);
+                if (uni) sweep_c3x2<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), smem_s + (uint32_t)(win1 & ~3), (uint32_t)win0 << 3, (uint32_t)win1 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
                 else sweep_c3x2<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)win1, smem_s + (uint32_t)slot_tab, 0u, 0u, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
             } else if (C == 3) {
-                if (U) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
+                if (uni) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
                 else sweep_c3<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, wB, rnd);
             } else if (C == 1) {
-                if (U) sweep_c1<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, rnd);
+                if (uni) sweep_c1<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, rnd);
                 else sweep_c1<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, rnd);
             } else {
                 int rp = tab + kTabRows;
@@ -759,7 +830,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 for (int s = -1; s < n_slots; ++s) {
                     if (s >= 0) {
                         uint32_t h[C];
-                        const int win = U ? win0 + s * (int)h0.z : arena + (int)ld32(slot_tab + 4 * s);
+                        const int win = uni ? win0 + s * (int)h0.z : arena + (int)ld32(slot_tab + 4 * s);
                         hblend_row<C>(win & ~3, (uint32_t)win << 3, wA, wB, h);
 #pragma unroll
                         for (int k = 0; k < C; ++k) P[k] = __byte_perm(P[k], h[k], 0x5432);
@@ -782,44 +853,38 @@ remap_u8_stream_kernel(const StreamArgs a) {
     }
 }
 
+// Strip geometry of one image: as few, equal strips as possible, a multiple of 16 columns so that
+// strip boundaries keep the 16-byte phase of a row.
+struct StripPlan { int n_strips, strip_cols; };
+inline StripPlan plan_strips(int Wo, int max_cols_) {
+    StripPlan p;
+    p.n_strips = (Wo + max_cols_ - 1) / max_cols_;
+    p.strip_cols = (((Wo + p.n_strips - 1) / p.n_strips) + 15) & ~15;
+    p.n_strips = (Wo + p.strip_cols - 1) / p.strip_cols;
+    return p;
+}
+
+// Shared-memory geometry for strips of at most `cols` columns, and the launch itself.
 template <int C, int R, int CPT>
-int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int Ho, int Wo,
-                  const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
-    // CPT output columns per consumer thread; as few, equal strips as possible
-    constexpr int kMaxCols = max_cols(CPT);
-    StreamArgs a;
-    a.n_strips = (Wo + kMaxCols - 1) / kMaxCols;
-    // equal strips, a multiple of 16 columns so that strip boundaries keep the 16-byte phase of a row
-    a.strip_cols = (((Wo + a.n_strips - 1) / a.n_strips) + 15) & ~15;
-    a.n_strips = (Wo + a.strip_cols - 1) / a.strip_cols;
-    const int Wt = (a.strip_cols + 32 * CPT - 1) / (32 * CPT) * (32 * CPT);   // columns covered by the consumer threads
-    a.src = src; a.dst = dst; a.map_x = map_x; a.map_y = map_y;
-    a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.map_div = map_div;
-    a.n_rowtiles = (Ho + R - 1) / R;
-    const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
-    if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
-    a.total_tiles = (int)total;
+int launch_kernel(StreamArgs& a, int cols, cudaStream_t st) {
+    const int Wt = (cols + 32 * CPT - 1) / (32 * CPT) * (32 * CPT);   // columns covered by the consumer threads
     a.rnd = 512;
     {
         const char* e = getenv("ATTWARP_REMAP_DBG");
         a.dbg = e ? atoi(e) : 0;
     }
-    const int cols_t = Wo < a.strip_cols ? Wo : a.strip_cols;   // widest strip actually processed
-    a.out_pitch = (cols_t * C + 15 + 15) & ~15;            // + the 16-byte phase of the destination
+    a.out_pitch = (cols * C + 15 + 15) & ~15;              // + the 16-byte phase of the destination
     // an arena holds R + 2 source rows at unit scale (first chunk of a segment: R + 1)
-    const int unit_pitch = (((cols_t + 1) * C + 30) & ~15) + 16;
+    const int unit_pitch = (((cols + 1) * C + 30) & ~15) + 16;
     a.stage_bytes = ((R + 2) * unit_pitch + 127) & ~127;
     const size_t smem_bytes = (size_t)kSrcStages * (a.stage_bytes + tab_bytes<R>()) +
-                              (size_t)kOutStages * ((size_t)R * a.out_pitch + 16) +
+                              (size_t)kOutStages * ((size_t)R * a.out_pitch + 32) +
                               2 * (kSrcStages + kOutStages) * sizeof(uint64_t);
-    // uniform phase: every source row of every image starts at the same 16-byte phase
-    const bool uniform = ((W * C) & 15) == 0 && (((int64_t)H * W * C) & 15) == 0;
-    auto kern = uniform ? remap_u8_stream_kernel<C, R, true, CPT> : remap_u8_stream_kernel<C, R, false, CPT>;
+    auto kern = remap_u8_stream_kernel<C, R, CPT>;
     const int threads = Wt / CPT + kRoleThreads;
     // the opt-in and the occupancy query cost microseconds of host time: once per configuration
     struct Cfg { size_t smem; int threads, dev, occ; };
-    static thread_local Cfg cache[2] = {{0, 0, -1, 0}, {0, 0, -1, 0}};
-    Cfg& c = cache[uniform ? 1 : 0];
+    static thread_local Cfg c = {0, 0, -1, 0};
     int dev = 0;
     AW_CUDA(cudaGetDevice(&dev));
     if (c.smem != smem_bytes || c.threads != threads || c.dev != dev) {
@@ -828,12 +893,64 @@ int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int
         AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
         c = Cfg{smem_bytes, threads, dev, o};
     }
-    const int occ = c.occ;
-    if (occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
-    const int64_t cap = (int64_t)sm_count() * occ;
-    const int grid = (int)(total < cap ? total : cap);
+    if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
+    const int64_t cap = (int64_t)sm_count() * c.occ;
+    const int grid = (int)(a.total_tiles < cap ? a.total_tiles : cap);
     kern<<<grid, threads, smem_bytes, st>>>(a);
     return check_launch("remap_u8_stream_kernel");
+}
+
+template <int C, int R, int CPT>
+int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int Ho, int Wo,
+                  const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
+    StreamArgs a;
+    const StripPlan sp = plan_strips(Wo, max_cols(CPT));
+    a.n_strips = sp.n_strips;
+    a.strip_cols = sp.strip_cols;
+    a.src = src; a.dst = dst; a.map_x = map_x; a.map_y = map_y;
+    a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.map_div = map_div;
+    a.n_rowtiles = (Ho + R - 1) / R;
+    a.imgs = nullptr;
+    a.n_img = n_img;
+    const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
+    if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
+    a.total_tiles = (int)total;
+    return launch_kernel<C, R, CPT>(a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
+}
+
+// Ragged batch, step 1: strip plan and tile prefix of host[0..n) (host[n] only carries the total), upload.
+template <int R, int CPT>
+int ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_table, cudaStream_t st) {
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        const StripPlan sp = plan_strips(host[i].Wo, max_cols(CPT));
+        host[i].n_strips = sp.n_strips;
+        host[i].strip_cols = sp.strip_cols;
+        host[i].n_rowtiles = (host[i].Ho + R - 1) / R;
+        host[i].tile_begin = (int)total;
+        total += (int64_t)sp.n_strips * host[i].n_rowtiles;
+        if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
+    }
+    host[n] = RaggedImage{};
+    host[n].tile_begin = (int)total;
+    AW_CUDA(cudaMemcpyAsync(dev_table, host, sizeof(RaggedImage) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    return ATTWARP_OK;
+}
+// Step 2: the launch.
+template <int C, int R, int CPT>
+int ragged_run(const RaggedImage* host, int n, const RaggedImage* dev_table, cudaStream_t st) {
+    int max_strip = 0;
+    for (int i = 0; i < n; ++i) {
+        const int cols = host[i].Wo < host[i].strip_cols ? host[i].Wo : host[i].strip_cols;
+        if (cols > max_strip) max_strip = cols;
+    }
+    StreamArgs a{};
+    a.map_div = 1;
+    a.imgs = dev_table;
+    a.n_img = n;
+    a.total_tiles = host[n].tile_begin;
+    if (a.total_tiles == 0) return ATTWARP_OK;
+    return launch_kernel<C, R, CPT>(a, max_strip, st);
 }
 
 // ATTWARP_REMAP_CPT=1 forces one column per thread for C = 3 (A/B comparisons).
@@ -859,6 +976,22 @@ int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, 
             if (columns_per_thread_c3() == 2) return launch_stream<3, AW_ROWS, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
             return launch_stream<3, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
         case 4: return launch_stream<4, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        default: return fail(ATTWARP_ERR_UNSUPPORTED, "remap supports C in {1,3,4} (got %d)", C);
+    }
+}
+
+// Ragged batch of HWC uint8 images (every H, W >= 2), see common.cuh.
+int launch_remap_u8_stream_ragged_prepare(RaggedImage* h, int n, int C, RaggedImage* d, cudaStream_t st) {
+    if (C == 3 && columns_per_thread_c3() == 2) return ragged_prepare<AW_ROWS, 2>(h, n, d, st);
+    return ragged_prepare<AW_ROWS, 1>(h, n, d, st);
+}
+int launch_remap_u8_stream_ragged_run(const RaggedImage* h, int n, int C, const RaggedImage* d, cudaStream_t st) {
+    switch (C) {
+        case 1: return ragged_run<1, AW_ROWS, 1>(h, n, d, st);
+        case 3:
+            if (columns_per_thread_c3() == 2) return ragged_run<3, AW_ROWS, 2>(h, n, d, st);
+            return ragged_run<3, AW_ROWS, 1>(h, n, d, st);
+        case 4: return ragged_run<4, AW_ROWS, 1>(h, n, d, st);
         default: return fail(ATTWARP_ERR_UNSUPPORTED, "remap supports C in {1,3,4} (got %d)", C);
     }
 }

@@ -241,3 +241,46 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
     if return_aux:
         return out, tok.view(B, gh, gw), map_x, map_y
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# ragged batches (mixed resolutions, BASELINE configs[3])
+# --------------------------------------------------------------------------------------------
+def warp_ragged_from_tokens(tok: torch.Tensor, images, out_sizes=None, grid_hw=None,
+                            transform="identity", exp_scale=1.0, exp_divisor=1.0,
+                            apply_inverse=False, outs=None):
+    """Stages 2-5 for n images of different shapes with ONE launch per stage.
+
+    tok     [n, gh, gw] (or [n, gh*gw] with ``grid_hw``) float32 token maps on the device
+    images  sequence of n uint8 HWC tensors [H_i, W_i, C] on the same device
+    out_sizes  sequence of (Ho_i, Wo_i), default = input sizes
+    Returns the list of warped images.  Replaces the per-image loops of AGW/main.py:395-533 and
+    AGW/main_batched.py:243-287 (one warp_image_by_attention call per image)."""
+    lib = load()
+    n = len(images)
+    assert n > 0 and tok.shape[0] == n
+    if tok.dim() == 3:
+        gh, gw = tok.shape[1], tok.shape[2]
+    else:
+        gh, gw = grid_hw
+    tok = tok.reshape(n, gh * gw).to(torch.float32).contiguous()
+    require_cuda(tok, *images)
+    dev = tok.device
+    Cc = images[0].shape[2]
+    imgs = [im.contiguous() for im in images]
+    if out_sizes is None:
+        out_sizes = [(im.shape[0], im.shape[1]) for im in imgs]
+    if outs is None:
+        outs = [torch.empty(ho, wo, Cc, dtype=torch.uint8, device=dev) for ho, wo in out_sizes]
+    table = (_lib.RaggedImage * n)()
+    for i, (im, o, (ho, wo)) in enumerate(zip(imgs, outs, out_sizes)):
+        assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == Cc and im.device == dev
+        assert o.dtype == torch.uint8 and tuple(o.shape) == (ho, wo, Cc) and o.is_contiguous()
+        table[i] = _lib.RaggedImage(im.data_ptr(), o.data_ptr(), im.shape[0], im.shape[1], ho, wo)
+    tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
+    wsb = lib.attwarp_ragged_workspace_bytes(table, n)
+    ws = _workspace(wsb, dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), n, gh, gw, table, Cc, C.byref(tp),
+                                                  ptr(ws), ws.numel(), current_stream(dev)))
+    return outs

@@ -169,6 +169,31 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
                                        size_t workspace_bytes, float* tok_out, float* map_x,
                                        float* map_y, void* const* stage_events, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ragged batches (BASELINE configs[3]: mixed resolutions): n independent images of different
+ * shapes in ONE launch per stage.  Replaces the per-image loop of the reference drivers
+ * (AGW/main.py:395-533 and AGW/main_batched.py:243-287 call save_warped_image ->
+ * warp_image_by_attention once per image).
+ *
+ * images    : HOST array of n descriptors; src/dst are DEVICE pointers to dense HWC uint8 images
+ *             ([H][W][C] -> [Ho][Wo][C]) that must stay valid until the stream has run the call
+ * tok       : device [n][gh*gw] float32 token maps (stage-1 output), index-upsampled to each
+ *             image's H x W exactly like attwarp_maps_from_tokens
+ * workspace : attwarp_ragged_workspace_bytes(images, n) bytes of device scratch (descriptor table
+ *             + the per-image map rows)
+ */
+typedef struct attwarp_ragged_image {
+    const void* src;
+    void* dst;
+    int32_t H, W, Ho, Wo;
+} attwarp_ragged_image;
+
+size_t attwarp_ragged_workspace_bytes(const attwarp_ragged_image* images, int n);
+int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
+                                    const attwarp_ragged_image* images, int C,
+                                    const attwarp_transform_params* tp, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* attwarp_warp_image_host: the whole of warp_image_by_attention (AGW/new_method.py:198-283) for
  * ONE image with HOST buffers, as the NumPy signature implies: H2D, stages 2b-5 on the device,
  * D2H, blocking.  image_host: uint8/float32 [H][W][C]; att_host: U8/F32/F64 [H][W];

@@ -1,0 +1,94 @@
+"""GPU parity of the ragged-batch driver (BASELINE configs[3]: mixed resolutions, one launch per
+stage) against the oracle image by image, and against the uniform-batch kernels."""
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, need_gpu
+from oracle import numpy_path as ON
+
+pytestmark = pytest.mark.gpu
+
+
+def _tokens(n, g, seed):
+    rng = np.random.default_rng(seed)
+    t = rng.random((n, g, g)) ** 3
+    return (t / t.sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+
+
+def _check(imgs, toks, out_sizes, outs, transform, max_off=1e-3):
+    for im, tk, (ho, wo), o in zip(imgs, toks, out_sizes, outs):
+        full = ON.upsample_tokens_nearest(tk, im.shape[0], im.shape[1])
+        ref = ON.warp_image_by_attention(im, full, wo, ho, transform)
+        diff = np.abs(o.cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1, f"{im.shape}->{(ho, wo)}: {diff.max()} LSB"
+        assert (diff != 0).mean() <= max_off
+
+
+@pytest.mark.parametrize("C,transform", [(3, "identity"), (3, "sqrt"), (1, "identity"), (4, "square")])
+def test_ragged_vs_oracle(C, transform):
+    """Sizes chosen to hit: rows that are / are not multiples of 16 bytes, one and several strips,
+    strips narrower than a warp, output sizes different from the input, odd sizes."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(11 + C)
+    sizes = [(224, 224), (336, 336), (97, 53), (500, 333), (240, 400), (64, 1000), (701, 18), (336, 336)]
+    out_sizes = [(224, 224), (500, 500), (64, 200), (500, 333), (300, 800), (64, 1000), (350, 40), (336, 336)]
+    imgs = [rng.integers(0, 256, (h, w, C), dtype=np.uint8) for h, w in sizes]
+    toks = _tokens(len(sizes), 24, seed=5)
+    outs = ops.warp_ragged_from_tokens(dev(toks), [dev(i) for i in imgs], out_sizes, transform=transform)
+    torch.cuda.synchronize()
+    _check(imgs, toks, out_sizes, outs, transform)
+
+
+def test_ragged_matches_uniform_batch():
+    """The same images through the ragged table and through the uniform-batch entry: bit-equal."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(3)
+    n, H, W = 9, 336, 336
+    imgs = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    toks = _tokens(n, 24, seed=9)
+    d_imgs = dev(imgs)
+    mx, my = ops.maps_from_tokens(dev(toks), (H, W), (H, W))
+    uni = ops.remap_bilinear(d_imgs, mx, my, "hwc")
+    rag = ops.warp_ragged_from_tokens(dev(toks), [d_imgs[i] for i in range(n)])
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert torch.equal(uni[i], rag[i])
+
+
+def test_ragged_degenerate_and_errors():
+    need_gpu()
+    from attwarp_b200 import ops
+    from attwarp_b200._lib import AttWarpError
+    rng = np.random.default_rng(4)
+    sizes = [(1, 50), (40, 40), (30, 1)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    toks = _tokens(3, 8, seed=2)
+    out_sizes = [(4, 60), (40, 40), (33, 5)]
+    outs = ops.warp_ragged_from_tokens(dev(toks), [dev(i) for i in imgs], out_sizes)
+    torch.cuda.synchronize()
+    _check(imgs, toks, out_sizes, outs, "identity", max_off=1.0)
+    with pytest.raises(AttWarpError):
+        ops.warp_ragged_from_tokens(dev(toks), [dev(np.zeros((8, 8, 2), np.uint8))] * 3)
+
+
+def test_ragged_mixed_resolution_c4_sample():
+    """A slice of BASELINE configs[3] (sides uniform in [224, 2048], 24x24 token maps): every
+    image against the oracle, plus determinism of a second run."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(1237)
+    sides = rng.integers(224, 2049, size=12)
+    imgs = [rng.integers(0, 256, (int(s), int(s), 3), dtype=np.uint8) for s in sides]
+    toks = _tokens(len(sides), 24, seed=1237)
+    d_imgs = [dev(i) for i in imgs]
+    outs = ops.warp_ragged_from_tokens(dev(toks), d_imgs)
+    again = ops.warp_ragged_from_tokens(dev(toks), d_imgs)
+    torch.cuda.synchronize()
+    sizes = [(int(s), int(s)) for s in sides]
+    _check(imgs, toks, sizes, outs, "identity")
+    for a, b in zip(outs, again):
+        assert torch.equal(a, b)
