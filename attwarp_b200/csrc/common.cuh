@@ -39,8 +39,11 @@ struct RaggedImage {
     const float* map_x;      // Wo floats
     const float* map_y;      // Ho floats
     int H, W, Ho, Wo;
-    int n_strips, strip_cols, n_rowtiles;   // stage-5 strip plan (filled in by the stage-5 launcher)
-    int tile_begin;          // index of the image's first tile; its tiles are strip-major
+    // stage-5 plan (filled in by the stage-5 launcher): strips, row tiles, and the image's position in
+    // the batch-wide cost axis that CTAs split evenly (a tile weighs tile_units units ~ its consumer warps)
+    int strips_units;        // n_strips | tile_units << 16
+    int strip_cols, n_rowtiles;
+    int unit_begin;          // first cost unit of the image; its tiles are strip-major
 };
 static_assert(sizeof(RaggedImage) == 64, "descriptor layout");
 

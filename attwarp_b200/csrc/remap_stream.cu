@@ -60,9 +60,10 @@ using namespace ptx;
 #endif
 constexpr int kSrcStages = AW_SRC_STAGES;          // source-row stages (chunks whose loads are in flight) per CTA
 constexpr int kOutStages = AW_OUT_STAGES;          // output tiles per CTA
-// output columns per strip: 352 at one column per thread (11 + 2 warps x 3 CTAs keep 48 registers),
-// 384 at two columns per thread (6 + 2 warps)
-constexpr int max_cols(int cpt) { return cpt == 2 ? 384 : 352; }
+// output columns per strip: 352, the widest strip whose stages let three CTAs share an SM.  One column per
+// thread: 11 + 2 warps (x 3 CTAs keeps 48 registers); two columns per thread: 6 + 2 warps.
+constexpr int max_cols(int) { return 352; }
+constexpr int max_threads(int cpt) { return (max_cols(cpt) + 32 * cpt - 1) / (32 * cpt) * 32 + 64; }
 constexpr int kRoleThreads = 64;       // producer warp + store warp
 
 // Shared memory is addressed as byte offsets from the one dynamic array below.
@@ -391,10 +392,10 @@ struct StreamArgs {
     int map_div;             // CHW planes share their image's maps
     int n_strips, n_rowtiles;
     int strip_cols;          // output columns per strip (<= consumer threads x CPT)
-    // ragged batch: per-image descriptors, n_img + 1 entries (the last one only carries tile_begin)
+    // ragged batch: per-image descriptors, n_img + 1 entries (the last one only carries unit_begin)
     const RaggedImage* imgs;
     int n_img;
-    int total_tiles;
+    int total_units;         // length of the cost axis (uniform batch: one unit per tile)
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int out_pitch;           // bytes per row of an output tile
     int rnd;                 // 512, the rounding constant of the vertical blend (kept out of the
@@ -408,7 +409,7 @@ struct View {
     uint8_t* dst;
     const float* mx;
     const float* my;
-    int H, W, Ho, Wo, n_strips, strip_cols, n_rowtiles, tile_begin;
+    int H, W, Ho, Wo, n_strips, strip_cols, n_rowtiles, unit_begin, tile_units;
 };
 template <int C>
 __device__ __forceinline__ View get_view(const StreamArgs& a, int img) {
@@ -421,7 +422,8 @@ __device__ __forceinline__ View get_view(const StreamArgs& a, int img) {
         v.mx = reinterpret_cast<const float*>(((uint64_t)p1.y << 32) | p1.x);
         v.my = reinterpret_cast<const float*>(((uint64_t)p1.w << 32) | p1.z);
         v.H = (int)p2.x; v.W = (int)p2.y; v.Ho = (int)p2.z; v.Wo = (int)p2.w;
-        v.n_strips = (int)p3.x; v.strip_cols = (int)p3.y; v.n_rowtiles = (int)p3.z; v.tile_begin = (int)p3.w;
+        v.n_strips = (int)(p3.x & 0xffffu); v.tile_units = (int)(p3.x >> 16);
+        v.strip_cols = (int)p3.y; v.n_rowtiles = (int)p3.z; v.unit_begin = (int)p3.w;
     } else {
         const int mrow = img / a.map_div;
         v.src = a.src + (int64_t)img * a.H * a.W * C;
@@ -430,7 +432,8 @@ __device__ __forceinline__ View get_view(const StreamArgs& a, int img) {
         v.my = a.map_y + (int64_t)mrow * a.Ho;
         v.H = a.H; v.W = a.W; v.Ho = a.Ho; v.Wo = a.Wo;
         v.n_strips = a.n_strips; v.strip_cols = a.strip_cols; v.n_rowtiles = a.n_rowtiles;
-        v.tile_begin = img * a.n_strips * a.n_rowtiles;
+        v.unit_begin = img * a.n_strips * a.n_rowtiles;
+        v.tile_units = 1;
     }
     return v;
 }
@@ -462,7 +465,7 @@ constexpr int kTabStore = 32, kTabStrip = 48;
 // The two rings are decoupled so that the loads of chunk c + kSrcStages start as soon as the
 // consumers leave chunk c, without waiting for its tile to be shipped.
 template <int C, int R, int CPT>
-__global__ void __launch_bounds__(max_cols(CPT) / CPT + kRoleThreads, CPT == 2 ? AW_MIN_CTAS : 3)
+__global__ void __launch_bounds__(max_threads(CPT), CPT == 2 ? AW_MIN_CTAS : 3)
 remap_u8_stream_kernel(const StreamArgs a) {
     static_assert(CPT == 1 || (CPT == 2 && C == 3), "two columns per thread are implemented for C = 3");
     const int Wt = ((int)blockDim.x - kRoleThreads) * CPT;
@@ -492,9 +495,9 @@ remap_u8_stream_kernel(const StreamArgs a) {
     }
     __syncthreads();
 
-    // contiguous, balanced range of tiles for this CTA
-    const int t0 = (int)(((int64_t)a.total_tiles * blockIdx.x) / gridDim.x);
-    const int t1 = (int)(((int64_t)a.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+    // contiguous, balanced range of the cost axis for this CTA: it owns the tiles that START inside it
+    const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
+    const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
 
     // warp-uniform role split (the shuffle tells the compiler the branch does not diverge)
     const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -507,34 +510,38 @@ remap_u8_stream_kernel(const StreamArgs a) {
             // =========================== producer warp =========================================
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
-            int t = t0;
-            int img = -1;
-            while (t < t1) {
-                // ---- segment: the tiles [t, t_end) of one (image, strip) ----------------------
-                if (a.imgs == nullptr) {
-                    img = t / (a.n_strips * a.n_rowtiles);
-                } else if (img < 0) {
-                    // first segment: the last image whose first tile is <= t (32-ary search)
-                    int lo = 0, hi = a.n_img;                          // answer in [lo, hi)
-                    while (hi - lo > 1) {
-                        const int step = (hi - lo + 31) / 32;
-                        const int probe = min(lo + (lane + 1) * step, hi);
-                        const bool le = probe < hi && __ldg(&a.imgs[probe].tile_begin) <= t;
-                        const int k = __popc(__ballot_sync(0xffffffffu, le));   // probes are monotone
-                        const int nlo = lo + k * step;
-                        hi = min(lo + (k + 1) * step, hi);
-                        lo = nlo;
-                    }
-                    img = lo;
-                } else {
-                    while (__ldg(&a.imgs[img + 1].tile_begin) <= t) ++img;
+            // first image: the last one whose first unit is <= u0 (32-ary search over the table)
+            int img;
+            if (a.imgs == nullptr) {
+                img = u0 / (a.n_strips * a.n_rowtiles);
+            } else {
+                int lo = 0, hi = a.n_img;                              // answer in [lo, hi)
+                while (hi - lo > 1) {
+                    const int step = (hi - lo + 31) / 32;
+                    const int probe = min(lo + (lane + 1) * step, hi);
+                    const bool le = probe < hi && __ldg(&a.imgs[probe].unit_begin) <= u0;
+                    const int k = __popc(__ballot_sync(0xffffffffu, le));       // probes are monotone
+                    const int nlo = lo + k * step;
+                    hi = min(lo + (k + 1) * step, hi);
+                    lo = nlo;
                 }
-                const View v = get_view<C>(a, img);
+                img = lo;
+            }
+            View v = get_view<C>(a, img);
+            int local = (u0 - v.unit_begin + v.tile_units - 1) / v.tile_units;   // first tile starting at >= u0
+            for (;;) {
+                if (local >= v.n_strips * v.n_rowtiles) {              // next image
+                    if (++img >= a.n_img) break;
+                    v = get_view<C>(a, img);
+                    local = 0;
+                }
+                if (v.unit_begin + local * v.tile_units >= u1) break;
+                // ---- segment: the tiles [local, local_end) of one (image, strip) ----------------
                 const int H = v.H, W = v.W, Ho = v.Ho, Wo = v.Wo;
-                const int local = t - v.tile_begin;
                 const int strip = local / v.n_rowtiles, rt = local % v.n_rowtiles;
-                const int t_end = min(t1, v.tile_begin + (strip + 1) * v.n_rowtiles);
-                const int y_end = min(Ho, (rt + (t_end - t)) * R);
+                const int mine_end = (u1 - v.unit_begin + v.tile_units - 1) / v.tile_units;   // tiles starting before u1
+                const int local_end = min((strip + 1) * v.n_rowtiles, mine_end);
+                const int y_end = min(Ho, (rt + (local_end - local)) * R);
                 const int x_first = strip * v.strip_cols;
                 const int ncols = min(v.strip_cols, Wo - x_first);
                 const uint8_t* simg = v.src;
@@ -665,7 +672,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                     y_cur += max(n_rows, 1);
                     if (++st == kSrcStages) { st = 0; ph ^= 1u; }
                 }
-                t = t_end;
+                local = local_end;
             }
             // terminator
             mbar_wait(sfree_s + 8u * st, ph ^ 1u);
@@ -895,7 +902,7 @@ int launch_kernel(StreamArgs& a, int cols, cudaStream_t st) {
     }
     if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
     const int64_t cap = (int64_t)sm_count() * c.occ;
-    const int grid = (int)(a.total_tiles < cap ? a.total_tiles : cap);
+    const int grid = (int)(a.total_units < cap ? a.total_units : cap);
     kern<<<grid, threads, smem_bytes, st>>>(a);
     return check_launch("remap_u8_stream_kernel");
 }
@@ -914,25 +921,30 @@ int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int
     a.n_img = n_img;
     const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
     if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
-    a.total_tiles = (int)total;
+    a.total_units = (int)total;
     return launch_kernel<C, R, CPT>(a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
 }
 
-// Ragged batch, step 1: strip plan and tile prefix of host[0..n) (host[n] only carries the total), upload.
+// Ragged batch, step 1: strip plan and cost prefix of host[0..n) (host[n] only carries the total), upload.
+// A tile weighs as many units as it keeps consumer warps busy, so that CTAs splitting the unit axis evenly
+// get even work whatever the mix of strip widths.
 template <int R, int CPT>
 int ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_table, cudaStream_t st) {
     int64_t total = 0;
     for (int i = 0; i < n; ++i) {
         const StripPlan sp = plan_strips(host[i].Wo, max_cols(CPT));
-        host[i].n_strips = sp.n_strips;
+        const int cols = host[i].Wo < sp.strip_cols ? host[i].Wo : sp.strip_cols;
+        const int units = (cols + 32 * CPT - 1) / (32 * CPT);
+        if (sp.n_strips > 0xffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: image %d is too wide", i);
+        host[i].strips_units = sp.n_strips | (units << 16);
         host[i].strip_cols = sp.strip_cols;
         host[i].n_rowtiles = (host[i].Ho + R - 1) / R;
-        host[i].tile_begin = (int)total;
-        total += (int64_t)sp.n_strips * host[i].n_rowtiles;
+        host[i].unit_begin = (int)total;
+        total += (int64_t)sp.n_strips * host[i].n_rowtiles * units;
         if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
     }
     host[n] = RaggedImage{};
-    host[n].tile_begin = (int)total;
+    host[n].unit_begin = (int)total;
     AW_CUDA(cudaMemcpyAsync(dev_table, host, sizeof(RaggedImage) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     return ATTWARP_OK;
 }
@@ -948,8 +960,8 @@ int ragged_run(const RaggedImage* host, int n, const RaggedImage* dev_table, cud
     a.map_div = 1;
     a.imgs = dev_table;
     a.n_img = n;
-    a.total_tiles = host[n].tile_begin;
-    if (a.total_tiles == 0) return ATTWARP_OK;
+    a.total_units = host[n].unit_begin;
+    if (a.total_units == 0) return ATTWARP_OK;
     return launch_kernel<C, R, CPT>(a, max_strip, st);
 }
 

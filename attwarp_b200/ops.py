@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -17,6 +18,10 @@ from ._lib import (LAYOUT_CHW, LAYOUT_HWC, TORCH_DTYPE_IDS, check, current_strea
                    make_transform, ptr, require_cuda)
 
 _ws_cache = {}
+
+# attwarp_ragged_image (include/attwarp.h)
+_RAGGED_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("H", np.int32), ("W", np.int32),
+                          ("Ho", np.int32), ("Wo", np.int32)])
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -272,15 +277,24 @@ def warp_ragged_from_tokens(tok: torch.Tensor, images, out_sizes=None, grid_hw=N
         out_sizes = [(im.shape[0], im.shape[1]) for im in imgs]
     if outs is None:
         outs = [torch.empty(ho, wo, Cc, dtype=torch.uint8, device=dev) for ho, wo in out_sizes]
-    table = (_lib.RaggedImage * n)()
-    for i, (im, o, (ho, wo)) in enumerate(zip(imgs, outs, out_sizes)):
-        assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == Cc and im.device == dev
-        assert o.dtype == torch.uint8 and tuple(o.shape) == (ho, wo, Cc) and o.is_contiguous()
-        table[i] = _lib.RaggedImage(im.data_ptr(), o.data_ptr(), im.shape[0], im.shape[1], ho, wo)
+    # descriptor table as one structured array (a ctypes struct per image costs ~3 us each)
+    table = np.empty(n, dtype=_RAGGED_DTYPE)
+    table["src"] = [im.data_ptr() for im in imgs]
+    table["dst"] = [o.data_ptr() for o in outs]
+    table["H"] = [im.shape[0] for im in imgs]
+    table["W"] = [im.shape[1] for im in imgs]
+    table["Ho"] = [hw[0] for hw in out_sizes]
+    table["Wo"] = [hw[1] for hw in out_sizes]
+    for im, o, (ho, wo) in zip(imgs, outs, out_sizes):
+        if (im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != Cc or im.device != dev
+                or o.dtype != torch.uint8 or tuple(o.shape) != (ho, wo, Cc) or not o.is_contiguous()):
+            raise ValueError("warp_ragged_from_tokens: images must be uint8 HWC tensors with the same channel "
+                             "count on one device, outputs contiguous [Ho, Wo, C]")
+    table_p = table.ctypes.data_as(C.c_void_p)           # `table` stays alive until the call returns
     tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
-    wsb = lib.attwarp_ragged_workspace_bytes(table, n)
+    wsb = lib.attwarp_ragged_workspace_bytes(table_p, n)
     ws = _workspace(wsb, dev)
     with torch.cuda.device(dev):
-        check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), n, gh, gw, table, Cc, C.byref(tp),
+        check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), n, gh, gw, table_p, Cc, C.byref(tp),
                                                   ptr(ws), ws.numel(), current_stream(dev)))
     return outs

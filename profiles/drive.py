@@ -36,7 +36,7 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["remap", "agg", "maps"])
+    ap.add_argument("what", choices=["remap", "agg", "maps", "ragged"])
     ap.add_argument("--side", type=int, default=336)
     ap.add_argument("--out-side", type=int, default=0)
     ap.add_argument("--batch", type=int, default=256)
@@ -49,6 +49,18 @@ def main():
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(0)
     B, S, G = a.batch, a.side, a.grid
+    if a.what == "ragged":
+        # BASELINE configs[3] slice: sides uniform in [224, 2048], 24x24 token maps, stages 2-5
+        import numpy as np
+        sides = np.random.default_rng(1237).integers(224, 2049, size=B)
+        imgs = [torch.randint(0, 256, (int(s), int(s), a.C), device=dev, dtype=torch.uint8, generator=g) for s in sides]
+        outs = [torch.empty_like(i) for i in imgs]
+        tok = torch.rand(B, G, G, device=dev, generator=g) ** 3
+        tok = tok / tok.sum(dim=(1, 2), keepdim=True)
+        ts = timed(lambda: ops.warp_ragged_from_tokens(tok, imgs, outs=outs), a.iters)
+        by = 2 * sum(i.numel() for i in imgs)
+        print(f"ragged x{B} ({by / 2e6:.0f} MB in): us {[round(t, 1) for t in ts]}  GB/s {[round(by / t / 1e3, 1) for t in ts]}")
+        return
     So = a.out_side or S
     if a.what in ("remap", "maps"):
         tok = torch.rand(B, G, G, device=dev, generator=g) ** 3
