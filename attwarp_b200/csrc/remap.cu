@@ -6,6 +6,8 @@
 // The per-pixel arithmetic is in warp_math.h (quantise_coord / bilinear_u8 / bilinear_f32).
 //
 // Kernels
+//   remap_f32_rows_kernel float32 images, any layout / channel count: one thread per output column,
+//                         walking a tile of rows with the tapped source rows carried in registers.
 //   remap_direct_kernel   any dtype / layout / channel count; one thread per output pixel,
 //                         taps gathered straight from global memory through L1/L2.  Baseline and
 //                         fallback for shapes the streaming kernel (remap_stream.cu) does not cover.
@@ -64,6 +66,108 @@ remap_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int H
     }
 }
 
+// ---- float32 images: one thread per output column (x channel), walking a tile of output rows --------
+// Each thread fixes its two horizontal taps and weights once and then walks kRowsF32 output rows of
+// its plane: the separable map makes every thread of the CTA tap the same two source rows, so the row
+// addresses and the vertical weights come from a small shared table, and a source row that the next
+// output row taps again (as its upper or lower row) stays in registers -- two loads per NEW source row
+// and thread instead of four per output.  Loads of neighbouring threads are neighbouring floats
+// (coalesced through L1), stores are fully coalesced.  Arithmetic is OpenCV's float path exactly:
+// w = fl32(wy * wx), ((p00 w00 + p01 w01) + p10 w10) + p11 w11 without FMA contraction.
+constexpr int kThreadsF32 = 256;
+constexpr int kRowsF32 = 32;
+constexpr int kColsF32 = 2;      // output columns per thread (independent chains)
+
+// ELEMS: floats per pixel that are interleaved in memory (HWC: C, planar: 1)
+template <bool HWC>
+__global__ void __launch_bounds__(kThreadsF32)
+remap_f32_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W, int Ho,
+                      int Wo, int map_div, const float* __restrict__ map_x, const float* __restrict__ map_y) {
+    __shared__ int4 rowtab[kRowsF32];      // {ya, yb, bits(1 - fy), bits(fy)}
+    const int E = HWC ? C : 1;             // interleaved floats per pixel
+    const int plane = blockIdx.z;
+    const int mrow = plane / map_div;
+    const int y0 = blockIdx.y * kRowsF32;
+    const int nrows = min(kRowsF32, Ho - y0);
+    if (threadIdx.x < nrows) {
+        const int sy = quantise_coord(__ldg(map_y + (int64_t)mrow * Ho + y0 + threadIdx.x));
+        const int ay = sy & 31;
+        const float fy = fmul_nofma((float)ay, 1.0f / 32.0f);
+        rowtab[threadIdx.x] = make_int4(clampi(sy >> 5, 0, H - 1), clampi((sy >> 5) + 1, 0, H - 1),
+                                        __float_as_int(fadd_nofma(1.0f, -fy)), __float_as_int(fy));
+    }
+    const int64_t src_pitch = (int64_t)W * E, dst_pitch = (int64_t)Wo * E;
+    const float* sp = src + (int64_t)plane * H * src_pitch;
+    float* dp = dst + (int64_t)plane * Ho * dst_pitch + (int64_t)y0 * dst_pitch;
+    const int n_e = Wo * E;                // floats per output row
+    int s0[kColsF32], s1[kColsF32], e_out[kColsF32];
+    float wx0[kColsF32], wx1[kColsF32];
+    bool valid[kColsF32];
+#pragma unroll
+    for (int j = 0; j < kColsF32; ++j) {
+        const int e = (blockIdx.x * kColsF32 + j) * kThreadsF32 + threadIdx.x;
+        valid[j] = e < n_e;
+        e_out[j] = e;
+        const int x = valid[j] ? e / E : 0, c = valid[j] ? e - x * E : 0;
+        const int sx = quantise_coord(__ldg(map_x + (int64_t)mrow * Wo + x));
+        const float fx = fmul_nofma((float)(sx & 31), 1.0f / 32.0f);
+        wx0[j] = fadd_nofma(1.0f, -fx);
+        wx1[j] = fx;
+        s0[j] = clampi(sx >> 5, 0, W - 1) * E + c;
+        s1[j] = clampi((sx >> 5) + 1, 0, W - 1) * E + c;
+    }
+    __syncthreads();
+    int cur_a = -1, cur_b = -1;            // source rows held in pa / pb
+    float pa0[kColsF32], pa1[kColsF32], pb0[kColsF32], pb1[kColsF32];
+#pragma unroll
+    for (int j = 0; j < kColsF32; ++j) pa0[j] = pa1[j] = pb0[j] = pb1[j] = 0.0f;
+    for (int r = 0; r < nrows; ++r) {
+        const int4 rt = rowtab[r];
+        if (rt.x != cur_a) {
+            if (rt.x == cur_b) {
+#pragma unroll
+                for (int j = 0; j < kColsF32; ++j) { pa0[j] = pb0[j]; pa1[j] = pb1[j]; }
+            } else {
+                const float* row = sp + (int64_t)rt.x * src_pitch;
+#pragma unroll
+                for (int j = 0; j < kColsF32; ++j)
+                    if (valid[j]) { pa0[j] = __ldg(row + s0[j]); pa1[j] = __ldg(row + s1[j]); }
+            }
+            cur_a = rt.x;
+        }
+        if (rt.y != cur_b) {
+            const float* row = sp + (int64_t)rt.y * src_pitch;
+#pragma unroll
+            for (int j = 0; j < kColsF32; ++j)
+                if (valid[j]) { pb0[j] = __ldg(row + s0[j]); pb1[j] = __ldg(row + s1[j]); }
+            cur_b = rt.y;
+        }
+        const float wy0 = __int_as_float(rt.z), wy1 = __int_as_float(rt.w);
+#pragma unroll
+        for (int j = 0; j < kColsF32; ++j) {
+            BilinearWeightsF32 w;
+            w.w00 = fmul_nofma(wy0, wx0[j]);
+            w.w01 = fmul_nofma(wy0, wx1[j]);
+            w.w10 = fmul_nofma(wy1, wx0[j]);
+            w.w11 = fmul_nofma(wy1, wx1[j]);
+            if (valid[j]) dp[(int64_t)r * dst_pitch + e_out[j]] = bilinear_f32(pa0[j], pa1[j], pb0[j], pb1[j], w);
+        }
+    }
+}
+
+int launch_f32_rows(const float* src, float* dst, int layout, int B, int C, int H, int W, int Ho, int Wo,
+                    const float* map_x, const float* map_y, cudaStream_t st) {
+    const bool hwc = layout == ATTWARP_LAYOUT_HWC;
+    const int planes = hwc ? B : B * C;
+    const int n_e = hwc ? Wo * C : Wo;
+    const dim3 grid((n_e + kThreadsF32 * kColsF32 - 1) / (kThreadsF32 * kColsF32), (Ho + kRowsF32 - 1) / kRowsF32, planes);
+    if (hwc)
+        remap_f32_rows_kernel<true><<<grid, kThreadsF32, 0, st>>>(src, dst, C, H, W, Ho, Wo, 1, map_x, map_y);
+    else
+        remap_f32_rows_kernel<false><<<grid, kThreadsF32, 0, st>>>(src, dst, C, H, W, Ho, Wo, C, map_x, map_y);
+    return check_launch("remap_f32_rows_kernel");
+}
+
 template <typename T>
 int launch_direct(const void* src, void* dst, int layout, int B, int C, int H, int W, int Ho,
                   int Wo, const float* map_x, const float* map_y, cudaStream_t st) {
@@ -109,8 +213,13 @@ int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C
     }
     if (dtype == ATTWARP_U8)
         return launch_direct<uint8_t>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
-    if (dtype == ATTWARP_F32)
+    if (dtype == ATTWARP_F32) {
+        const int64_t planes = layout == ATTWARP_LAYOUT_HWC ? B : (int64_t)B * C;
+        if (!force_direct() && planes <= 65535 && (int64_t)Wo * C < 0x7fffffff && (int64_t)W * C < 0x7fffffff)
+            return launch_f32_rows(static_cast<const float*>(src), static_cast<float*>(dst), layout, B, C, H, W,
+                                   Ho, Wo, map_x, map_y, st);
         return launch_direct<float>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
+    }
     return fail(ATTWARP_ERR_INVALID_ARG, "remap: image dtype must be u8/f32 (got %d)", dtype);
 }
 
