@@ -248,6 +248,25 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
 }
 
 // ---------------------------------------------------------------------------------------------
+int attwarp_warp_from_pdfs(const float* px, const float* py, int B, int Nx, int Ny, float alpha,
+                           const float* Mx, const float* My, const void* src, void* dst, int dtype,
+                           int layout, int C, int H, int W, int Ho, int Wo, float* Fx, float* Fy,
+                           float* map_x, float* map_y, void* stream) {
+    AW_REQUIRE(px && py && Mx && My && src && dst && Fx && Fy && map_x && map_y, "warp_from_pdfs: NULL pointer");
+    AW_REQUIRE(B > 0 && Nx > 0 && Ny > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0,
+               "warp_from_pdfs: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "warp_from_pdfs: B=%d exceeds 65535", B);
+    AW_REQUIRE(layout == ATTWARP_LAYOUT_HWC || layout == ATTWARP_LAYOUT_CHW, "warp_from_pdfs: bad layout %d", layout);
+    AW_REQUIRE(src != dst, "warp_from_pdfs: in-place operation is not supported");
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_pdf_to_cdf(px, py, B, Nx, Ny, alpha, Mx, My, W, H, Fx, Fy, st);
+    if (rc != ATTWARP_OK) return rc;
+    rc = launch_maps_from_cdf(Fx, Fy, B, H, W, Wo, Ho, map_x, map_y, st);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_remap(src, dst, dtype, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ragged batch: descriptor table (n + 1 entries) followed by the map rows of every image.
 static size_t ragged_table_bytes(int n) { return align_up(sizeof(RaggedImage) * (size_t)(n + 1), 256); }
 

@@ -64,6 +64,10 @@ int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int
                                cudaStream_t st);
 int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C, int H, int W,
                  int Ho, int Wo, const float* map_x, const float* map_y, cudaStream_t st);
+int launch_pdf_to_cdf(const float* px, const float* py, int B, int Nx, int Ny, float alpha, const float* Mx,
+                      const float* My, int W, int H, float* Fx, float* Fy, cudaStream_t st);
+int launch_maps_from_cdf(const float* Fx, const float* Fy, int B, int H, int W, int Wo, int Ho, float* map_x,
+                         float* map_y, cudaStream_t st);
 // ragged batches: `imgs` is a device table of n entries (dims + map pointers are read per image)
 int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, const RaggedImage* imgs,
                                    int max_h, int max_w, const attwarp_transform_params& tp,

@@ -74,9 +74,15 @@ remap_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int H
 // and thread instead of four per output.  Loads of neighbouring threads are neighbouring floats
 // (coalesced through L1), stores are fully coalesced.  Arithmetic is OpenCV's float path exactly:
 // w = fl32(wy * wx), ((p00 w00 + p01 w01) + p10 w10) + p11 w11 without FMA contraction.
+#ifndef AW_F32_ROWS
+#define AW_F32_ROWS 32
+#endif
+#ifndef AW_F32_COLS
+#define AW_F32_COLS 2
+#endif
 constexpr int kThreadsF32 = 256;
-constexpr int kRowsF32 = 32;
-constexpr int kColsF32 = 2;      // output columns per thread (independent chains)
+constexpr int kRowsF32 = AW_F32_ROWS;
+constexpr int kColsF32 = AW_F32_COLS;      // output columns per thread (independent chains)
 
 // ELEMS: floats per pixel that are interleaved in memory (HWC: C, planar: 1)
 template <bool HWC>

@@ -88,6 +88,45 @@ __global__ void upsample_right_inverse_kernel(const float* __restrict__ y,
     x[(int64_t)b * L_in + i] = acc;
 }
 
+// Fused PDF -> CDF for both axes of a batch (BASELINE configs[4]; trainer.py:212-218, 285-288):
+//   mix_with_uniform -> upsample_pdf_right_inverse (x = M y) -> .clamp_min(0) -> cdf_from_density
+// in one launch, grid (B, 2): blockIdx.y = 0 is the x axis (px -> Fx, length W), 1 the y axis.
+// Each step is the arithmetic of the stand-alone kernels above, in the same order, so the result is
+// bit-identical to running them one after the other; the upsampled PDF never leaves shared memory.
+__global__ void __launch_bounds__(kRowThreads)
+pdf_to_cdf_kernel(const float* __restrict__ px, const float* __restrict__ py, int Nx, int Ny, float c1x,
+                  float c2x, float c1y, float c2y, int mix, const float* __restrict__ Mx,
+                  const float* __restrict__ My, int W, int H, float* __restrict__ Fx, float* __restrict__ Fy) {
+    extern __shared__ double sm[];
+    const int axis = blockIdx.y;
+    const int N = axis ? Ny : Nx, L = axis ? H : W;
+    const float* y = (axis ? py : px) + (int64_t)blockIdx.x * N;
+    const float* M = axis ? My : Mx;
+    float* o = (axis ? Fy : Fx) + (int64_t)blockIdx.x * L;
+    const float c1 = axis ? c1y : c1x, c2 = axis ? c2y : c2x;
+    double* red = sm;                                  // kRowThreads
+    double* a = sm + kRowThreads;                      // L
+    float* ys = reinterpret_cast<float*>(a + L);       // N
+    for (int k = threadIdx.x; k < N; k += blockDim.x)
+        ys[k] = mix ? fadd_nofma(fmul_nofma(c1, y[k]), c2) : y[k];
+    __syncthreads();
+    double part = 0.0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float* m = M + (int64_t)i * N;
+        float acc = 0.f;
+        for (int k = 0; k < N; ++k) acc = fmaf(__ldg(m + k), ys[k], acc);
+        float v = isnan(acc) ? acc : fmaxf(acc, 0.f);  // .clamp_min(0) (idempotent with the CDF's own clamp)
+        v = nan_inf_to_zero(v);
+        a[i] = (double)v;
+        part += (double)v;
+    }
+    const float denom = fmaxf((float)block_sum(part, red), 1e-6f);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) a[i] = (double)((float)a[i] / denom);
+    __syncthreads();
+    block_inclusive_scan(a, L, red);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) o[i] = (i == L - 1) ? 1.0f : (float)a[i];
+}
+
 // adaptive_avg_pool2d: one warp per output cell, window [floor(i*H/gh), ceil((i+1)*H/gh)).
 __global__ void adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw,
                                            float* __restrict__ out) {
@@ -131,6 +170,21 @@ int launch_cdf_from_density(const float* p, int B, int N, float* F, cudaStream_t
         AW_CUDA(cudaFuncSetAttribute(cdf_from_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cdf_from_density_kernel<<<B, kRowThreads, smem, st>>>(p, N, F);
     return check_launch("cdf_from_density_kernel");
+}
+
+int launch_pdf_to_cdf(const float* px, const float* py, int B, int Nx, int Ny, float alpha, const float* Mx,
+                      const float* My, int W, int H, float* Fx, float* Fy, cudaStream_t st) {
+    const int Lmax = W > H ? W : H, Nmax = Nx > Ny ? Nx : Ny;
+    const size_t smem = sizeof(double) * ((size_t)kRowThreads + Lmax) + sizeof(float) * (size_t)Nmax;
+    if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "pdf_to_cdf: length %d too long", Lmax);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(pdf_to_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (1 - alpha) and alpha / N are Python floats (float64) cast to the tensor dtype by torch
+    const float c1 = (float)(1.0 - (double)alpha);
+    pdf_to_cdf_kernel<<<dim3(B, 2), kRowThreads, smem, st>>>(
+        px, py, Nx, Ny, c1, (float)((double)alpha / (double)Nx), c1, (float)((double)alpha / (double)Ny),
+        alpha > 0.f ? 1 : 0, Mx, My, W, H, Fx, Fy);
+    return check_launch("pdf_to_cdf_kernel");
 }
 
 int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,

@@ -249,6 +249,50 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
 
 
 # --------------------------------------------------------------------------------------------
+# predicted PDFs -> warped images (BASELINE configs[4])
+# --------------------------------------------------------------------------------------------
+def warp_from_pdfs(img: torch.Tensor, px: torch.Tensor, py: torch.Tensor, alpha: float = 0.0,
+                   out_size=None, layout: str = "chw", eps: float = 1e-8, out: torch.Tensor | None = None,
+                   return_aux: bool = False):
+    """MarginalNet PDFs px [B,Nx], py [B,Ny] + images -> warped images, three launches:
+    (mix_with_uniform + upsample_pdf_right_inverse + clamp_min(0) + cdf_from_density) for both axes,
+    inverse-CDF maps, resample.  Same arithmetic as calling the mirrors in checkpoint_utils / model one
+    after the other (trainer.py:212-218, 285-289)."""
+    from .checkpoint_utils import right_inverse_matrix
+    lib = load()
+    require_cuda(img, px, py, out)
+    img = img.contiguous()
+    if layout == "chw":
+        B, Cc, H, W = img.shape
+        lay = LAYOUT_CHW
+    else:
+        B, H, W, Cc = img.shape
+        lay = LAYOUT_HWC
+    Ho, Wo = (H, W) if out_size is None else (int(out_size[0]), int(out_size[1]))
+    dev = img.device
+    px = px.detach().to(device=dev, dtype=torch.float32).contiguous()
+    py = py.detach().to(device=dev, dtype=torch.float32).contiguous()
+    assert px.shape[0] == B and py.shape[0] == B and px.dim() == 2 and py.dim() == 2
+    Mx = right_inverse_matrix(W, px.shape[1], eps, dev)
+    My = right_inverse_matrix(H, py.shape[1], eps, dev)
+    if out is None:
+        shape = (B, Cc, Ho, Wo) if layout == "chw" else (B, Ho, Wo, Cc)
+        out = torch.empty(shape, dtype=img.dtype, device=dev)
+    Fx = torch.empty(B, W, dtype=torch.float32, device=dev)
+    Fy = torch.empty(B, H, dtype=torch.float32, device=dev)
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_warp_from_pdfs(ptr(px), ptr(py), B, px.shape[1], py.shape[1], float(alpha),
+                                         ptr(Mx), ptr(My), ptr(img), ptr(out), TORCH_DTYPE_IDS[img.dtype],
+                                         lay, Cc, H, W, Ho, Wo, ptr(Fx), ptr(Fy), ptr(map_x), ptr(map_y),
+                                         current_stream(dev)))
+    if return_aux:
+        return out, Fx, Fy, map_x, map_y
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # ragged batches (mixed resolutions, BASELINE configs[3])
 # --------------------------------------------------------------------------------------------
 def warp_ragged_from_tokens(tok: torch.Tensor, images, out_sizes=None, grid_hw=None,

@@ -170,6 +170,22 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
                                        float* map_y, void* const* stage_events, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * attwarp_warp_from_pdfs: predicted marginal PDFs -> warped images in three launches (BASELINE
+ * configs[4]).  Replaces the chain of model/marginalnet_full_dataset/trainer.py:212-218, 285-289:
+ *   mix_with_uniform(p, alpha) -> upsample_pdf_right_inverse(p, L).clamp_min(0) -> cdf_from_density
+ *   -> warp_from_cdf_torch(img, Fx, Fy, out_size)
+ * px [B][Nx], py [B][Ny] : float32 PDFs over the token grid (MarginalNet outputs, model.py:93-95)
+ * Mx [W][Nx], My [H][Ny] : right-inverse matrices as for attwarp_upsample_right_inverse
+ * src/dst                : images as for attwarp_remap_bilinear (dtype u8/f32, layout HWC/CHW)
+ * Fx [B][W], Fy [B][H], map_x [B][Wo], map_y [B][Ho] : device scratch owned by the caller; on return
+ *                          (in stream order) they hold the CDFs and the separable maps
+ */
+int attwarp_warp_from_pdfs(const float* px, const float* py, int B, int Nx, int Ny, float alpha,
+                           const float* Mx, const float* My, const void* src, void* dst, int dtype,
+                           int layout, int C, int H, int W, int Ho, int Wo, float* Fx, float* Fy,
+                           float* map_x, float* map_y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Ragged batches (BASELINE configs[3]: mixed resolutions): n independent images of different
  * shapes in ONE launch per stage.  Replaces the per-image loop of the reference drivers
  * (AGW/main.py:395-533 and AGW/main_batched.py:243-287 call save_warped_image ->
