@@ -75,6 +75,8 @@ SIGNATURES = {
     "attwarp_safe_softmax": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "attwarp_mix_with_uniform": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "attwarp_cdf_from_density": (_i, [_vp, _i, _i, _vp, _vp]),
+    "attwarp_make_strictly_increasing": (_i, [_vp, _i, _i, _f, _vp, _vp]),
+    "attwarp_interp_linear_rows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "attwarp_gt_marginals": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _vp]),
     "attwarp_upsample_right_inverse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "attwarp_adaptive_avg_pool2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

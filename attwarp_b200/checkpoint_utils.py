@@ -4,6 +4,7 @@
 * ``gt_marginals(A)``                                   (checkpoint_utils.py:43-51)
 * ``upsample_pdf_right_inverse(y, target_len, eps)``    (checkpoint_utils.py:64-131)
 * ``warp_from_cdf_torch(img, Fx_img, Fy_img, out_size)`` (checkpoint_utils.py:133-204)
+* ``_make_strictly_increasing(Fcdf, eps)`` / ``resample_cdf(Fcdf, target_len)`` (checkpoint_utils.py:17-28, 53-62)
 * ``adaptive_avg_pool2d_24`` -- the ``F.adaptive_avg_pool2d(A_full, (24, 24))`` prologue of
   ``trainer.py:197``
 
@@ -44,6 +45,32 @@ def cdf_from_density(p: torch.Tensor) -> torch.Tensor:
         check(lib.attwarp_cdf_from_density(ptr(rows), rows.shape[0], rows.shape[1], ptr(out),
                                            current_stream(dev)))
     return out.to(p.device)
+
+
+def _make_strictly_increasing(Fcdf: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
+    """(B,N) CDF rows -> strictly increasing rows in [0,1] ending at 1 (checkpoint_utils.py:17-28)."""
+    lib = load()
+    dev = _cuda_device(Fcdf)
+    rows = Fcdf.detach().to(dev).float().contiguous()
+    assert rows.dim() == 2, "_make_strictly_increasing expects (B, N)"
+    out = torch.empty_like(rows)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_make_strictly_increasing(ptr(rows), rows.shape[0], rows.shape[1], float(eps),
+                                                   ptr(out), current_stream(dev)))
+    return out.to(Fcdf.device)
+
+
+def resample_cdf(Fcdf: torch.Tensor, target_len: int) -> torch.Tensor:
+    """(B,N) CDF -> (B,target_len): strictly increasing -> linear interpolation (align_corners=True)
+    -> strictly increasing (checkpoint_utils.py:53-62)."""
+    lib = load()
+    dev = _cuda_device(Fcdf)
+    F1 = _make_strictly_increasing(Fcdf.detach().to(dev).float())
+    B, N = F1.shape
+    up = torch.empty(B, int(target_len), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_interp_linear_rows(ptr(F1), B, N, int(target_len), ptr(up), current_stream(dev)))
+    return _make_strictly_increasing(up).to(Fcdf.device)
 
 
 def gt_marginals(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -23,6 +23,8 @@ int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_o
                                   float* x, cudaStream_t st);
 int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                cudaStream_t st);
+int launch_strictly_increasing(const float* F, int B, int N, float eps, float* out, cudaStream_t st);
+int launch_interp_linear_rows(const float* F, int B, int N, int L, float* out, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -385,6 +387,19 @@ int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* o
     AW_REQUIRE(p && out, "mix_with_uniform: NULL pointer");
     AW_REQUIRE(B > 0 && N > 0, "mix_with_uniform: sizes must be positive");
     return launch_mix_with_uniform(p, B, N, alpha, out, as_stream(stream));
+}
+
+int attwarp_make_strictly_increasing(const float* F, int B, int N, float eps, float* out, void* stream) {
+    AW_REQUIRE(F && out, "make_strictly_increasing: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "make_strictly_increasing: sizes must be positive");
+    return launch_strictly_increasing(F, B, N, eps, out, as_stream(stream));
+}
+
+int attwarp_interp_linear_rows(const float* F, int B, int N, int L, float* out, void* stream) {
+    AW_REQUIRE(F && out, "interp_linear_rows: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0 && L > 0, "interp_linear_rows: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "interp_linear_rows: B=%d exceeds 65535", B);
+    return launch_interp_linear_rows(F, B, N, L, out, as_stream(stream));
 }
 
 int attwarp_cdf_from_density(const float* p, int B, int N, float* F, void* stream) {

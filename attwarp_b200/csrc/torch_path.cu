@@ -127,6 +127,57 @@ pdf_to_cdf_kernel(const float* __restrict__ px, const float* __restrict__ py, in
     for (int i = threadIdx.x; i < L; i += blockDim.x) o[i] = (i == L - 1) ? 1.0f : (float)a[i];
 }
 
+// _make_strictly_increasing (checkpoint_utils.py:17-28), one CTA per row:
+//   nan_to_num(nan 0, +inf 1, -inf 0) -> cummax -> steps clamped to >= eps/N -> re-accumulated from the
+//   first value (torch.cumsum semantics as in cdf_from_density) -> / max(last, 1e-6) -> clip [0,1] -> last = 1.
+__global__ void __launch_bounds__(kRowThreads)
+strictly_increasing_kernel(const float* __restrict__ F, int N, float min_step, float* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* red = sm;                                   // kRowThreads
+    double* a = sm + kRowThreads;                       // N
+    float* nd = reinterpret_cast<float*>(a + N);        // N   running maximum
+    __shared__ float chunk_max[kRowThreads];
+    const float* row = F + (int64_t)blockIdx.x * N;
+    float* o = out + (int64_t)blockIdx.x * N;
+    const int per = (N + blockDim.x - 1) / blockDim.x;
+    const int beg = min((int)threadIdx.x * per, N), end = min(beg + per, N);
+    float m = -INFINITY;
+    for (int i = beg; i < end; ++i) {                   // cummax inside the thread's chunk
+        float v = row[i];
+        v = isnan(v) ? 0.f : (isinf(v) ? (v > 0.f ? 1.f : 0.f) : v);
+        m = fmaxf(m, v);
+        nd[i] = m;
+    }
+    chunk_max[threadIdx.x] = m;
+    __syncthreads();
+    float before = -INFINITY;                           // maximum of all earlier chunks
+    for (int t = 0; t < (int)threadIdx.x; ++t) before = fmaxf(before, chunk_max[t]);
+    for (int i = beg; i < end; ++i) nd[i] = fmaxf(nd[i], before);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x)   // a[i] = clamped step into element i (a[0] = 0)
+        a[i] = i == 0 ? 0.0 : (double)fmaxf(fadd_nofma(nd[i], -nd[i - 1]), min_step);
+    __syncthreads();
+    block_inclusive_scan(a, N, red);
+    const float first = nd[0];
+    const float last = fmaxf(N > 1 ? fadd_nofma(first, (float)a[N - 1]) : first, 1e-6f);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float v = i == 0 ? first : fadd_nofma(first, (float)a[i]);
+        o[i] = (i == N - 1) ? 1.0f : fminf(fmaxf(v / last, 0.f), 1.f);
+    }
+}
+
+// F.interpolate(mode='linear', align_corners=True) on rows (checkpoint_utils.py:57-59).
+__global__ void interp_linear_rows_kernel(const float* __restrict__ F, int N, int L, float scale,
+                                          float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    const float* row = F + (int64_t)blockIdx.y * N;
+    const float pos = fmul_nofma(scale, (float)j);
+    const int i0 = min((int)pos, N - 1), i1 = min(i0 + 1, N - 1);
+    const float lam1 = fadd_nofma(pos, -(float)i0), lam0 = fadd_nofma(1.0f, -lam1);
+    out[(int64_t)blockIdx.y * L + j] = fadd_nofma(fmul_nofma(lam0, row[i0]), fmul_nofma(lam1, row[i1]));
+}
+
 // adaptive_avg_pool2d: one warp per output cell, window [floor(i*H/gh), ceil((i+1)*H/gh)).
 __global__ void adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw,
                                            float* __restrict__ out) {
@@ -185,6 +236,22 @@ int launch_pdf_to_cdf(const float* px, const float* py, int B, int Nx, int Ny, f
         px, py, Nx, Ny, c1, (float)((double)alpha / (double)Nx), c1, (float)((double)alpha / (double)Ny),
         alpha > 0.f ? 1 : 0, Mx, My, W, H, Fx, Fy);
     return check_launch("pdf_to_cdf_kernel");
+}
+
+int launch_strictly_increasing(const float* F, int B, int N, float eps, float* out, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)kRowThreads + N) + sizeof(float) * (size_t)N;
+    if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "make_strictly_increasing: N=%d too long", N);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(strictly_increasing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float min_step = (float)((double)eps / (double)(N > 1 ? N : 1));
+    strictly_increasing_kernel<<<B, kRowThreads, smem, st>>>(F, N, min_step, out);
+    return check_launch("strictly_increasing_kernel");
+}
+
+int launch_interp_linear_rows(const float* F, int B, int N, int L, float* out, cudaStream_t st) {
+    const float scale = L > 1 ? (float)(N - 1) / (float)(L - 1) : 0.f;
+    interp_linear_rows_kernel<<<dim3((L + 127) / 128, B), 128, 0, st>>>(F, N, L, scale, out);
+    return check_launch("interp_linear_rows_kernel");
 }
 
 int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,

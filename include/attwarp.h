@@ -230,6 +230,11 @@ int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* o
                              void* stream);
 /* cdf_from_density (mnfd/checkpoint_utils.py:30-41). */
 int attwarp_cdf_from_density(const float* p, int B, int N, float* F, void* stream);
+/* _make_strictly_increasing (mnfd/checkpoint_utils.py:17-28): F [B][N] -> out [B][N]; and the row-wise
+ * F.interpolate(mode='linear', align_corners=True) of resample_cdf (:53-62), F [B][N] -> out [B][L].
+ * resample_cdf(F, L) = strictly_increasing(interp(strictly_increasing(F), L)). */
+int attwarp_make_strictly_increasing(const float* F, int B, int N, float eps, float* out, void* stream);
+int attwarp_interp_linear_rows(const float* F, int B, int N, int L, float* out, void* stream);
 /* gt_marginals (mnfd/checkpoint_utils.py:43-51): A float32 [B][H][W] (the singleton channel is
  * dropped) -> px [B][W], py [B][H].  workspace: attwarp_maps_workspace_bytes(B,H,W). */
 int attwarp_gt_marginals(const float* A, int B, int H, int W, void* workspace,

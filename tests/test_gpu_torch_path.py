@@ -74,6 +74,26 @@ def test_cdf_marginals_pool(golden_torch):
     assert rel_err(mx.cpu().numpy(), rx) <= 1e-5 and rel_err(my.cpu().numpy(), ry) <= 1e-5
 
 
+def test_resample_cdf_and_strictly_increasing(golden_torch):
+    """checkpoint_utils.py:17-28, 53-62 (plot-only callers in the reference) against the reference's
+    outputs, plus NaN / Inf / flat / decreasing rows against the oracle."""
+    need_gpu()
+    from attwarp_b200 import checkpoint_utils as cu
+    g = golden_torch
+    assert rel_err(cu._make_strictly_increasing(dev(g["resample/F"])).cpu().numpy(), g["strict/out"]) <= 1e-5
+    assert rel_err(cu.resample_cdf(dev(g["resample/F"]), 200).cpu().numpy(), g["resample/out"]) <= 1e-5
+    rng = np.random.default_rng(8)
+    F = np.sort(rng.random((6, 700)).astype(np.float32), axis=1)
+    F[0, 5] = np.nan; F[1, 9] = np.inf; F[1, 3] = -np.inf; F[2, :] = 0.25; F[3] = F[3, ::-1]
+    got = cu._make_strictly_increasing(dev(F)).cpu().numpy()
+    assert rel_err(got, OT.make_strictly_increasing(F)) <= 1e-5
+    assert np.all(np.diff(got, axis=1) > 0) and np.all(got[:, -1] == 1.0)
+    for L in (64, 700, 1500):
+        assert rel_err(cu.resample_cdf(dev(F), L).cpu().numpy(), OT.resample_cdf(F, L)) <= 1e-5
+    out = cu.resample_cdf(torch.from_numpy(F[:2]), 100)
+    assert out.device.type == "cpu" and out.shape == (2, 100)
+
+
 @pytest.mark.parametrize("name", ["u8_same", "f32_out", "u8_odd", "f32_c4", "u8_c4_sharp"])
 def test_warp_from_cdf_torch(golden_torch, name):
     need_gpu()
