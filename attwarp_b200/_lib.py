@@ -66,6 +66,8 @@ SIGNATURES = {
     "attwarp_warp_from_attention_tokens": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _i,
                                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _tp, _vp,
                                                 _sz, _vp, _vp, _vp, C.POINTER(_vp), _vp]),
+    "attwarp_revise_mask": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "attwarp_resize_lanczos_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "attwarp_warp_from_pdfs": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp]),
     "attwarp_ragged_workspace_bytes": (_sz, [_vp, _i]),

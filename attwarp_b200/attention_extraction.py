@@ -3,6 +3,9 @@
 
 * ``MaskHookLogger``       (llava.py:37-153)  -- single sample per generate call
 * ``BatchMaskHookLogger``  (llava.py:338-448) -- per-sample image-token ranges
+* ``revise_mask`` / ``blend_mask`` (llava.py:223-270) -- mask post-processing and the image-size
+  uint8 mask the drivers warp with (the JET overlay half of ``blend_mask`` is visualisation and stays on
+  OpenCV like in the reference)
 
 Same constructor / method names.  ``_process_attention`` hands the live
 ``[B, Hh, q, kv]`` attention tensor (fp16/bf16/fp32, on the GPU, no copy) to the stage-1 CUDA
@@ -190,3 +193,45 @@ class BatchMaskHookLogger(object):
         if self._original_forward is not None:
             self.model.model.layers[self.layer_index].self_attn.forward = self._original_forward
             self._original_forward = None
+
+
+# ----------------------------------------------------------------------------------------------
+# mask post-processing (llava.py:207-270)
+# ----------------------------------------------------------------------------------------------
+def revise_mask(patch_mask: torch.Tensor, kernel_size: int = 3, enhance_coe: int = 10) -> torch.Tensor:
+    """[gh, gw] token map -> [gh, gw] smoothed sigmoid mask (llava.py:223-238), on the mask's device."""
+    assert kernel_size % 2 == 1
+    dev = patch_mask.device if patch_mask.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    out = ops.revise_mask(patch_mask.detach().to(dev).float()[None], kernel_size, enhance_coe)[0]
+    return out.to(patch_mask.device)
+
+
+def blend_mask(image_path_or_pil_image, mask, enhance_coe, kernel_size, interpolate_method, grayscale):
+    """Same signature and return value as llava.py:240-270: (overlay PIL image, mode-'L' PIL mask at the
+    image size).  The mask is computed on the GPU (bit-identical to Pillow's LANCZOS resize); only LANCZOS
+    -- what the drivers configure -- is implemented there."""
+    import cv2
+    import numpy as np
+    from PIL import Image
+    if isinstance(image_path_or_pil_image, str):
+        image = Image.open(image_path_or_pil_image)
+    elif isinstance(image_path_or_pil_image, Image.Image):
+        image = image_path_or_pil_image
+    else:
+        raise NotImplementedError
+    if interpolate_method not in (Image.LANCZOS, "LANCZOS"):
+        raise NotImplementedError("blend_mask: only Image.LANCZOS is implemented on the device")
+    dev = mask.device if mask.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    W, H = image.size
+    m = ops.mota_mask(mask.detach().to(dev).float()[None], (H, W), kernel_size, enhance_coe)[0]
+    mask_img = Image.fromarray(m.cpu().numpy(), mode="L")
+    mask_np = np.array(mask_img).astype(np.float32)
+    mask_norm = cv2.normalize(mask_np, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    heatmap_bgr = cv2.applyColorMap(mask_norm, cv2.COLORMAP_JET)
+    if isinstance(image_path_or_pil_image, str):
+        orig_bgr = cv2.imread(image_path_or_pil_image)
+    else:
+        orig_bgr = cv2.cvtColor(np.array(image.convert("RGB")), cv2.COLOR_RGB2BGR)
+    alpha = grayscale if (isinstance(grayscale, (int, float)) and 0 < grayscale <= 1) else 0.5
+    overlay_bgr = cv2.addWeighted(orig_bgr, 1 - alpha, heatmap_bgr, alpha, 0)
+    return Image.fromarray(cv2.cvtColor(overlay_bgr, cv2.COLOR_BGR2RGB)), mask_img

@@ -23,6 +23,9 @@ int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_o
                                   float* x, cudaStream_t st);
 int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                cudaStream_t st);
+int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float coe, float* revised,
+                       uint8_t* mask_u8, cudaStream_t st);
+int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, int Wo, uint8_t* dst, cudaStream_t st);
 int launch_strictly_increasing(const float* F, int B, int N, float eps, float* out, cudaStream_t st);
 int launch_interp_linear_rows(const float* F, int B, int N, int L, float* out, cudaStream_t st);
 
@@ -387,6 +390,24 @@ int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* o
     AW_REQUIRE(p && out, "mix_with_uniform: NULL pointer");
     AW_REQUIRE(B > 0 && N > 0, "mix_with_uniform: sizes must be positive");
     return launch_mix_with_uniform(p, B, N, alpha, out, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+int attwarp_revise_mask(const float* tok, int B, int gh, int gw, int kernel_size, float enhance_coe,
+                        float* revised, void* mask_u8, void* stream) {
+    AW_REQUIRE(tok && (revised || mask_u8), "revise_mask: NULL pointer");
+    AW_REQUIRE(B > 0 && gh > 0 && gw > 0 && gh * gw > 1, "revise_mask: sizes must be positive (and more than one token)");
+    AW_REQUIRE(kernel_size > 0 && (kernel_size & 1), "revise_mask: kernel_size must be odd (got %d)", kernel_size);
+    return launch_revise_mask(tok, B, gh, gw, kernel_size, enhance_coe, revised, static_cast<uint8_t*>(mask_u8),
+                              as_stream(stream));
+}
+
+int attwarp_resize_lanczos_u8(const void* src, int B, int h, int w, int Ho, int Wo, void* dst, void* stream) {
+    AW_REQUIRE(src && dst && src != dst, "resize_lanczos_u8: bad pointers");
+    AW_REQUIRE(B > 0 && h > 0 && w > 0 && Ho > 0 && Wo > 0, "resize_lanczos_u8: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "resize_lanczos_u8: B=%d exceeds 65535", B);
+    return launch_resize_lanczos_u8(static_cast<const uint8_t*>(src), B, h, w, Ho, Wo, static_cast<uint8_t*>(dst),
+                                    as_stream(stream));
 }
 
 int attwarp_make_strictly_increasing(const float* F, int B, int N, float eps, float* out, void* stream) {

@@ -1,0 +1,233 @@
+// mask.cu -- the mask post-processing between stage 1 and stage 2b of the driver flow.
+//
+// Replaces, on the device, the mask half of blend_mask
+// ("Attention Guided Warping/attention_extraction/llava.py:207-256", called at AGW/main.py:361 and
+// AGW/main_batched.py:268):
+//   revise_mask: normalize(min) -> z-score x coe -> sigmoid -> clamp -> k x k box filter (replicate pad)
+//   ToPILImage : float -> uint8 by truncation of v * 255
+//   PIL resize(image.size, LANCZOS) of the mode-'L' mask
+// The resize restates Pillow's 8-bit two-pass resampler (src/libImaging/Resample.c) exactly:
+// per output coordinate a window of taps with weights normalised in double and rounded to 22-bit
+// fixed point (computed once per (in, out) size pair on the host, with the C library's sin like Pillow),
+// int32 accumulation from 1 << 21, clip to uint8 after the horizontal pass and after the vertical pass.
+// Everything here is a few hundred KB per batch: one CTA per image (revise) / per tile of output rows
+// (resize, the horizontal pass of the token rows recomputed per CTA into shared memory).
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace aw {
+namespace {
+
+constexpr int kMaskThreads = 256;
+constexpr int kPrecisionBits = 32 - 8 - 2;      // Resample.c PRECISION_BITS
+constexpr int kResizeRows = 32;                 // output rows per CTA
+
+// ---- revise_mask + ToPILImage ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kMaskThreads)
+revise_mask_kernel(const float* __restrict__ tok, int gh, int gw, int ksize, float coe,
+                   float* __restrict__ revised, uint8_t* __restrict__ mask_u8) {
+    extern __shared__ float sm_f[];
+    __shared__ float red[32];
+    __shared__ double redd[32];
+    const int G = gh * gw;
+    float* m = sm_f;                    // G
+    const float* src = tok + (int64_t)blockIdx.x * G;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        const float v = src[i];
+        m[i] = v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    mn = -block_max(-mn, red);
+    const float range = mx - mn;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {          // normalize(mat, "min")
+        const float v = (m[i] - mn) / range;
+        m[i] = v;
+        part += v;
+    }
+    const float mean = block_sum(part, red) / (float)G;
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {          // enhance: centre, unbiased std
+        const float v = m[i] - mean;
+        m[i] = v;
+        sq += (double)v * (double)v;
+    }
+    const float sd = (float)sqrt(block_sum(sq, redd) / (double)(G - 1));
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        const float z = m[i] / sd * coe;
+        const float s = 1.0f / (1.0f + expf(-z));
+        m[i] = fminf(fmaxf(s, 0.f), 1.f);
+    }
+    __syncthreads();
+    const int pad = (ksize - 1) / 2;
+    const float w = 1.0f / (float)(ksize * ksize);
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {          // box filter, replicate padding
+        const int y = i / gw, x = i - y * gw;
+        float acc = 0.f;
+        for (int dy = -pad; dy <= pad; ++dy)
+            for (int dx = -pad; dx <= pad; ++dx)
+                acc = fadd_nofma(acc, fmul_nofma(w, m[clampi(y + dy, 0, gh - 1) * gw + clampi(x + dx, 0, gw - 1)]));
+        if (revised != nullptr) revised[(int64_t)blockIdx.x * G + i] = acc;
+        if (mask_u8 != nullptr) mask_u8[(int64_t)blockIdx.x * G + i] = (uint8_t)(int)fmul_nofma(acc, 255.0f);   // .mul(255).byte()
+    }
+}
+
+// ---- Pillow LANCZOS resize of mode-'L' images -------------------------------------------------------
+// tables: bounds [out] = {first tap, taps}, weights [out][ks]
+__global__ void __launch_bounds__(kMaskThreads)
+resize_lanczos_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, int Wo,
+                         const int2* __restrict__ bx, const int* __restrict__ kx, int ksx,
+                         const int2* __restrict__ by, const int* __restrict__ ky, int ksy,
+                         uint8_t* __restrict__ dst) {
+    extern __shared__ uint8_t sm_b[];
+    uint8_t* in = sm_b;                          // h * w        source image
+    uint8_t* tmp = sm_b + ((h * w + 15) & ~15);  // rows * Wo    horizontal pass of the rows this tile taps
+    const int b = blockIdx.y;
+    const int y0 = blockIdx.x * kResizeRows, y1 = min(y0 + kResizeRows, Ho);
+    // source rows tapped by the output rows [y0, y1): windows move monotonically with y
+    const int r0 = Ho != h ? by[y0].x : y0;
+    const int r1 = Ho != h ? by[y1 - 1].x + by[y1 - 1].y : y1;
+    const uint8_t* img = src + (int64_t)b * h * w;
+    for (int i = threadIdx.x; i < (r1 - r0) * w; i += blockDim.x) in[i] = img[r0 * w + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < (r1 - r0) * Wo; i += blockDim.x) {     // horizontal pass
+        const int r = i / Wo, x = i - r * Wo;
+        if (Wo != w) {
+            const int2 bd = bx[x];
+            const int* k = kx + (int64_t)x * ksx;
+            int acc = 1 << (kPrecisionBits - 1);
+            for (int t = 0; t < bd.y; ++t) acc += (int)in[r * w + bd.x + t] * k[t];
+            tmp[i] = (uint8_t)clampi(acc >> kPrecisionBits, 0, 255);
+        } else {
+            tmp[i] = in[i];
+        }
+    }
+    __syncthreads();
+    uint8_t* out = dst + (int64_t)b * Ho * Wo;
+    for (int i = threadIdx.x; i < (y1 - y0) * Wo; i += blockDim.x) {     // vertical pass
+        const int yy = i / Wo, x = i - yy * Wo;
+        const int y = y0 + yy;
+        if (Ho != h) {
+            const int2 bd = by[y];
+            const int* k = ky + (int64_t)y * ksy;
+            int acc = 1 << (kPrecisionBits - 1);
+            for (int t = 0; t < bd.y; ++t) acc += (int)tmp[(bd.x - r0 + t) * Wo + x] * k[t];
+            out[(int64_t)y * Wo + x] = (uint8_t)clampi(acc >> kPrecisionBits, 0, 255);
+        } else {
+            out[(int64_t)y * Wo + x] = tmp[yy * Wo + x];
+        }
+    }
+}
+
+// ---- coefficient tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc, Lanczos, support 3) ----
+double sinc_filter(double x) {
+    if (x == 0.0) return 1.0;
+    x = x * M_PI;
+    return sin(x) / x;
+}
+double lanczos_filter(double x) { return (-3.0 <= x && x < 3.0) ? sinc_filter(x) * sinc_filter(x / 3.0) : 0.0; }
+
+struct CoeffTable {
+    int2* bounds = nullptr;     // device
+    int* weights = nullptr;     // device
+    int ksize = 0;
+};
+
+int build_table(int in_size, int out_size, CoeffTable* t) {
+    const double scale = (double)in_size / (double)out_size;
+    const double fscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 3.0 * fscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    std::vector<int2> bounds((size_t)out_size);
+    std::vector<int> kk((size_t)out_size * ksize, 0);
+    std::vector<double> w((size_t)ksize);
+    const double ss = 1.0 / fscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            w[(size_t)x] = lanczos_filter((x + xmin - center + 0.5) * ss);
+            ww += w[(size_t)x];
+        }
+        for (int x = 0; x < xmax; ++x) {
+            const double v = ww != 0.0 ? w[(size_t)x] / ww : w[(size_t)x];
+            kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
+        }
+        bounds[(size_t)xx] = make_int2(xmin, xmax);
+    }
+    AW_CUDA(cudaMalloc(&t->bounds, sizeof(int2) * (size_t)out_size));
+    AW_CUDA(cudaMalloc(&t->weights, sizeof(int) * kk.size()));
+    AW_CUDA(cudaMemcpy(t->bounds, bounds.data(), sizeof(int2) * (size_t)out_size, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(t->weights, kk.data(), sizeof(int) * kk.size(), cudaMemcpyHostToDevice));
+    t->ksize = ksize;
+    return ATTWARP_OK;
+}
+
+// Tables are constants of (device, in, out): built once (synchronous upload) and kept for the life of the
+// process, so later calls on any stream only read them.
+int get_table(int in_size, int out_size, CoeffTable* out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, std::pair<int, int>>, CoeffTable> cache;
+    int dev = 0;
+    AW_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(dev, std::make_pair(in_size, out_size));
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        CoeffTable t;
+        const int rc = build_table(in_size, out_size, &t);
+        if (rc != ATTWARP_OK) return rc;
+        it = cache.emplace(key, t).first;
+    }
+    *out = it->second;
+    return ATTWARP_OK;
+}
+
+}  // namespace
+
+int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float coe, float* revised,
+                       uint8_t* mask_u8, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)gh * gw;
+    if (smem > 160 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "revise_mask: token grid %dx%d too large", gh, gw);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(revise_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    revise_mask_kernel<<<B, kMaskThreads, smem, st>>>(tok, gh, gw, ksize, coe, revised, mask_u8);
+    return check_launch("revise_mask_kernel");
+}
+
+int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, int Wo, uint8_t* dst, cudaStream_t st) {
+    CoeffTable tx, ty;
+    if (Wo != w) {
+        const int rc = get_table(w, Wo, &tx);
+        if (rc != ATTWARP_OK) return rc;
+    }
+    if (Ho != h) {
+        const int rc = get_table(h, Ho, &ty);
+        if (rc != ATTWARP_OK) return rc;
+    }
+    // shared memory: the source rows a tile taps (at most all of them) + their horizontal pass
+    const size_t smem = (((size_t)h * w + 15) & ~(size_t)15) + (size_t)h * Wo;
+    if (smem > 200 * 1024)
+        return fail(ATTWARP_ERR_UNSUPPORTED, "resize_lanczos: %dx%d -> width %d does not fit shared memory", h, w, Wo);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(resize_lanczos_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resize_lanczos_u8_kernel<<<dim3((Ho + kResizeRows - 1) / kResizeRows, B), kMaskThreads, smem, st>>>(
+        src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, dst);
+    return check_launch("resize_lanczos_u8_kernel");
+}
+
+}  // namespace aw

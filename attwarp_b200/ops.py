@@ -95,6 +95,46 @@ def aggregate_attention(attn: torch.Tensor, tok_start: torch.Tensor | None = Non
 
 
 # --------------------------------------------------------------------------------------------
+# mask post-processing of the driver flow (between stage 1 and stage 2b)
+# --------------------------------------------------------------------------------------------
+def revise_mask(tok: torch.Tensor, kernel_size: int = 3, enhance_coe: float = 10.0, return_u8: bool = False):
+    """tok [B,gh,gw] float32 -> revise_mask(tok) [B,gh,gw] float32 (llava.py:207-238); with
+    ``return_u8`` also the uint8 image ToPILImage makes of it (truncation of v * 255)."""
+    lib = load()
+    require_cuda(tok)
+    tok = tok.contiguous().float()
+    B, gh, gw = tok.shape
+    rev = torch.empty_like(tok)
+    u8 = torch.empty(B, gh, gw, dtype=torch.uint8, device=tok.device) if return_u8 else None
+    with torch.cuda.device(tok.device):
+        check(lib.attwarp_revise_mask(ptr(tok), B, gh, gw, int(kernel_size), float(enhance_coe), ptr(rev),
+                                      ptr(u8), current_stream(tok.device)))
+    return (rev, u8) if return_u8 else rev
+
+
+def resize_lanczos_u8(img: torch.Tensor, out_hw) -> torch.Tensor:
+    """img [B,h,w] uint8 -> [B,Ho,Wo], bit-identical to PIL.Image.resize((Wo,Ho), LANCZOS) in mode 'L'."""
+    lib = load()
+    require_cuda(img)
+    assert img.dtype == torch.uint8 and img.dim() == 3
+    img = img.contiguous()
+    B, h, w = img.shape
+    Ho, Wo = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty(B, Ho, Wo, dtype=torch.uint8, device=img.device)
+    with torch.cuda.device(img.device):
+        check(lib.attwarp_resize_lanczos_u8(ptr(img), B, h, w, Ho, Wo, ptr(out), current_stream(img.device)))
+    return out
+
+
+def mota_mask(tok: torch.Tensor, image_hw, kernel_size: int = 3, enhance_coe: float = 10.0) -> torch.Tensor:
+    """tok [B,gh,gw] -> the uint8 [B,H,W] mask blend_mask returns at image size (llava.py:240-256):
+    revise_mask -> ToPILImage -> resize(LANCZOS) -> 'L'.  It is the att_map the drivers pass to
+    save_warped_image (main.py:361, 520): feed it to ``maps_from_attention``."""
+    _, u8 = revise_mask(tok, kernel_size, enhance_coe, return_u8=True)
+    return resize_lanczos_u8(u8, image_hw)
+
+
+# --------------------------------------------------------------------------------------------
 # stages 2b-4
 # --------------------------------------------------------------------------------------------
 def maps_from_attention(att: torch.Tensor, out_size, transform="identity", exp_scale=1.0,

@@ -170,6 +170,22 @@ int attwarp_warp_from_attention_tokens(const void* attn, int attn_dtype, int B, 
                                        float* map_y, void* const* stage_events, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mask post-processing of the driver flow (AGW/attention_extraction/llava.py:207-256, called at
+ * AGW/main.py:361 and AGW/main_batched.py:268), SURVEY section 8(f) N2.
+ *
+ * attwarp_revise_mask: tok [B][gh*gw] float32 -> revise_mask (min-max, z-score x enhance_coe, sigmoid,
+ *   clamp, kernel_size x kernel_size box filter with replicate padding; llava.py:207-238) as float32
+ *   `revised` [B][gh*gw] (nullable) and, like ToPILImage, as uint8 `mask_u8` [B][gh*gw] (nullable).
+ * attwarp_resize_lanczos_u8: src [B][h][w] uint8 -> dst [B][Ho][Wo], bit-identical to
+ *   PIL.Image.resize((Wo, Ho), LANCZOS) on mode-'L' images (llava.py:195-196, 253).
+ * The mask at image size is what the drivers hand to save_warped_image as att_map; feed it to
+ * attwarp_maps_from_attention (ATTWARP_U8).
+ */
+int attwarp_revise_mask(const float* tok, int B, int gh, int gw, int kernel_size, float enhance_coe,
+                        float* revised, void* mask_u8, void* stream);
+int attwarp_resize_lanczos_u8(const void* src, int B, int h, int w, int Ho, int Wo, void* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * attwarp_warp_from_pdfs: predicted marginal PDFs -> warped images in three launches (BASELINE
  * configs[4]).  Replaces the chain of model/marginalnet_full_dataset/trainer.py:212-218, 285-289:
  *   mix_with_uniform(p, alpha) -> upsample_pdf_right_inverse(p, L).clamp_min(0) -> cdf_from_density

@@ -18,6 +18,9 @@ Contents
                  ``model/marginalnet_full_dataset/model.py:8-14,98-101``).
 ``aggregate``    restatement of the hook-logger reducers
                  (reference: ``Attention Guided Warping/attention_extraction/llava.py:94-132,385-411``).
+``mask_path``    restatement of ``revise_mask`` and the mask half of ``blend_mask``
+                 (reference: ``Attention Guided Warping/attention_extraction/llava.py:207-256``),
+                 including Pillow's 8-bit two-pass LANCZOS resampler (third-party, unpinned; 12.2.0 here).
 ``ref_loader``   imports the *unmodified* reference from ``/root/reference`` (only exists
                  in the build container) -- used to generate ``tests/golden/*.npz`` and
                  to pin the restatements.
@@ -28,4 +31,4 @@ container by ``tests/golden/make_golden.py`` and committed as ``tests/golden/*.n
 ``tests/test_oracle_vs_golden.py`` replays them.
 """
 
-from . import numpy_path, torch_path, aggregate  # noqa: F401
+from . import numpy_path, torch_path, aggregate, mask_path  # noqa: F401

@@ -1,0 +1,113 @@
+"""Mask post-processing of the driver flow: revise_mask + ToPILImage + Pillow
+LANCZOS resize, i.e. the uint8 mask ``blend_mask`` returns and the drivers warp with
+(llava.py:207-256; main.py:361, 520).
+
+CPU part: the oracle restatement against outputs of the reference (tests/golden/mask_path.npz) and,
+bit for bit, against Pillow itself.  GPU part (-m gpu): the CUDA kernels against both, and the whole C1
+driver chain (token map -> mask -> marginals -> maps -> resample) against the oracle chain.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import mask_path as OM
+from oracle import numpy_path as ON
+
+CASES = ["c1_336", "wide_500x333", "tall_97x53", "big_1344", "small_20x30"]
+
+
+@pytest.fixture(scope="module")
+def gm():
+    return np.load(os.path.join(GOLDEN_DIR, "mask_path.npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_blend_mask(gm, name):
+    tok, ref = gm[name + "/tok"], gm[name + "/mask"]
+    rev = OM.revise_mask(tok)
+    assert np.max(np.abs(rev - gm[name + "/revised"]) / (np.abs(gm[name + "/revised"]) + 1e-8)) <= 1e-5
+    assert np.array_equal(OM.resize_lanczos_u8(gm[name + "/u8_24"], ref.shape[1], ref.shape[0]), ref)
+    d = np.abs(OM.mota_mask(tok, ref.shape).astype(int) - ref.astype(int))
+    assert d.max() <= 2 and (d != 0).mean() <= 0.02          # a token on a x255 truncation boundary may flip
+
+
+@pytest.mark.parametrize("size", [(24, 24, 336, 336), (24, 24, 333, 500), (24, 24, 2048, 224), (24, 24, 12, 40),
+                                  (48, 48, 1344, 1344), (7, 13, 100, 9)])
+def test_lanczos_restatement_matches_pillow(size):
+    from PIL import Image
+    h, w, Ho, Wo = size
+    rng = np.random.default_rng(h * 1000 + Wo)
+    for _ in range(2):
+        m = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        ref = np.array(Image.fromarray(m, mode="L").resize((Wo, Ho), Image.LANCZOS))
+        assert np.array_equal(OM.resize_lanczos_u8(m, Wo, Ho), ref)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_mask_vs_reference(gm, name):
+    _need_gpu()
+    from attwarp_b200 import ops
+    tok, ref = gm[name + "/tok"], gm[name + "/mask"]
+    H, W = ref.shape
+    rev, u8 = ops.revise_mask(torch.from_numpy(tok)[None].cuda(), 3, 10, return_u8=True)
+    assert np.max(np.abs(rev[0].cpu().numpy() - gm[name + "/revised"]) / (np.abs(gm[name + "/revised"]) + 1e-8)) <= 1e-5
+    assert np.abs(u8[0].cpu().numpy().astype(int) - gm[name + "/u8_24"].astype(int)).max() <= 1
+    # stage-wise: the reference's own 24 x 24 uint8 image through the GPU resize is bit-equal
+    got = ops.resize_lanczos_u8(torch.from_numpy(gm[name + "/u8_24"])[None].cuda(), (H, W))[0].cpu().numpy()
+    assert np.array_equal(got, ref)
+    e2e = ops.mota_mask(torch.from_numpy(tok)[None].cuda(), (H, W))[0].cpu().numpy()
+    d = np.abs(e2e.astype(int) - ref.astype(int))
+    assert d.max() <= 2 and (d != 0).mean() <= 0.02
+
+
+@pytest.mark.gpu
+def test_gpu_lanczos_vs_pillow_batched():
+    _need_gpu()
+    from PIL import Image
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(77)
+    for (h, w, Ho, Wo) in [(24, 24, 336, 336), (24, 24, 500, 333), (24, 24, 224, 2048), (48, 48, 1344, 1344),
+                           (24, 24, 24, 100), (24, 24, 100, 24), (24, 24, 12, 40), (7, 13, 100, 9)]:
+        m = rng.integers(0, 256, (5, h, w), dtype=np.uint8)
+        got = ops.resize_lanczos_u8(torch.from_numpy(m).cuda(), (Ho, Wo)).cpu().numpy()
+        for b in range(5):
+            ref = np.array(Image.fromarray(m[b], mode="L").resize((Wo, Ho), Image.LANCZOS))
+            assert np.array_equal(got[b], ref), (h, w, Ho, Wo)
+
+
+@pytest.mark.gpu
+def test_gpu_c1_driver_chain(gm):
+    """BASELINE configs[0] the way main.py runs it: 24 x 24 attention -> blend_mask's uint8 mask at image
+    size -> save_warped_image(att_map=mask, 500 x 500, 'identity')."""
+    _need_gpu()
+    from attwarp_b200 import attention_extraction as AE, ops
+    from PIL import Image
+    tok = gm["c1_336/tok"]
+    rng = np.random.default_rng(1234)
+    img = rng.integers(0, 256, (336, 336, 3), dtype=np.uint8)
+    mask = ops.mota_mask(torch.from_numpy(tok)[None].cuda(), (336, 336))
+    mx, my = ops.maps_from_attention(mask, (500, 500), "identity")
+    out = ops.remap_bilinear(torch.from_numpy(img)[None].cuda(), mx, my, "hwc")[0].cpu().numpy()
+    ref_mask = gm["c1_336/mask"]
+    ref = ON.warp_image_by_attention(img, ref_mask, 500, 500, "identity")
+    if np.array_equal(mask[0].cpu().numpy(), ref_mask):
+        assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
+    else:                                   # a flipped token byte moves the maps by a few 1e-3 px
+        assert (np.abs(out.astype(int) - ref.astype(int)) > 1).mean() <= 0.02
+    # the mirror of blend_mask returns the same mask as a PIL image
+    overlay, pil_mask = AE.blend_mask(Image.fromarray(img, mode="RGB"), torch.from_numpy(tok), 10, 3, Image.LANCZOS, 0)
+    assert pil_mask.mode == "L" and pil_mask.size == (336, 336) and overlay.size == (336, 336)
+    assert np.array_equal(np.array(pil_mask), mask[0].cpu().numpy())
+    rev = AE.revise_mask(torch.from_numpy(tok), 3, 10)
+    assert rev.shape == (24, 24) and rev.device.type == "cpu"
