@@ -81,6 +81,8 @@ __device__ __forceinline__ void st8(int off, uint32_t v) { smem[off] = (uint8_t)
 //                      z = slot after which the row is emitted (= slot of its LOWER tap);
 //                          0xffffffff: both taps are the carried pair, emit before slot 0;
 //                          entry n_rows is a sentinel (z = kRowSentinel)
+//                      w = 512, the rounding constant of the vertical blend (as a literal it would be
+//                          rematerialised inside the row loop; here it arrives with the row entry)
 //   uint32 slot_base[2 R]:  slot * slot_pitch + (global address of its first byte & 15)
 constexpr int kTabRows = 64;
 constexpr uint32_t kRowSentinel = 0x7fffffffu;
@@ -187,9 +189,9 @@ __device__ __forceinline__ void vblend_store(const uint32_t* PQ, uint32_t wy, in
     "ld.shared.b32 lo, [cur];\n"                                \
     "ld.shared.b32 mid, [cur+4];\n"
 #define AW_SW_EMIT3                                             \
-    "dp2a.lo.u32.u32 r0, %0, ex, %14;\n"                        \
-    "dp2a.lo.u32.u32 r1, %1, ex, %14;\n"                        \
-    "dp2a.lo.u32.u32 r2, %2, ex, %14;\n"                        \
+    "dp2a.lo.u32.u32 r0, %0, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r1, %1, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r2, %2, ex, ew;\n"                         \
     "add.u32 o, ey, %8;\n"                                      \
     "shr.u32 r0, r0, 10;\n shr.u32 r1, r1, 10;\n shr.u32 r2, r2, 10;\n" \
     "st.shared.u8 [o], r0;\n st.shared.u8 [o+1], r1;\n st.shared.u8 [o+2], r2;\n"
@@ -206,7 +208,7 @@ __device__ __forceinline__ void vblend_store(const uint32_t* PQ, uint32_t wy, in
     "prmt.b32 %1, %1, h1, 0x5432;\n"                            \
     "prmt.b32 %2, %2, h2, 0x5432;\n"
 #define AW_SW_EMIT1                                             \
-    "dp2a.lo.u32.u32 r0, %0, ex, %8;\n"                         \
+    "dp2a.lo.u32.u32 r0, %0, ex, ew;\n"                         \
     "add.u32 o, ey, %6;\n"                                      \
     "shr.u32 r0, r0, 10;\n"                                     \
     "st.shared.u8 [o], r0;\n"
@@ -290,17 +292,19 @@ __device__ __forceinline__ void sweep_c1(uint32_t* P, int n_slots, uint32_t cur_
 // the one-column sweep) are shared by both columns and each thread carries two independent chains.
 //   bdelta : byte distance of column b from column a inside an output row;  bvalid: column b exists
 //   ca/cb : window addresses of column a / b (as cur/arena above);  sha/shb: their shift amounts (U)
-#define AW_SW2_BLEND(SHA, SHB)                                  \
+#define AW_SW2_LOAD                                             \
     "ld.shared.b32 loa, [ca];\n"                                \
     "ld.shared.b32 mida, [ca+4];\n"                             \
     "ld.shared.b32 hia, [ca+8];\n"                              \
     "ld.shared.b32 lob, [cb];\n"                                \
     "ld.shared.b32 midb, [cb+4];\n"                             \
-    "ld.shared.b32 hib, [cb+8];\n"                              \
+    "ld.shared.b32 hib, [cb+8];\n"
+#define AW_SW2_ALIGN(SHA, SHB)                                  \
     "shf.r.wrap.b32 Aa, loa, mida, " SHA ";\n"                  \
     "shf.r.wrap.b32 Ba, mida, hia, " SHA ";\n"                  \
     "shf.r.wrap.b32 Ab, lob, midb, " SHB ";\n"                  \
-    "shf.r.wrap.b32 Bb, midb, hib, " SHB ";\n"                  \
+    "shf.r.wrap.b32 Bb, midb, hib, " SHB ";\n"
+#define AW_SW2_DOT                                              \
     "dp4a.u32.u32 h0, Aa, %14, 0;\n"                            \
     "dp4a.u32.u32 t, Aa, %15, 0;\n"                             \
     "dp4a.u32.u32 h1, Ba, %17, t;\n"                            \
@@ -317,13 +321,14 @@ __device__ __forceinline__ void sweep_c1(uint32_t* P, int n_slots, uint32_t cur_
     "prmt.b32 %3, %3, h3, 0x5432;\n"                            \
     "prmt.b32 %4, %4, h4, 0x5432;\n"                            \
     "prmt.b32 %5, %5, h5, 0x5432;\n"
+#define AW_SW2_BLEND(SHA, SHB) AW_SW2_LOAD AW_SW2_ALIGN(SHA, SHB) AW_SW2_DOT
 #define AW_SW2_EMIT                                             \
-    "dp2a.lo.u32.u32 r0, %0, ex, %13;\n"                        \
-    "dp2a.lo.u32.u32 r1, %1, ex, %13;\n"                        \
-    "dp2a.lo.u32.u32 r2, %2, ex, %13;\n"                        \
-    "dp2a.lo.u32.u32 r3, %3, ex, %13;\n"                        \
-    "dp2a.lo.u32.u32 r4, %4, ex, %13;\n"                        \
-    "dp2a.lo.u32.u32 r5, %5, ex, %13;\n"                        \
+    "dp2a.lo.u32.u32 r0, %0, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r1, %1, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r2, %2, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r3, %3, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r4, %4, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r5, %5, ex, ew;\n"                         \
     "add.u32 o, ey, %12;\n"                                     \
     "add.u32 o2, o, %25;\n"                                     \
     "shr.u32 r0, r0, 10;\n shr.u32 r1, r1, 10;\n shr.u32 r2, r2, 10;\n" \
@@ -344,8 +349,12 @@ __device__ __forceinline__ void sweep_c3x2(uint32_t* P, int n_slots, uint32_t ca
             ".reg .b32 r0, r1, r2, r3, r4, r5, o, o2, ca, cb, rp, ex, ey, ez, ew;\n"
             "setp.ne.u32 pb, %26, 0;\n"
             "mov.b32 ca, %7;\n mov.b32 cb, %8;\n mov.b32 rp, %11;\n" AW_SW_PRE_BEGIN AW_SW2_EMIT AW_SW_PRE_END("%6")
-            "SLOT:\n" AW_SW2_BLEND("%9", "%24")
-            "add.u32 ca, ca, %10;\n add.u32 cb, cb, %10;\n" AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
+            // software pipeline: the window of slot s + 1 is requested before slot s is blended (the slot
+            // after the last one is read too -- still inside the CTA's shared memory -- and never used)
+            AW_SW2_LOAD
+            "SLOT:\n" AW_SW2_ALIGN("%9", "%24")
+            "add.u32 ca, ca, %10;\n add.u32 cb, cb, %10;\n" AW_SW2_LOAD AW_SW2_DOT
+            AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
             "@p bra.uni SLOT;\n"
             "DONE:\n"
             "}\n"
@@ -638,7 +647,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                         st128(tab + kTabRows + 16 * lane,
                               make_uint4((uint32_t)wa | ((uint32_t)(32 - wa) << 8),
                                          (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 15),
-                                         (uint32_t)(ra + 1 - r_lo), 0u));
+                                         (uint32_t)(ra + 1 - r_lo), 512u));
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, kRowSentinel, 0u));
                     }
