@@ -6,19 +6,21 @@
 // pixels runs out of issue slots long before it runs out of HBM bandwidth, so the kernel is
 // organised around instructions per output pixel and around never making a warp wait for another:
 //
-//   * work = column strips (<= 384 output columns) of images, cut into tiles of kRows output rows;
-//     the grid is persistent (three CTAs per SM) and every CTA walks a contiguous range of tiles.
-//     Consecutive tiles of one strip form a SEGMENT that is streamed top to bottom in CHUNKS of
-//     <= kRows output rows through a ring of shared-memory source stages and a ring of output tiles;
+//   * work = column strips (<= 352 output columns) of images, split over a persistent grid (three CTAs
+//     per SM) in units of kTileRows output rows; every CTA walks a contiguous range of units.  The units
+//     it owns in one strip form a SEGMENT that is streamed top to bottom in CHUNKS of <= R (12) output
+//     rows through a ring of shared-memory source stages and a ring of output tiles;
 //   * the PRODUCER warp plans a chunk -- the contiguous range of source rows its output rows tap,
 //     minus the (at most two) rows whose horizontal blends the consumers still hold in registers
 //     from the previous chunk -- writes the chunk's row table and fetches the rows with
 //     cp.async.bulk (TMA bulk copy, global -> shared): ONE copy for the whole range when the strip
 //     spans full image rows that are multiples of 16 bytes, else one copy per row (the 16-byte
 //     aligned span around the strip's source columns); completion lands on the stage's `full`
-//     mbarrier.  Planning costs ~60 dependent instructions per chunk: the single producer warp
-//     must stay well ahead of eleven consumer warps;
-//   * CONSUMER warps own 32 output columns each, one per lane.  The warp map is separable, so the
+//     mbarrier.  Planning costs ~60 dependent instructions per chunk and reads map_y through a
+//     register window refilled 32 rows ahead: the single producer warp must stay well ahead of the
+//     consumer warps;
+//   * CONSUMER threads own one output column each (two, half a strip apart, for 3-channel images: the
+//     table loads and loop control are shared by both).  The warp map is separable, so the
 //     horizontal blend of a source row is computed ONCE per (row, output column) -- a funnel-shifted
 //     8-byte window and dp4a with byte-positioned weights -- and kept packed with the previous
 //     row's blend as the two 16-bit halves of one register; each output row is then ONE dp2a
@@ -65,6 +67,12 @@ constexpr int kOutStages = AW_OUT_STAGES;          // output tiles per CTA
 constexpr int max_cols(int) { return 352; }
 constexpr int max_threads(int cpt) { return (max_cols(cpt) + 32 * cpt - 1) / (32 * cpt) * 32 + 64; }
 constexpr int kRoleThreads = 64;       // producer warp + store warp
+// Work is split over the CTAs in units of kTileRows output rows (finer than a chunk: with ~16 chunks per CTA
+// a split in whole chunks leaves the slowest CTA 5 % more work than the average)
+#ifndef AW_TILE_ROWS
+#define AW_TILE_ROWS 1
+#endif
+constexpr int kTileRows = AW_TILE_ROWS;
 
 // Shared memory is addressed as byte offsets from the one dynamic array below.
 extern __shared__ __align__(128) uint8_t smem[];
@@ -550,7 +558,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 const int strip = local / v.n_rowtiles, rt = local % v.n_rowtiles;
                 const int mine_end = (u1 - v.unit_begin + v.tile_units - 1) / v.tile_units;   // tiles starting before u1
                 const int local_end = min((strip + 1) * v.n_rowtiles, mine_end);
-                const int y_end = min(Ho, (rt + (local_end - local)) * R);
+                const int y_end = min(Ho, (rt + (local_end - local)) * kTileRows);
                 const int x_first = strip * v.strip_cols;
                 const int ncols = min(v.strip_cols, Wo - x_first);
                 const uint8_t* simg = v.src;
@@ -593,7 +601,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 }
                 uint32_t seg_flags = kFlagNewStrip | (uni ? kFlagUniform : 0u);
                 int carry_row = kNoCarry;    // source row whose blend sits in the upper half of P
-                int y_cur = rt * R;
+                int y_cur = rt * kTileRows;
                 // map_y is read through a register window of 2 x 32 rows (lane i holds rows y_win + i
                 // and y_win + 32 + i) refilled 32 rows ahead of use: a global-load latency per chunk
                 // on the planning path would cap the whole CTA at one chunk per microsecond.
@@ -925,7 +933,7 @@ int launch_stream(const uint8_t* src, uint8_t* dst, int n_img, int H, int W, int
     a.strip_cols = sp.strip_cols;
     a.src = src; a.dst = dst; a.map_x = map_x; a.map_y = map_y;
     a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.map_div = map_div;
-    a.n_rowtiles = (Ho + R - 1) / R;
+    a.n_rowtiles = (Ho + kTileRows - 1) / kTileRows;
     a.imgs = nullptr;
     a.n_img = n_img;
     const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
@@ -947,7 +955,7 @@ int ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_table, cudaStream_
         if (sp.n_strips > 0xffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: image %d is too wide", i);
         host[i].strips_units = sp.n_strips | (units << 16);
         host[i].strip_cols = sp.strip_cols;
-        host[i].n_rowtiles = (host[i].Ho + R - 1) / R;
+        host[i].n_rowtiles = (host[i].Ho + kTileRows - 1) / kTileRows;
         host[i].unit_begin = (int)total;
         total += (int64_t)sp.n_strips * host[i].n_rowtiles * units;
         if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");

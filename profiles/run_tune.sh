@@ -1,9 +1,10 @@
 cd $GRAFT_REPO_ROOT
-for cfg in "3 2 12 3" "3 2 8 4" "2 2 12 4" "3 2 6 5"; do
-set -- $cfg
+for tr in 4 2 12 1; do
 touch attwarp_b200/csrc/remap_stream.cu
-ATTWARP_NVCC_EXTRA="-DAW_SRC_STAGES=$1 -DAW_OUT_STAGES=$2 -DAW_ROWS=$3 -DAW_MIN_CTAS=$4" python -m attwarp_b200.build > /dev/null 2>&1 || echo build failed
-echo "== S=$1 O=$2 R=$3 CTAS=$4"
+ATTWARP_NVCC_EXTRA="-DAW_TILE_ROWS=$tr" python -m attwarp_b200.build > /dev/null 2>&1 || echo build failed
+echo "== tile rows $tr"
 timeout 120 python profiles/drive.py remap --side 336 --batch 256 --iters 12 | sed 's/GB.*//' | sed 's/.*us//'
 timeout 120 python profiles/drive.py remap --side 1344 --batch 64 --iters 8| sed 's/GB.*//' | sed 's/.*us//'
 done
+touch attwarp_b200/csrc/remap_stream.cu; python -m attwarp_b200.build > /dev/null 2>&1
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
