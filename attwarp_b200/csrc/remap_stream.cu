@@ -764,13 +764,16 @@ remap_u8_stream_kernel(const StreamArgs a) {
     const int out_col = xl * C;
     const uint32_t rnd = (uint32_t)a.rnd;
 
-    for (int it = 0;; ++it) {
-        const int st = it % kSrcStages, ot = it % kOutStages;
+    int st = 0, ot = 0;               // source stage / output tile of the current chunk
+    uint32_t sph = 0u, oph = 1u;      // parities to wait for: stage filled / tile shipped and free
+    bool warp_b = false;              // CPT = 2: some lane of this warp owns a second column
+    for (;; st = st + 1 == kSrcStages ? 0 : st + 1, sph ^= st == 0 ? 1u : 0u,
+            ot = ot + 1 == kOutStages ? 0 : ot + 1, oph ^= ot == 0 ? 1u : 0u) {
         const int tab = tab_off0 + st * tab_bytes<R>();
-        mbar_wait(full_s + 8u * st, (uint32_t)(it / kSrcStages) & 1u);
+        mbar_wait(full_s + 8u * st, sph);
         const uint4 h0 = ld128(tab);
         const int n_rows = (int)h0.x;
-        mbar_wait(ofree_s + 8u * ot, ((uint32_t)(it / kOutStages) & 1u) ^ 1u);   // tile shipped and free
+        mbar_wait(ofree_s + 8u * ot, oph);                                       // tile shipped and free
         if (n_rows < 0) {                                                        // pass the stop on
             if (tid == 0) st128(ohdr_off0 + 32 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
             __syncwarp();
@@ -784,6 +787,7 @@ remap_u8_stream_kernel(const StreamArgs a) {
             const int W = (int)hx.z, ncols = (int)hx.w;
             xvalid = xl < ncols;
             bvalid = (CPT == 2 && xl + xstep < ncols) ? 1u : 0u;
+            warp_b = __any_sync(0xffffffffu, bvalid != 0u);
             int xb = (int)h1.w;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
@@ -838,7 +842,12 @@ remap_u8_stream_kernel(const StreamArgs a) {
             const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
             const int slot_tab = tab + tab_slots<R>();
             const int win0 = arena + (uni ? (int)h0.w : 0);
-            if (CPT == 2) {
+            if (CPT == 2 && !warp_b) {
+                // no lane of this warp has a second column in this strip (the strip is narrower than the
+                // consumer threads x 2): the one-column sweep does the same work in 3/5 of the instructions
+                if (uni) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
+                else sweep_c3<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, wB, rnd);
+            } else if (CPT == 2) {
                 const int win1 = st * a.stage_bytes + wo[CPT - 1] + (uni ? (int)h0.w : 0);
                 if (uni) sweep_c3x2<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), smem_s + (uint32_t)(win1 & ~3), (uint32_t)win0 << 3, (uint32_t)win1 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
                 else sweep_c3x2<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)win1, smem_s + (uint32_t)slot_tab, 0u, 0u, rp_s, ocol_s, wA, wB, rnd, (uint32_t)(xstep * C), bvalid);
@@ -915,6 +924,9 @@ int launch_kernel(StreamArgs& a, int cols, cudaStream_t st) {
         AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         int o = 0;
         AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
+        // ATTWARP_REMAP_CTAS_PER_SM caps the persistent grid (leaves shared memory for a kernel of another
+        // stream to co-run on the same SMs)
+        if (const char* e = getenv("ATTWARP_REMAP_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < o) o = v; }
         c = Cfg{smem_bytes, threads, dev, o};
     }
     if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);

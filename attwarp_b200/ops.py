@@ -24,10 +24,15 @@ _RAGGED_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("H", np.int32
                           ("Ho", np.int32), ("Wo", np.int32)])
 
 
+_ws_scope = 0        # > 0 while a GraphedCall warms up / captures: that graph's private scratch
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     """A reusable uint8 scratch tensor of at least ``nbytes`` on ``device`` (stream-ordered
-    reuse is safe because all kernels of this package run on the caller's current stream)."""
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    reuse is safe because all kernels of this package run on the caller's current stream).
+    A captured graph keeps scratch of its own: graphs may be replayed concurrently on different
+    streams, whatever stream they were captured on."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream if _ws_scope == 0 else -1, _ws_scope)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -46,17 +51,28 @@ class GraphedCall:
     stream, on pre-allocated tensors -- into a CUDA graph; ``replay()`` launches the whole
     sequence with one driver call (the per-kernel launch gaps of a 150 us step disappear)."""
 
+    _n = 0
+
     def __init__(self, fn, warmup: int = 2, device=None):
+        global _ws_scope
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        GraphedCall._n += 1
+        self._scope = GraphedCall._n
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):          # workspace allocation, kernel attribute opt-ins
+        prev, _ws_scope = _ws_scope, self._scope
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):          # kernel attribute opt-ins, this graph's scratch
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            fn()
+        finally:
+            _ws_scope = prev
+        # the scratch tensors this graph baked in stay alive with it
+        self._scratch = [v for k, v in _ws_cache.items() if k[2] == self._scope]
 
     def replay(self):
         self.graph.replay()

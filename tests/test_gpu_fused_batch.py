@@ -100,3 +100,43 @@ def test_full_size_properties_c3():
         ref = ON.warp_image_by_attention(imgs[b].cpu().numpy(), full, H, H, "identity")
         diff = np.abs(out[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1
+
+
+def test_stream_ring_matches_serial():
+    """Consecutive batches spread over four streams (graph replays, concurrent kernels of different
+    batches on the same SMs) give bit-identical results to the same batches run in turn."""
+    need_gpu()
+    from attwarp_b200 import ops
+    from attwarp_b200.batched import StreamRing
+    B, L, Hh, g, H, n = 32, 8, 8, 24, 336, 8
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    sets = []
+    for _ in range(n):
+        attn = torch.softmax(torch.randn(B, L, Hh, g * g, device="cuda", generator=gen) * 2, -1).to(torch.bfloat16)
+        img = torch.randint(0, 256, (B, H, H, 3), device="cuda", dtype=torch.uint8, generator=gen)
+        aux = (torch.empty(B, g * g, device="cuda"), torch.empty(B, H, device="cuda"), torch.empty(B, H, device="cuda"))
+        sets.append(dict(attn=attn, img=img, out=torch.zeros_like(img), aux=aux))
+
+    def enqueue(s):
+        ops.warp_from_attention_tokens(s["attn"], s["img"], (g, g), None, "hwc", out=s["out"], aux=s["aux"])
+
+    serial = []
+    for s in sets:
+        enqueue(s)
+        serial.append((s["out"].clone(), s["aux"][0].clone(), s["aux"][1].clone()))
+        s["out"].zero_()
+    torch.cuda.synchronize()
+    graphs = [ops.GraphedCall(lambda s=s: enqueue(s)) for s in sets]
+    for s in sets:
+        s["out"].zero_()
+    ring = StreamRing(4)
+    ring.fork()
+    for rep in range(3):
+        for gph in graphs:
+            ring.submit(gph.replay)
+    ring.join()
+    torch.cuda.synchronize()
+    for s, (o, t, mx) in zip(sets, serial):
+        assert torch.equal(s["out"], o)
+        assert torch.equal(s["aux"][0], t)
+        assert torch.equal(s["aux"][1], mx)
