@@ -23,23 +23,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park the waiting thread for up to that long before try_wait
-// returns false: without it an idle role warp re-issues the test every few cycles and takes issue
-// slots from the warps that do the work (a tenth of all warp instructions in the resample kernel).
-#ifndef AW_WAIT_HINT_NS
-#define AW_WAIT_HINT_NS 20000
-#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity), "r"((uint32_t)AW_WAIT_HINT_NS)
+        "r"(parity)
         : "memory");
 }
 // global -> shared, completion counted in bytes on an mbarrier; addresses and size multiples of 16

@@ -46,19 +46,23 @@ namespace {
 
 using namespace ptx;
 
-// Tuned on B200 at 336^2 and 1344^2 (profiles/run_tune.sh): 3 source stages x 12 rows, 2 output tiles,
-// 3 CTAs per SM; 4-5 smaller CTAs per SM or deeper rings of smaller chunks are 3-20 % slower.
+// Tuned on B200 at 336^2 and 1344^2 (profiles/run_tune.sh, run_tune2.sh): 2 source stages x 16 rows, 2 output
+// tiles, 3 CTAs per SM (72 KB each).  3 x 12 rows is 1-2 % slower (a quarter more chunk prologues), 4 CTAs per
+// SM with 2 x 12 / 2 x 10 / 3 x 8 rows 2-8 % slower, a third output tile (3 x 10 + 3) 3 % slower.
 #ifndef AW_SRC_STAGES
-#define AW_SRC_STAGES 3
+#define AW_SRC_STAGES 2
 #endif
 #ifndef AW_OUT_STAGES
 #define AW_OUT_STAGES 2
 #endif
 #ifndef AW_ROWS
-#define AW_ROWS 12
+#define AW_ROWS 16
 #endif
 #ifndef AW_MIN_CTAS
 #define AW_MIN_CTAS 3
+#endif
+#ifndef AW_SKIP_SCAN
+#define AW_SKIP_SCAN 1
 #endif
 constexpr int kSrcStages = AW_SRC_STAGES;          // source-row stages (chunks whose loads are in flight) per CTA
 constexpr int kOutStages = AW_OUT_STAGES;          // output tiles per CTA
@@ -567,7 +571,16 @@ remap_u8_stream_kernel(const StreamArgs a) {
                 const float* mx = v.mx + x_first;
                 // source column span of the strip
                 int c_lo, row_bytes, slot_pitch, max_slots;
-                {
+                // A single strip over an image whose whole rows (multiples of 16 bytes) fit a stage R + 2 at a
+                // time: stage whole rows without looking for the span first (the maps of this library cover
+                // the image, so the span is the whole row anyway; the scan is 11 dependent-latency global
+                // loads on the critical path of the CTA's first chunk).
+                if (AW_SKIP_SCAN && v.n_strips == 1 && ((W * C) & 15) == 0 && (a.stage_bytes - 32) / (W * C) >= R + 2) {
+                    c_lo = 0;
+                    row_bytes = W * C;
+                    slot_pitch = row_bytes;
+                    max_slots = 0;      // both set below (one_copy)
+                } else {
                     int lo = 0x7fffffff, hi = -1;
                     for (int x = lane; x < ncols; x += 32) {
                         int xb, w0, w1;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- warped images/s of the attention-guided warp hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic input:
   c2 (default; BASELINE.json configs[1]): 256 x 336^2 RGB uint8 + bf16 attention
@@ -9,6 +9,7 @@ One "step" = one pass of the hot path over one batch of synthetic input:
       inverse-CDF maps -> bilinear resample (cv2.remap semantics) to 336^2.
   c3 (configs[2]): 64 x 1344^2 RGB uint8 + 48x48 token maps -> maps -> resample.
   c4 (configs[3]): 1024 mixed-resolution images, LPT-sharded over the ranks (strong scaling), ragged launches.
+  c5 (configs[4]): 128 x 3 x 512^2 float32 images + PDFs [128,24] x 2 -> fused PDF->CDF -> maps -> resample.
 For N > 1 (launched under torchrun, one rank per GPU) every rank processes its own batch
 (weak scaling, images sharded by index, no data-path collective); NCCL only gathers timings and
 checksums.  Rank 0 prints ONE JSON line.
@@ -48,6 +49,9 @@ WORKLOADS = {
     "c4": dict(name="c4: mixed-resolution batch of 1024 RGB u8 images (sides uniform in [224, 2048]) + 24x24 "
                     "token maps -> inverse-CDF warp at input size, ragged launches, LPT-sharded over the GPUs",
                B=1024, L=0, Hh=0, grid=24, side=0, C=3, has_attention=False, ragged=True),
+    "c5": dict(name="c5: MarginalNet-style PDFs (2 x [128,24], softmax of seeded logits, alpha=0.1) -> fused "
+                    "PDF->CDF + inverse-CDF maps + float32 resample of 128x3x512^2 images (NCHW)",
+               B=128, L=0, Hh=0, grid=24, side=512, C=3, has_attention=False, pdf=True),
 }
 
 
@@ -186,9 +190,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
-    if wl.get("ragged"):
+    if wl.get("ragged") or wl.get("pdf"):
         print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the bench workloads c2 and c3; "
-                          "c4 is a parity/scaling configuration"}), flush=True)
+                          "c4 and c5 are parity/scaling configurations"}), flush=True)
         return 0
     info, ms_per_step = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0,
                                 full_steps=True)
@@ -290,10 +294,109 @@ def run_gpu_ragged(args, rank, local_rank, world):
     return 0
 
 
+def run_gpu_pdf(args, rank, local_rank, world):
+    """configs[4]: predicted PDFs feeding the fused CDF + resample path (trainer.py:212-218, 285-289 chain):
+    a step = attwarp_warp_from_pdfs over one batch of 128 float32 NCHW images (three launches)."""
+    import torch
+    import torch.distributed as dist
+
+    from attwarp_b200 import ops, sharding
+
+    wl = WORKLOADS[args.workload]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, side, N = wl["B"], wl["C"], wl["side"], wl["grid"]
+    R = args.rotate if args.rotate > 0 else 3
+    gen = torch.Generator(device=dev).manual_seed(1238 + rank)
+    sets = []
+    for _ in range(R):
+        sets.append(dict(px=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
+                         py=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
+                         img=torch.rand(B, C, side, side, device=dev, generator=gen),
+                         out=torch.empty(B, C, side, side, device=dev)))
+
+    def enqueue(s):
+        ops.warp_from_pdfs(s["img"], s["px"], s["py"], alpha=0.1, layout="chw", out=s["out"])
+
+    graphs = None if args.no_graph else [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            enqueue(sets[i % R])
+        return 3
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ev0.record()
+    for i in range(args.steps):
+        launches += step(args.warmup + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    chk = int(sets[(args.warmup + args.steps - 1) % R]["out"][:2].double().sum().item() * 1e3)
+    stats = sharding.gather_stats(elapsed_ms, B * args.steps, chk, dev)
+    value = sharding.aggregate_throughput(stats)
+    worst_ms = max(s[0] for s in stats)
+    # the resample kernel alone: back-to-back launches with the maps of the last step
+    _, _, _, mx, my = ops.warp_from_pdfs(sets[0]["img"], sets[0]["px"], sets[0]["py"], alpha=0.1, layout="chw",
+                                         out=sets[0]["out"], return_aux=True)
+    kreps = max(10, min(args.steps, 30))
+    for i in range(3):
+        ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(kreps):
+        ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / kreps
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak()
+    by = B * C * side * side * 4 * 2
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (PDF/CDF rows), f64 (inversion), f32 (resample)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "images_per_step_per_gpu": B,
+                       "l2_policy": f"inputs rotate over {R} resident buffer sets; one batch is {by / 1e6:.0f} MB in+out > 126 MB L2",
+                       "parallelism": f"images sharded by index over {world} GPU(s), no data-path collective",
+                       "launch": "one CUDA graph replay per step" if graphs is not None else "eager launches"},
+            "clocks": clocks, "e2e": None, "gpu_launches": launches * world,
+            "roofline": {"bound": "hbm", "kernel": "remap_f32_rows_kernel", "achieved": by / kms / 1e6, "peak": peak,
+                         "unit": "GB/s", "frac": by / kms / 1e6 / peak, "traffic": ncu_traffic("remap_f32_rows_kernel", "c5"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": by, "kernel_ms": kms},
+            "cpu_baseline": None, "per_rank_ms": [s[0] for s in stats]}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_gpu(args, rank, local_rank, world):
     wl = WORKLOADS[args.workload]
     if wl.get("ragged"):
         return run_gpu_ragged(args, rank, local_rank, world)
+    if wl.get("pdf"):
+        return run_gpu_pdf(args, rank, local_rank, world)
     cpu_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised (the pool forks)
@@ -429,22 +532,33 @@ def run_gpu(args, rank, local_rank, world):
             ms = sum(evs[k].elapsed_time(evs[k + 1]) for evs in stage_ev) / kreps
             kernels[nm] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
                            "frac": by / ms / 1e6 / peak, "how": "library stage events inside the fused call"}
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(3):
-        s = sets[i % R]
-        ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"])
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(kreps):
-        s = sets[i % R]
-        ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"])
-    e1.record()
-    torch.cuda.synchronize()
+    def back_to_back(fn):
+        """Average duration of one launch of a kernel launched kreps times in a row over the rotating
+        sets (the launch of kernel n+1 overlaps kernel n, so there is no launch gap in the figure)."""
+        for i in range(3):
+            fn(sets[i % R])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(kreps):
+            fn(sets[i % R])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / kreps
+
+    how = f"{kreps} back-to-back launches over the rotating sets"
+    ms = back_to_back(lambda s: ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"]))
     by = B * side * side * C * 2
-    ms = e0.elapsed_time(e1) / kreps
     kernels["remap_u8_stream_kernel"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
-                                        "frac": by / ms / 1e6 / peak,
-                                        "how": f"{kreps} back-to-back launches over the rotating sets"}
+                                        "frac": by / ms / 1e6 / peak, "how": how}
+    if wl["has_attention"]:
+        # stage 1 alone (the stage events above include the gap between the event and the kernel start)
+        k1 = kernels["aggregate_rows_tma_kernel"]
+        ms = back_to_back(lambda s: ops.aggregate_attention(s["attn"], out=s["aux"][0]))
+        by = k1["algorithmic_bytes"]
+        kernels["aggregate_rows_tma_kernel"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
+                                                "frac": by / ms / 1e6 / peak, "how": how,
+                                                "ms_between_stage_events": k1["ms"]}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.workload),
