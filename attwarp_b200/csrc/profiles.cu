@@ -9,6 +9,8 @@
 // many CTAs per image) and O(H+W) afterwards (one CTA per image: block scan in shared memory,
 // knots in shared memory, one bisection per output coordinate).  The 2-D meshgrid of the
 // reference (new_method.py:263-265) is never built: the maps stay separable.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace aw {
@@ -227,6 +229,174 @@ marginals_partial_kernel(const T* __restrict__ att, int H, int W, TransformArgs 
     }
 }
 
+// (P2b) the driver case of (P2): uint8 attention map (the mask blend_mask returns, main.py:361), identity
+// transform, rows that are multiples of 16 bytes.  HBM-bound as it should be: every lane reads 16 pixels
+// per load (8-12 loads in flight per lane: rows x 512-column steps), a warp owns whole rows of its column tile
+// (row sum = 4 dp4a per load + one REDUX per row), column sums are carried as packed 16-bit lanes (a warp
+// adds at most 256 / 8 = 32 rows of <= 255 before they are widened) and combined across the CTA's warps
+// in shared memory.  All sums are exact integers; the + 1e-9 per element (new_method.py:212) is added as
+// count x 1e-9 when the partial is written (differs from the reference's term-by-term float64 sum by
+// < 1e-15 relative).  Partial layout and finish kernel as (P2), with its own chunk / tile geometry.
+constexpr int kU8TileCols = 1536, kU8MaxRows = 256;
+// STEPS: 512-column steps a warp takes across its tile (tile_cols <= 512 * STEPS); U: rows in flight per warp
+template <int STEPS, int U>
+__global__ void __launch_bounds__(kMargThreads)
+marginals_u8_identity_kernel(const uint8_t* __restrict__ att, int H, int W, int rows_per_cta,
+                             double* __restrict__ colpart, double* __restrict__ rowpart, int n_row_chunks,
+                             int n_col_tiles) {
+    constexpr int kWarps = kMargThreads / 32;
+    __shared__ uint32_t cw[kWarps][STEPS * 32 * 8];        // per warp: the packed accumulators, as they are
+    const int b = blockIdx.z, chunk = blockIdx.y, tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int y0 = chunk * rows_per_cta, y1 = min(y0 + rows_per_cta, H);
+    const int xt = tile * kU8TileCols;                     // first column of the tile
+    const int tile_cols = min(kU8TileCols, W - xt);
+    const uint8_t* img = att + (int64_t)b * H * W + xt;
+
+    uint32_t acc[STEPS][8];                                // [step][2 * word + odd]: two 16-bit column sums
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[s][k] = 0u;
+    double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
+    const double row_base = (double)tile_cols * kBaseAttention;
+    for (int y = y0 + wid; y < y1; y += U * kWarps) {
+        uint4 v[U][STEPS];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool row_in = y + u * kWarps < y1;
+            const uint8_t* r = img + (int64_t)(y + u * kWarps) * W;
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int x = s * 512 + lane * 16;
+                v[u][s] = (row_in && x < tile_cols) ? __ldg(reinterpret_cast<const uint4*>(r + x))
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        uint32_t rs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            rs[u] = 0u;
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const uint32_t a[4] = {v[u][s].x, v[u][s].y, v[u][s].z, v[u][s].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    rs[u] = __dp4a(a[k], 0x01010101u, rs[u]);
+                    acc[s][2 * k] += a[k] & 0x00ff00ffu;
+                    acc[s][2 * k + 1] += (a[k] >> 8) & 0x00ff00ffu;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = __reduce_add_sync(0xffffffffu, rs[u]);
+            if (lane == 0 && y + u * kWarps < y1) rp[y + u * kWarps] = (double)t + row_base;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cw[wid][(s * 32 + lane) * 8 + k] = acc[s][k];
+    __syncthreads();
+    double* cp = colpart + ((int64_t)b * n_row_chunks + chunk) * W + xt;
+    const double base = (double)(y1 - y0) * kBaseAttention;
+    for (int c = threadIdx.x; c < tile_cols; c += kMargThreads) {
+        // column c sits in word 2k + (q & 1), half q >> 1 of its lane's step block (k = word, q = byte)
+        const int blk = c >> 4, k = (c >> 2) & 3, q = c & 3;
+        const int wi = blk * 8 + 2 * k + (q & 1), sh = (q >> 1) * 16;
+        uint32_t t = 0u;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += (cw[w][wi] >> sh) & 0xffffu;
+        cp[c] = (double)t + base;
+    }
+}
+
+// Rows per CTA for (P2b) / (P2c): as many as possible (P2b: <= 256, the 16-bit lanes) without a ragged last wave:
+// minimise  waves x (rows + the epilogue's worth of rows)  over multiples of 8.
+static int rows_per_cta(int B, int H, int nct, int ctas_per_sm, int max_rows) {
+    const int64_t slots = ctas_per_sm * (int64_t)sm_count();
+    int best = kMargRows;
+    int64_t best_cost = -1;
+    for (int rows = kMargRows; rows <= max_rows; rows += 8) {      // >= kMargRows: the workspace is sized for those
+        const int64_t ctas = (int64_t)B * nct * ((H + rows - 1) / rows);
+        const int64_t cost = ((ctas + slots - 1) / slots) * (rows + 24);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && rows > best)) { best_cost = cost; best = rows; }
+    }
+    return best;
+}
+
+// (P2c) float32 attention maps with rows that are multiples of 4 floats (gt_marginals' A_full,
+// checkpoint_utils.py:43-51; float att maps of the NumPy path): the (P2b) organisation in float64.
+// A warp owns whole rows of a 512-column tile (4 float4 loads per lane and row, two rows in flight), column
+// sums stay in 16 float64 registers per lane, the row sum is one shuffle tree per ROW (the generic kernel
+// pays one per 128 columns), warps are combined in shared memory in warp order -> deterministic.
+constexpr int kF32TileCols = 512;
+template <int MODE>
+__global__ void __launch_bounds__(kMargThreads)
+marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_per_cta, TransformArgs ta,
+                          double* __restrict__ colpart, double* __restrict__ rowpart, int n_row_chunks,
+                          int n_col_tiles) {
+    constexpr int kWarps = kMargThreads / 32, kSteps = kF32TileCols / 128, U = 2;
+    extern __shared__ double cwd[];                        // [kWarps][kF32TileCols]
+    const int b = blockIdx.z, chunk = blockIdx.y, tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int y0 = chunk * rows_per_cta, y1 = min(y0 + rows_per_cta, H);
+    const int xt = tile * kF32TileCols;
+    const int tile_cols = min(kF32TileCols, W - xt);
+    const float* img = att + (int64_t)b * H * W + xt;
+    double acc[kSteps][4];
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[s][k] = 0.0;
+    double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
+    for (int y = y0 + wid; y < y1; y += U * kWarps) {
+        float4 v[U][kSteps];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool row_in = y + u * kWarps < y1;
+            const float* r = img + (int64_t)(y + u * kWarps) * W;
+#pragma unroll
+            for (int s = 0; s < kSteps; ++s) {
+                const int x = s * 128 + lane * 4;
+                v[u][s] = (row_in && x < tile_cols) ? __ldg(reinterpret_cast<const float4*>(r + x))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool row_in = y + u * kWarps < y1;
+            double rs = 0.0;
+#pragma unroll
+            for (int s = 0; s < kSteps; ++s) {
+                const bool in = row_in && s * 128 + lane * 4 < tile_cols;
+                const float f[4] = {v[u][s].x, v[u][s].y, v[u][s].z, v[u][s].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double a = clamp_nonneg((double)f[k]);
+                    if (MODE == 0) a = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
+                    if (in) { acc[s][k] += a; rs += a; }
+                }
+            }
+            rs = warp_sum(rs);
+            if (lane == 0 && row_in) rp[y + u * kWarps] = rs;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cwd[wid * kF32TileCols + s * 128 + lane * 4 + k] = acc[s][k];
+    __syncthreads();
+    double* cp = colpart + ((int64_t)b * n_row_chunks + chunk) * W + xt;
+    for (int c = threadIdx.x; c < tile_cols; c += kMargThreads) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += cwd[w * kF32TileCols + c];
+        cp[c] = t;
+    }
+}
+
 // (P3) finish: sum the partials in fixed order, then the shared tail.
 __global__ void __launch_bounds__(2 * kProfThreads)
 maps_from_partials_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
@@ -345,9 +515,11 @@ TransformArgs to_args(const attwarp_transform_params& tp) {
 
 }  // namespace
 
+// Workspace geometry: the finest tiling any marginals kernel uses (64-row chunks, 512-column tiles); every
+// kernel reports the chunk / tile counts it actually wrote and the finish kernels sum exactly those.
 void marginals_geometry(int H, int W, int* n_row_chunks, int* n_col_tiles) {
     *n_row_chunks = (H + kMargRows - 1) / kMargRows;
-    *n_col_tiles = (W + kMargCols - 1) / kMargCols;
+    *n_col_tiles = (W + kF32TileCols - 1) / kF32TileCols;
 }
 
 int launch_maps_from_tokens(const float* tok, int nsplit, float scale, float* tok_out, int B,
@@ -376,13 +548,51 @@ int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, cons
     return check_launch("maps_from_tokens_kernel");
 }
 
+// One pass over the attention maps -> column / row partials.  Picks the kernel, launches it and reports the
+// number of row chunks / column tiles it wrote (<= marginals_geometry's, which sizes the workspace).
 template <typename T, int MODE>
 static int launch_marginals(const void* att, int B, int H, int W, const TransformArgs& ta,
-                            double* colpart, double* rowpart, cudaStream_t st) {
-    int nrc, nct;
-    marginals_geometry(H, W, &nrc, &nct);
+                            double* colpart, double* rowpart, cudaStream_t st, int* nrc_out, int* nct_out) {
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(att) & 15) == 0;
+    if (std::is_same<T, uint8_t>::value && MODE == 0 && ta.transform == T_IDENTITY && (W & 15) == 0 && aligned16) {
+        static_assert(kU8MaxRows / (kMargThreads / 32) * 255 < 65536, "16-bit column lanes would overflow");
+        const int nct = (W + kU8TileCols - 1) / kU8TileCols;
+        const int cols = W < kU8TileCols ? W : kU8TileCols;
+        auto kern = cols <= 512 ? marginals_u8_identity_kernel<1, 8>
+                  : cols <= 1024 ? marginals_u8_identity_kernel<2, 4> : marginals_u8_identity_kernel<3, 4>;
+        static thread_local int occ[3] = {0, 0, 0};
+        int& o = occ[cols <= 512 ? 0 : cols <= 1024 ? 1 : 2];
+        if (o == 0) {
+            AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kMargThreads, 0));
+            if (o < 1) o = 1;
+        }
+        const int rows = rows_per_cta(B, H, nct, o, kU8MaxRows);
+        const int nrc = (H + rows - 1) / rows;
+        kern<<<dim3(nct, nrc, B), kMargThreads, 0, st>>>(static_cast<const uint8_t*>(att), H, W, rows, colpart,
+                                                      rowpart, nrc, nct);
+        *nrc_out = nrc; *nct_out = nct;
+        return check_launch("marginals_u8_identity_kernel");
+    }
+    if (std::is_same<T, float>::value && (W & 3) == 0 && aligned16) {
+        const int nct = (W + kF32TileCols - 1) / kF32TileCols;
+        auto kern = marginals_f32_rows_kernel<MODE>;
+        const size_t smem = sizeof(double) * (kMargThreads / 32) * kF32TileCols;
+        static thread_local int occ = 0;
+        if (occ == 0) {
+            AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMargThreads, smem));
+            if (occ < 1) occ = 1;
+        }
+        const int rows = rows_per_cta(B, H, nct, occ, 256);
+        const int nrc = (H + rows - 1) / rows;
+        kern<<<dim3(nct, nrc, B), kMargThreads, smem, st>>>(static_cast<const float*>(att), H, W, rows, ta, colpart,
+                                                         rowpart, nrc, nct);
+        *nrc_out = nrc; *nct_out = nct;
+        return check_launch("marginals_f32_rows_kernel");
+    }
+    const int nrc = (H + kMargRows - 1) / kMargRows, nct = (W + kMargCols - 1) / kMargCols;
     marginals_partial_kernel<T, MODE><<<dim3(nct, nrc, B), kMargThreads, 0, st>>>(
         static_cast<const T*>(att), H, W, ta, colpart, rowpart, nrc, nct);
+    *nrc_out = nrc; *nct_out = nct;
     return check_launch("marginals_partial_kernel");
 }
 
@@ -405,9 +615,9 @@ int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int
     const TransformArgs ta = to_args(tp);
     int rc;
     switch (att_dtype) {
-        case ATTWARP_U8: rc = launch_marginals<uint8_t, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
-        case ATTWARP_F32: rc = launch_marginals<float, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
-        case ATTWARP_F64: rc = launch_marginals<double, 0>(att, B, H, W, ta, colpart, rowpart, st); break;
+        case ATTWARP_U8: rc = launch_marginals<uint8_t, 0>(att, B, H, W, ta, colpart, rowpart, st, &nrc, &nct); break;
+        case ATTWARP_F32: rc = launch_marginals<float, 0>(att, B, H, W, ta, colpart, rowpart, st, &nrc, &nct); break;
+        case ATTWARP_F64: rc = launch_marginals<double, 0>(att, B, H, W, ta, colpart, rowpart, st, &nrc, &nct); break;
         default: return fail(ATTWARP_ERR_INVALID_ARG, "attention map dtype must be u8/f32/f64 (got %d)", att_dtype);
     }
     if (rc != ATTWARP_OK) return rc;
@@ -428,7 +638,7 @@ int launch_gt_marginals(const float* A, int B, int H, int W, void* ws, size_t ws
     double* colpart = static_cast<double*>(ws);
     double* rowpart = colpart + (size_t)B * nrc * W;
     TransformArgs ta = {0, 0, 1.0, 1.0};
-    int rc = launch_marginals<float, 1>(A, B, H, W, ta, colpart, rowpart, st);
+    int rc = launch_marginals<float, 1>(A, B, H, W, ta, colpart, rowpart, st, &nrc, &nct);
     if (rc != ATTWARP_OK) return rc;
     gt_marginals_finish_kernel<<<dim3(B, 2), kProfThreads, 0, st>>>(colpart, rowpart, nrc, nct, H, W, px, py);
     return check_launch("gt_marginals_finish_kernel");

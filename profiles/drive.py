@@ -36,7 +36,7 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["remap", "agg", "maps", "ragged"])
+    ap.add_argument("what", choices=["remap", "agg", "maps", "ragged", "att"])
     ap.add_argument("--side", type=int, default=336)
     ap.add_argument("--out-side", type=int, default=0)
     ap.add_argument("--batch", type=int, default=256)
@@ -62,6 +62,21 @@ def main():
         print(f"ragged x{B} ({by / 2e6:.0f} MB in): us {[round(t, 1) for t in ts]}  GB/s {[round(by / t / 1e3, 1) for t in ts]}")
         return
     So = a.out_side or S
+    if a.what == "att":
+        # stage 2b of the NumPy path: marginals of a materialised attention map [B,H,W] (uint8 or float32)
+        if (a.dtype or "u8") == "u8":
+            sets = [torch.randint(0, 256, (B, S, S), device=dev, dtype=torch.uint8, generator=g) for _ in range(3)]
+        else:
+            sets = [torch.rand(B, S, S, device=dev, generator=g) for _ in range(3)]
+        k = [0]
+
+        def run():
+            ops.maps_from_attention(sets[k[0] % 3], (So, So))
+            k[0] += 1
+        ts = timed(run, a.iters)
+        by = sets[0].numel() * sets[0].element_size()
+        print(f"maps_from_attention {a.dtype or 'u8'} {S}^2 x{B}: us {[round(t, 1) for t in ts]}  GB/s {[round(by / t / 1e3, 1) for t in ts]}")
+        return
     if a.what in ("remap", "maps"):
         tok = torch.rand(B, G, G, device=dev, generator=g) ** 3
         tok = tok / tok.sum(dim=(1, 2), keepdim=True)

@@ -113,3 +113,54 @@ def test_error_behaviour():
     assert new_method.set_transform_function("nope") == "identity"
     assert new_method.save_warped_image("/nonexistent.png", np.zeros((4, 4)), None, None,
                                         "/tmp/x.png") is False
+
+
+@pytest.mark.parametrize("H,W", [(1, 16), (63, 336), (64, 336), (65, 1024), (200, 1040), (130, 1344), (70, 2064)])
+def test_u8_identity_marginals_fast_path(H, W):
+    """uint8 attention maps with rows of 16-byte multiples take the integer marginals kernel; it must
+    agree with the float64 oracle profile sums and with the generic kernel (same map as float32)."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(H * 31 + W)
+    B = 3
+    att = rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+    att[1] = 0                                             # all-zero map: + 1e-9 only -> identity warp
+    att[2, :, : W // 2] = 0
+    Ho, Wo = max(H, 2) + 3, W + 5
+    mx, my = ops.maps_from_attention(dev(att), (Ho, Wo), "identity")
+    gx, gy = ops.maps_from_attention(dev(att.astype(np.float32)), (Ho, Wo), "identity")
+    assert np.abs(mx.cpu().numpy() - gx.cpu().numpy()).max() <= 1e-4
+    assert np.abs(my.cpu().numpy() - gy.cpu().numpy()).max() <= 1e-4
+    for b in range(B):
+        _, rx, ry = ON.warp_image_by_attention(np.zeros((H, W, 3), np.uint8), att[b], Wo, Ho, "identity",
+                                               return_maps=True)
+        assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4
+
+
+@pytest.mark.parametrize("H,W,transform", [(1, 4, "identity"), (63, 336, "sqrt"), (130, 512, "identity"),
+                                            (70, 516, "square"), (129, 1028, "identity"), (66, 1344, "sqrt"),
+                                            (40, 333, "identity")])
+def test_f32_marginals_rows_kernel(H, W, transform):
+    """float32 attention maps with rows of 4-float multiples take the row-owning float64 kernel (W = 333
+    keeps the generic one): maps must match the float64 oracle; gt_marginals must match its definition."""
+    need_gpu()
+    from attwarp_b200 import ops, checkpoint_utils as CU
+    rng = np.random.default_rng(H * 17 + W)
+    B = 3
+    att = (rng.random((B, H, W)) ** 3).astype(np.float32)
+    att[1, :, W // 3:] = 0.0
+    att[2] -= 0.2                                          # negatives are clamped
+    Ho, Wo = max(H, 2) + 3, W + 5
+    mx, my = ops.maps_from_attention(dev(att), (Ho, Wo), transform)
+    for b in range(B):
+        _, rx, ry = ON.warp_image_by_attention(np.zeros((H, W, 3), np.uint8), att[b], Wo, Ho, transform,
+                                               return_maps=True)
+        assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4
+    px, py = CU.gt_marginals(dev(att)[:, None])
+    a = np.maximum(att.astype(np.float64), 0.0)
+    rpx = a.sum(1) / np.maximum(a.sum(1).sum(1, keepdims=True), 1e-6)
+    rpy = a.sum(2) / np.maximum(a.sum(2).sum(1, keepdims=True), 1e-6)
+    assert np.abs(px.cpu().numpy() - rpx).max() <= 1e-5 * rpx.max() + 1e-9
+    assert np.abs(py.cpu().numpy() - rpy).max() <= 1e-5 * rpy.max() + 1e-9
