@@ -128,6 +128,108 @@ resize_lanczos_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
     }
 }
 
+// ---- the up-scaling case (a token-grid mask to image size: <= 8 taps per axis) ----------------------
+// Same arithmetic, organised for throughput: the CTA owns a tile of output rows of one image, computes the
+// horizontal pass of the (few) source rows the tile taps into shared memory once, then every thread owns
+// FOUR adjacent output columns and walks down its share of the tile's rows with the tapped rows of the
+// horizontal pass held in registers as a sliding window (the window moves one source row every Ho / h
+// output rows); an output row is 8 x 4 IMAD with coefficients broadcast from shared memory, clip, one
+// 32-bit store.  Zero-padded coefficient rows make every output row an 8-tap row.
+constexpr int kUpTaps = 8;        // most taps per axis (coefficient rows in shared memory are padded to 8)
+__device__ __forceinline__ void unpack4(uint32_t w, int* v) {
+    v[0] = (int)(w & 0xffu); v[1] = (int)((w >> 8) & 0xffu); v[2] = (int)((w >> 16) & 0xffu); v[3] = (int)(w >> 24);
+}
+__device__ __forceinline__ uint32_t clip8(int acc) { return (uint32_t)clampi(acc >> kPrecisionBits, 0, 255); }
+
+constexpr int kUpMaxThreads = 512;
+template <int TAPS>     // taps per axis actually used (7 for pure up-scaling)
+__global__ void __launch_bounds__(kUpMaxThreads)
+resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, int Wo,
+                         const int2* __restrict__ bx, const int* __restrict__ kx, int ksx,
+                         const int2* __restrict__ by, const int* __restrict__ ky, int ksy,
+                         int rows_per_tile, int n_rowgroups, uint8_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t sm_b[];
+    const int Wp = (Wo + 3) & ~3;                        // pitch of the horizontal pass
+    const int b = blockIdx.y;
+    const int y0 = blockIdx.x * rows_per_tile, y1 = min(y0 + rows_per_tile, Ho);
+    const int r0 = by[y0].x;
+    const int nr = by[y1 - 1].x + by[y1 - 1].y - r0;     // source rows the tile taps: [r0, r0 + nr)
+    int4* coef = reinterpret_cast<int4*>(sm_b);          // [rows_per_tile][2] int4: 8 coefficients per output row
+    int* ymin = reinterpret_cast<int*>(sm_b + (size_t)rows_per_tile * 32);      // [rows_per_tile], relative to r0
+    uint8_t* in = sm_b + (size_t)rows_per_tile * 36;                            // [nr][w]
+    uint8_t* tmp = in + (((size_t)h * w + 15) & ~(size_t)15);                   // [nr][Wp]
+    const uint8_t* img = src + ((int64_t)b * h + r0) * w;
+    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) in[i] = img[i];
+    for (int i = threadIdx.x; i < (y1 - y0) * kUpTaps; i += blockDim.x) {
+        const int yy = i >> 3, t = i & 7;
+        reinterpret_cast<int*>(coef)[i] = t < ksy ? __ldg(ky + (int64_t)(y0 + yy) * ksy + t) : 0;
+        if (t == 0) ymin[yy] = by[y0 + yy].x - r0;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < Wp; x += blockDim.x) {                      // horizontal pass, column x
+        int k[TAPS], c0 = 0;
+        if (x < Wo) c0 = bx[x].x;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) k[t] = (x < Wo && t < ksx) ? __ldg(kx + (int64_t)x * ksx + t) : 0;
+        for (int r = 0; r < nr; ++r) {
+            int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) acc += (int)in[r * w + min(c0 + t, w - 1)] * k[t];
+            tmp[r * Wp + x] = (uint8_t)clip8(acc);
+        }
+    }
+    __syncthreads();
+    // vertical pass: thread = (row group, column group of 4)
+    const int n_cg = Wp >> 2;
+    const int rg = threadIdx.x / n_cg;
+    if (rg >= n_rowgroups) return;
+    const int cg = threadIdx.x - rg * n_cg;
+    const int rows = y1 - y0;
+    const int ya = (int)(((int64_t)rows * rg) / n_rowgroups), yb = (int)(((int64_t)rows * (rg + 1)) / n_rowgroups);
+    const bool vec = (Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+    uint8_t* out = dst + ((int64_t)b * Ho + y0) * Wo;
+    {
+        const int g = cg;               // one column group per thread (the launcher sizes the CTA so)
+        int win[TAPS][4];
+        int base = -1000;
+        for (int yy = ya; yy < yb; ++yy) {
+            const int ym = ymin[yy];
+            if (ym != base) {
+                if (ym == base + 1) {
+#pragma unroll
+                    for (int t = 0; t < TAPS - 1; ++t)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) win[t][q] = win[t + 1][q];
+                    unpack4(*reinterpret_cast<const uint32_t*>(tmp + min(ym + TAPS - 1, nr - 1) * Wp + 4 * g), win[TAPS - 1]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < TAPS; ++t)
+                        unpack4(*reinterpret_cast<const uint32_t*>(tmp + min(ym + t, nr - 1) * Wp + 4 * g), win[t]);
+                }
+                base = ym;
+            }
+            const int4 ca = coef[2 * yy], cb = coef[2 * yy + 1];
+            const int c[kUpTaps] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+            int acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = 1 << (kPrecisionBits - 1);
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += win[t][q] * c[t];
+            const uint32_t o = clip8(acc[0]) | (clip8(acc[1]) << 8) | (clip8(acc[2]) << 16) | (clip8(acc[3]) << 24);
+            uint8_t* p = out + (int64_t)yy * Wo + 4 * g;
+            if (vec) {
+                *reinterpret_cast<uint32_t*>(p) = o;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * g + q < Wo) p[q] = (uint8_t)(o >> (8 * q));
+            }
+        }
+    }
+}
+
 // ---- coefficient tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc, Lanczos, support 3) ----
 double sinc_filter(double x) {
     if (x == 0.0) return 1.0;
@@ -218,6 +320,27 @@ int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, in
     if (Ho != h) {
         const int rc = get_table(h, Ho, &ty);
         if (rc != ATTWARP_OK) return rc;
+    }
+    // up-scaling (or any resize with <= 8 taps per axis) of both axes: the register-window kernel
+    const int Wp = (Wo + 3) & ~3, n_cg = Wp / 4;
+    if (Wo != w && Ho != h && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps && n_cg <= kUpMaxThreads) {
+        // tiles: enough CTAs to fill the GPU, as tall as possible (the horizontal pass is redone per tile)
+        int n_tiles = (2 * sm_count() + B - 1) / B;
+        n_tiles = n_tiles < 1 ? 1 : n_tiles;
+        if (n_tiles > (Ho + 31) / 32) n_tiles = (Ho + 31) / 32;
+        const int rows = (Ho + n_tiles - 1) / n_tiles;
+        n_tiles = (Ho + rows - 1) / rows;
+        const int n_rg = kUpMaxThreads / n_cg;
+        const int threads = (n_cg * n_rg + 31) & ~31;
+        const size_t smem_up = (size_t)rows * 36 + (((size_t)h * w + 15) & ~(size_t)15) + (size_t)h * Wp;
+        if (smem_up <= 200 * 1024) {
+            auto kern = (tx.ksize <= 7 && ty.ksize <= 7) ? resize_lanczos_up_kernel<7> : resize_lanczos_up_kernel<8>;
+            if (smem_up > 48 * 1024)
+                AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up));
+            kern<<<dim3(n_tiles, B), threads, smem_up, st>>>(
+                src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, rows, n_rg, dst);
+            return check_launch("resize_lanczos_up_kernel");
+        }
     }
     // shared memory: the source rows a tile taps (at most all of them) + their horizontal pass
     const size_t smem = (((size_t)h * w + 15) & ~(size_t)15) + (size_t)h * Wo;

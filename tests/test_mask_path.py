@@ -78,6 +78,7 @@ def test_gpu_lanczos_vs_pillow_batched():
     from attwarp_b200 import ops
     rng = np.random.default_rng(77)
     for (h, w, Ho, Wo) in [(24, 24, 336, 336), (24, 24, 500, 333), (24, 24, 224, 2048), (48, 48, 1344, 1344),
+                           (24, 24, 1344, 1344), (24, 24, 337, 339), (24, 24, 40, 2052), (16, 30, 31, 64),
                            (24, 24, 24, 100), (24, 24, 100, 24), (24, 24, 12, 40), (7, 13, 100, 9)]:
         m = rng.integers(0, 256, (5, h, w), dtype=np.uint8)
         got = ops.resize_lanczos_u8(torch.from_numpy(m).cuda(), (Ho, Wo)).cpu().numpy()
