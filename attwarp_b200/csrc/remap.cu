@@ -123,30 +123,50 @@ remap_f32_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, in
         s1[j] = clampi((sx >> 5) + 1, 0, W - 1) * E + c;
     }
     __syncthreads();
-    int cur_a = -1, cur_b = -1;            // source rows held in pa / pb
-    float pa0[kColsF32], pa1[kColsF32], pb0[kColsF32], pb1[kColsF32];
+    // Source rows held in registers: pa (upper tap), pb (lower tap) and pc, the lower row of the NEXT output
+    // row, requested one iteration ahead so that its latency overlaps this row's arithmetic (the taps of a row
+    // are otherwise consumed right after they are requested and the kernel is bound by bytes in flight).
+    // Offsets are 32-bit (the launcher checks that a plane has fewer than 2^31 elements).
+    int cur_a = -1, cur_b = -1, cur_c = -1;
+    float pa0[kColsF32], pa1[kColsF32], pb0[kColsF32], pb1[kColsF32], pc0[kColsF32], pc1[kColsF32];
+    float* op[kColsF32];
 #pragma unroll
-    for (int j = 0; j < kColsF32; ++j) pa0[j] = pa1[j] = pb0[j] = pb1[j] = 0.0f;
+    for (int j = 0; j < kColsF32; ++j) {
+        pa0[j] = pa1[j] = pb0[j] = pb1[j] = pc0[j] = pc1[j] = 0.0f;
+        op[j] = dp + e_out[j];
+        if (!valid[j]) { s0[j] = 0; s1[j] = 0; }         // loads stay in range, only the store is predicated
+    }
+    const int pitch32 = (int)src_pitch;
+    int4 rt = rowtab[0];
     for (int r = 0; r < nrows; ++r) {
-        const int4 rt = rowtab[r];
+        const int4 nx = rowtab[min(r + 1, nrows - 1)];
         if (rt.x != cur_a) {
             if (rt.x == cur_b) {
 #pragma unroll
                 for (int j = 0; j < kColsF32; ++j) { pa0[j] = pb0[j]; pa1[j] = pb1[j]; }
             } else {
-                const float* row = sp + (int64_t)rt.x * src_pitch;
+                const int ro = rt.x * pitch32;
 #pragma unroll
-                for (int j = 0; j < kColsF32; ++j)
-                    if (valid[j]) { pa0[j] = __ldg(row + s0[j]); pa1[j] = __ldg(row + s1[j]); }
+                for (int j = 0; j < kColsF32; ++j) { pa0[j] = __ldg(sp + (ro + s0[j])); pa1[j] = __ldg(sp + (ro + s1[j])); }
             }
             cur_a = rt.x;
         }
         if (rt.y != cur_b) {
-            const float* row = sp + (int64_t)rt.y * src_pitch;
+            if (rt.y == cur_c) {
 #pragma unroll
-            for (int j = 0; j < kColsF32; ++j)
-                if (valid[j]) { pb0[j] = __ldg(row + s0[j]); pb1[j] = __ldg(row + s1[j]); }
+                for (int j = 0; j < kColsF32; ++j) { pb0[j] = pc0[j]; pb1[j] = pc1[j]; }
+            } else {
+                const int ro = rt.y * pitch32;
+#pragma unroll
+                for (int j = 0; j < kColsF32; ++j) { pb0[j] = __ldg(sp + (ro + s0[j])); pb1[j] = __ldg(sp + (ro + s1[j])); }
+            }
             cur_b = rt.y;
+        }
+        if (nx.y != cur_b && nx.y != cur_c) {                // request the next row's lower tap now
+            const int ro = nx.y * pitch32;
+#pragma unroll
+            for (int j = 0; j < kColsF32; ++j) { pc0[j] = __ldg(sp + (ro + s0[j])); pc1[j] = __ldg(sp + (ro + s1[j])); }
+            cur_c = nx.y;
         }
         const float wy0 = __int_as_float(rt.z), wy1 = __int_as_float(rt.w);
 #pragma unroll
@@ -156,8 +176,11 @@ remap_f32_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, in
             w.w01 = fmul_nofma(wy0, wx1[j]);
             w.w10 = fmul_nofma(wy1, wx0[j]);
             w.w11 = fmul_nofma(wy1, wx1[j]);
-            if (valid[j]) dp[(int64_t)r * dst_pitch + e_out[j]] = bilinear_f32(pa0[j], pa1[j], pb0[j], pb1[j], w);
+            const float v = bilinear_f32(pa0[j], pa1[j], pb0[j], pb1[j], w);
+            if (valid[j]) *op[j] = v;
+            op[j] += dst_pitch;
         }
+        rt = nx;
     }
 }
 
@@ -221,7 +244,7 @@ int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C
         return launch_direct<uint8_t>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
     if (dtype == ATTWARP_F32) {
         const int64_t planes = layout == ATTWARP_LAYOUT_HWC ? B : (int64_t)B * C;
-        if (!force_direct() && planes <= 65535 && (int64_t)Wo * C < 0x7fffffff && (int64_t)W * C < 0x7fffffff)
+        if (!force_direct() && planes <= 65535 && (int64_t)Wo * C < 0x7fffffff && (int64_t)H * W * C < 0x7fffffff)
             return launch_f32_rows(static_cast<const float*>(src), static_cast<float*>(dst), layout, B, C, H, W,
                                    Ho, Wo, map_x, map_y, st);
         return launch_direct<float>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
