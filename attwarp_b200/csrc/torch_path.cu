@@ -178,24 +178,48 @@ __global__ void interp_linear_rows_kernel(const float* __restrict__ F, int N, in
     out[(int64_t)blockIdx.y * L + j] = fadd_nofma(fmul_nofma(lam0, row[i0]), fmul_nofma(lam1, row[i1]));
 }
 
-// adaptive_avg_pool2d: one warp per output cell, window [floor(i*H/gh), ceil((i+1)*H/gh)).
-__global__ void adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw,
-                                           float* __restrict__ out) {
-    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
-    if (cell >= gh * gw) return;
-    const int i = cell / gw, j = cell - i * gw;
+// adaptive_avg_pool2d (trainer.py:197,433,465): window [floor(i*H/gh), ceil((i+1)*H/gh)) per axis.
+// One CTA per (image, output row): the rows of the window are read once, coalesced (float4 per lane, four
+// rows in flight), into float64 column sums; the gw window sums of the row are then taken from shared
+// memory.  Rows shared by two windows (H % gh != 0) are read by two CTAs: + gh / H of traffic.
+__global__ void __launch_bounds__(128)
+adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw, float* __restrict__ out) {
+    extern __shared__ double cs[];                         // [W] column sums over the window's rows
+    const int i = blockIdx.x, b = blockIdx.y;
     const int y0 = (int)(((int64_t)i * H) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
-    const int x0 = (int)(((int64_t)j * W) / gw), x1 = (int)(((int64_t)(j + 1) * W + gw - 1) / gw);
     const float* img = A + (int64_t)b * H * W;
-    const int ww = x1 - x0, n = (y1 - y0) * ww;
-    double s = 0.0;
-    for (int e = lane; e < n; e += 32) {
-        const int yy = e / ww, xx = e - yy * ww;
-        s += (double)__ldg(img + (int64_t)(y0 + yy) * W + x0 + xx);
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    if (vec) {
+        for (int x = threadIdx.x * 4; x < W; x += blockDim.x * 4) {
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int y = y0; y < y1; y += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = y + u < y1 ? __ldg(reinterpret_cast<const float4*>(img + (int64_t)(y + u) * W + x))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[0] += (double)v[u].x; a[1] += (double)v[u].y; a[2] += (double)v[u].z; a[3] += (double)v[u].w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cs[x + k] = a[k];
+        }
+    } else {
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            double a = 0.0;
+            for (int y = y0; y < y1; ++y) a += (double)__ldg(img + (int64_t)y * W + x);
+            cs[x] = a;
+        }
     }
-    s = warp_sum(s);
-    if (lane == 0) out[(int64_t)b * gh * gw + cell] = (float)(s / (double)n);
+    __syncthreads();
+    for (int j = threadIdx.x; j < gw; j += blockDim.x) {
+        const int x0 = (int)(((int64_t)j * W) / gw), x1 = (int)(((int64_t)(j + 1) * W + gw - 1) / gw);
+        double t = 0.0;
+        for (int x = x0; x < x1; ++x) t += cs[x];
+        out[((int64_t)b * gh + i) * gw + j] = (float)(t / (double)((y1 - y0) * (x1 - x0)));
+    }
 }
 
 }  // namespace
@@ -263,9 +287,12 @@ int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_o
 
 int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                cudaStream_t st) {
-    const int warps_per_cta = 8;
-    adaptive_avg_pool2d_kernel<<<dim3((gh * gw + warps_per_cta - 1) / warps_per_cta, B),
-                                 warps_per_cta * 32, 0, st>>>(A, H, W, gh, gw, out);
+    if (gh > 65535 || B > 65535) return fail(ATTWARP_ERR_UNSUPPORTED, "adaptive_avg_pool2d: grid too large");
+    const size_t smem = sizeof(double) * (size_t)W;
+    if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "adaptive_avg_pool2d: W=%d too wide", W);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(adaptive_avg_pool2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    adaptive_avg_pool2d_kernel<<<dim3(gh, B), 128, smem, st>>>(A, H, W, gh, gw, out);
     return check_launch("adaptive_avg_pool2d_kernel");
 }
 

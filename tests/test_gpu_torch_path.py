@@ -72,6 +72,11 @@ def test_cdf_marginals_pool(golden_torch):
     rx, ry = OT.gt_marginals(big)
     mx, my = cu.gt_marginals(dev(big))
     assert rel_err(mx.cpu().numpy(), rx) <= 1e-5 and rel_err(my.cpu().numpy(), ry) <= 1e-5
+    # odd shapes: scalar path (W % 4 != 0), windows of one pixel, up-sampling windows (H < gh)
+    for (H, W) in [(97, 53), (24, 24), (10, 36), (336, 500)]:
+        a = np.random.default_rng(H + W).random((3, 1, H, W)).astype(np.float32)
+        ref = torch.nn.functional.adaptive_avg_pool2d(torch.from_numpy(a), (24, 24)).numpy()
+        assert rel_err(cu.adaptive_avg_pool2d_24(dev(a)).cpu().numpy(), ref) <= 1e-5, (H, W)
 
 
 def test_resample_cdf_and_strictly_increasing(golden_torch):
