@@ -99,7 +99,7 @@ __device__ __forceinline__ void st8(int off, uint32_t v) { smem[off] = (uint8_t)
 constexpr int kTabRows = 64;
 constexpr uint32_t kRowSentinel = 0x7fffffffu;
 template <int R> constexpr int tab_slots() { return kTabRows + 16 * (R + 1); }
-template <int R> constexpr int tab_bytes() { return tab_slots<R>() + 4 * 2 * R; }
+template <int R> constexpr int tab_bytes() { return tab_slots<R>() + 4 * 2 * R + 16; }   // + the entry after the last slot
 constexpr uint32_t kFlagNewStrip = 1u, kFlagUniform = 2u;
 constexpr int kNoCarry = -(1 << 29);
 
@@ -334,6 +334,16 @@ __device__ __forceinline__ void sweep_c1(uint32_t* P, int n_slots, uint32_t cur_
     "prmt.b32 %4, %4, h4, 0x5432;\n"                            \
     "prmt.b32 %5, %5, h5, 0x5432;\n"
 #define AW_SW2_BLEND(SHA, SHB) AW_SW2_LOAD AW_SW2_ALIGN(SHA, SHB) AW_SW2_DOT
+// non-uniform phase: window addresses and shifts of the next slot from slot_base[] (sp walks the table)
+#define AW_SW2_ADDR_T                                           \
+    "ld.shared.b32 t, [sp];\n"                                  \
+    "add.u32 sp, sp, 4;\n"                                      \
+    "add.u32 ta, t, %7;\n"                                      \
+    "add.u32 tb, t, %8;\n"                                      \
+    "and.b32 ca, ta, 0xfffffffc;\n"                             \
+    "and.b32 cb, tb, 0xfffffffc;\n"                             \
+    "shl.b32 sha, ta, 3;\n"                                     \
+    "shl.b32 shb, tb, 3;\n"
 #define AW_SW2_EMIT                                             \
     "dp2a.lo.u32.u32 r0, %0, ex, ew;\n"                         \
     "dp2a.lo.u32.u32 r1, %1, ex, ew;\n"                         \
@@ -383,15 +393,11 @@ __device__ __forceinline__ void sweep_c3x2(uint32_t* P, int n_slots, uint32_t ca
             ".reg .b32 r0, r1, r2, r3, r4, r5, o, o2, ca, cb, sp, rp, ex, ey, ez, ew;\n"
             "setp.ne.u32 pb, %26, 0;\n"
             "mov.b32 sp, %9;\n mov.b32 rp, %11;\n" AW_SW_PRE_BEGIN AW_SW2_EMIT AW_SW_PRE_END("%6")
-            "SLOT:\n"
-            "ld.shared.b32 t, [sp];\n"
-            "add.u32 sp, sp, 4;\n"
-            "add.u32 ta, t, %7;\n"
-            "add.u32 tb, t, %8;\n"
-            "and.b32 ca, ta, 0xfffffffc;\n"
-            "and.b32 cb, tb, 0xfffffffc;\n"
-            "shl.b32 sha, ta, 3;\n"
-            "shl.b32 shb, tb, 3;\n" AW_SW2_BLEND("sha", "shb") AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
+            // software pipeline as in the uniform variant: the window of slot s + 1 is addressed and requested
+            // before slot s is blended (slot_base has a harmless entry after the last slot)
+            AW_SW2_ADDR_T AW_SW2_LOAD
+            "SLOT:\n" AW_SW2_ALIGN("sha", "shb") AW_SW2_ADDR_T AW_SW2_LOAD AW_SW2_DOT
+            AW_SW_ROWCTL_BEGIN AW_SW2_EMIT AW_SW_ROWCTL_END("%6")
             "@p bra.uni SLOT;\n"
             "DONE:\n"
             "}\n"
@@ -672,7 +678,11 @@ remap_u8_stream_kernel(const StreamArgs a) {
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, kRowSentinel, 0u));
                     }
-                    if (!uni && lane < n_slots) st32(tab + tab_slots<R>() + 4 * lane, (uint32_t)(lane * slot_pitch + off));
+                    if (!uni) {
+                        if (lane < n_slots) st32(tab + tab_slots<R>() + 4 * lane, (uint32_t)(lane * slot_pitch + off));
+                        // the two-column sweep requests one slot ahead: a valid address after the last slot
+                        if (lane == 0) st32(tab + tab_slots<R>() + 4 * n_slots, 0u);
+                    }
                     if (lane == 0) {
                         st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (seg_flags << 16),
                                               (uint32_t)slot_pitch, (uint32_t)phase));

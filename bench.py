@@ -301,6 +301,7 @@ def run_gpu_pdf(args, rank, local_rank, world):
     import torch.distributed as dist
 
     from attwarp_b200 import ops, sharding
+    from attwarp_b200.batched import StreamRing
 
     wl = WORKLOADS[args.workload]
     torch.cuda.set_device(local_rank)
@@ -321,16 +322,28 @@ def run_gpu_pdf(args, rank, local_rank, world):
         ops.warp_from_pdfs(s["img"], s["px"], s["py"], alpha=0.1, layout="chw", out=s["out"])
 
     graphs = None if args.no_graph else [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
+    n_streams = max(1, min(args.streams if args.streams > 0 else 3, R))
+    ring = StreamRing(n_streams, dev) if n_streams > 1 else None
 
-    def step(i):
+    def run_step(i):
         if graphs is not None:
             graphs[i % R].replay()
         else:
             enqueue(sets[i % R])
+
+    def step(i):
+        if ring is not None:
+            ring.submit(lambda: run_step(i))
+        else:
+            run_step(i)
         return 3
 
+    if ring is not None:
+        ring.fork()
     for i in range(args.warmup):
         step(i)
+    if ring is not None:
+        ring.join()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -341,8 +354,12 @@ def run_gpu_pdf(args, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     ev0.record()
+    if ring is not None:
+        ring.fork()
     for i in range(args.steps):
         launches += step(args.warmup + i)
+    if ring is not None:
+        ring.join()
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -381,7 +398,8 @@ def run_gpu_pdf(args, rank, local_rank, world):
             "config": {"workload": wl["name"], "images_per_step_per_gpu": B,
                        "l2_policy": f"inputs rotate over {R} resident buffer sets; one batch is {by / 1e6:.0f} MB in+out > 126 MB L2",
                        "parallelism": f"images sharded by index over {world} GPU(s), no data-path collective",
-                       "launch": "one CUDA graph replay per step" if graphs is not None else "eager launches"},
+                       "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
+                                 (f"; consecutive steps round-robin over {n_streams} CUDA streams" if ring is not None else "")},
             "clocks": clocks, "e2e": None, "gpu_launches": launches * world,
             "roofline": {"bound": "hbm", "kernel": "remap_f32_rows_kernel", "achieved": by / kms / 1e6, "peak": peak,
                          "unit": "GB/s", "frac": by / kms / 1e6 / peak, "traffic": ncu_traffic("remap_f32_rows_kernel", "c5"),
@@ -415,7 +433,7 @@ def run_gpu(args, rank, local_rank, world):
 
     B, side, C, grid = wl["B"], wl["side"], wl["C"], wl["grid"]
     L, Hh, T = wl["L"], wl["Hh"], wl["grid"] ** 2
-    R = args.rotate if args.rotate > 0 else (8 if wl["has_attention"] else 3)
+    R = args.rotate if args.rotate > 0 else (8 if wl["has_attention"] else 4)
     gen = torch.Generator(device=dev).manual_seed(1235 + rank)
     sets = []
     for _ in range(R):
@@ -459,7 +477,7 @@ def run_gpu(args, rank, local_rank, world):
 
     # Consecutive steps are independent batches: they go round-robin over a few streams so that the
     # HBM-bound stage 1 of one step shares the GPU with the issue-bound stage 5 of the previous one.
-    n_streams = args.streams if args.streams > 0 else (4 if wl["has_attention"] else 1)
+    n_streams = args.streams if args.streams > 0 else (4 if wl["has_attention"] else 3)
     n_streams = max(1, min(n_streams, R))        # concurrent steps need distinct buffer sets
     ring = StreamRing(n_streams, dev) if n_streams > 1 else None
 
@@ -613,7 +631,7 @@ def run_gpu(args, rank, local_rank, world):
                        "transform": "identity",
                        "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
                                  (f"; consecutive steps round-robin over {n_streams} CUDA streams (independent batches: "
-                                  "stage 1 of one step overlaps stage 5 of the previous one)" if ring is not None else "")},
+                                  "the early stages of one step overlap stage 5 of the previous one)" if ring is not None else "")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_info,
             "per_rank_ms": [s[0] for s in stats]}
@@ -628,8 +646,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--rotate", type=int, default=0, help="resident input buffer sets to rotate over (default 8 with attention, else 3)")
-    ap.add_argument("--streams", type=int, default=0, help="CUDA streams consecutive steps alternate over (default 4 with attention, else 1)")
+    ap.add_argument("--rotate", type=int, default=0, help="resident input buffer sets to rotate over (default 8 with attention, else 4)")
+    ap.add_argument("--streams", type=int, default=0, help="CUDA streams consecutive steps alternate over (default 4 with attention, else 3)")
     ap.add_argument("--e2e-chunk", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python profiles/kernel_survey.py 2>&1 | tee gpurun_out/kernel_survey.txt | grep -E "pool|gt_marg"
+for w in c3 c5; do
+python bench.py --workload $w --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$w', round(d['value']), 'img/s', round(d['ms_per_step']*1e3,1), 'us/step', d['config']['launch'][:90])"
+done
+python bench.py --workload c5 --no-cpu-baseline --streams 1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c5 1 stream', round(d['value']), 'img/s', round(d['ms_per_step']*1e3,1), 'us/step')"
