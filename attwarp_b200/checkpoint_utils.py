@@ -34,17 +34,40 @@ def _cuda_device(t: torch.Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+class _CdfFromDensity(torch.autograd.Function):
+    """Forward in the library; backward of clamp -> normalise -> cumsum -> last = 1 written out with torch
+    tensor ops on the device (only the reference's unused l1_cdf_loss, losses.py:11-12, differentiates it)."""
+
+    @staticmethod
+    def forward(ctx, rows):
+        lib = load()
+        out = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_cdf_from_density(ptr(rows), rows.shape[0], rows.shape[1], ptr(out),
+                                               current_stream(rows.device)))
+        ctx.save_for_backward(rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rows,) = ctx.saved_tensors
+        live = torch.isfinite(rows) & (rows > 0)
+        c = torch.where(live, rows, torch.zeros_like(rows))
+        tot = c.sum(dim=1, keepdim=True)
+        S = tot.clamp_min(1e-6)
+        g = grad.clone().float()
+        g[:, -1] = 0                                       # F[:, -1] = 1.0 overwrites the last element
+        gq = g.flip(1).cumsum(1).flip(1)                   # d/dq of cumsum
+        gc = gq / S - torch.where(tot > 1e-6, (gq * c).sum(dim=1, keepdim=True) / (S * S), torch.zeros_like(S))
+        return torch.where(live, gc, torch.zeros_like(gc))
+
+
 def cdf_from_density(p: torch.Tensor) -> torch.Tensor:
     """p: (B,N) -> (B,N) non-decreasing CDF in [0,1], ends at 1."""
-    lib = load()
     dev = _cuda_device(p)
-    rows = p.detach().to(dev).float().contiguous()
+    rows = p.to(dev).float().contiguous()
     assert rows.dim() == 2, "cdf_from_density expects (B, N)"
-    out = torch.empty_like(rows)
-    with torch.cuda.device(dev):
-        check(lib.attwarp_cdf_from_density(ptr(rows), rows.shape[0], rows.shape[1], ptr(out),
-                                           current_stream(dev)))
-    return out.to(p.device)
+    return _CdfFromDensity.apply(rows).to(p.device)
 
 
 def _make_strictly_increasing(Fcdf: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
@@ -115,19 +138,43 @@ def right_inverse_matrix(L_in: int, L_out: int, eps: float, device) -> torch.Ten
     return M
 
 
+class _UpsampleRightInverse(torch.autograd.Function):
+    """rows [B, L_out] float32 (CUDA) -> rows M^T [B, L_in]; backward grad_x M (the op is linear)."""
+
+    @staticmethod
+    def forward(ctx, rows, M):
+        lib = load()
+        L_in, L_out = M.shape
+        x = torch.empty(rows.shape[0], L_in, dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_upsample_right_inverse(ptr(rows), ptr(M), rows.shape[0], L_out, L_in,
+                                                     ptr(x), current_stream(rows.device)))
+        ctx.save_for_backward(M)
+        return x
+
+    @staticmethod
+    def backward(ctx, grad):
+        (M,) = ctx.saved_tensors
+        lib = load()
+        L_in, L_out = M.shape
+        g = grad.contiguous().float()
+        gy = torch.empty(g.shape[0], L_out, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib.attwarp_upsample_right_inverse_backward(ptr(g), ptr(M), g.shape[0], L_out, L_in, ptr(gy),
+                                                              current_stream(g.device)))
+        return gy, None
+
+
 def upsample_pdf_right_inverse(y: torch.Tensor, target_len: int, eps: float = 1e-8) -> torch.Tensor:
-    """Minimum-norm right inverse of AdaptiveAvgPool1d; y (L_out,), (B,L_out) or (B,C,L_out)."""
+    """Minimum-norm right inverse of AdaptiveAvgPool1d; y (L_out,), (B,L_out) or (B,C,L_out).
+    Differentiable in y like the reference's (trainer.py:217-218 trains through it)."""
     if y.dim() not in (1, 2, 3):
         raise ValueError(f"upsample_pdf_right_inverse expects 1D/2D/3D y; got shape {tuple(y.shape)}")
-    lib = load()
     dev = _cuda_device(y)
     L_out, L_in = y.shape[-1], int(target_len)
-    rows = y.detach().to(dev).float().reshape(-1, L_out).contiguous()
+    rows = y.to(dev).float().reshape(-1, L_out).contiguous()
     M = right_inverse_matrix(L_in, L_out, eps, dev)
-    x = torch.empty(rows.shape[0], L_in, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        check(lib.attwarp_upsample_right_inverse(ptr(rows), ptr(M), rows.shape[0], L_out, L_in,
-                                                 ptr(x), current_stream(dev)))
+    x = _UpsampleRightInverse.apply(rows, M)
     return x.reshape(tuple(y.shape[:-1]) + (L_in,)).to(device=y.device, dtype=y.dtype)
 
 

@@ -21,6 +21,11 @@ int launch_mix_with_uniform(const float* p, int B, int N, float alpha, float* ou
 int launch_cdf_from_density(const float* p, int B, int N, float* F, cudaStream_t st);
 int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,
                                   float* x, cudaStream_t st);
+int launch_mix_with_uniform_backward(const float* g, int B, int N, float alpha, float* gp, cudaStream_t st);
+int launch_safe_softmax_backward(const float* logits, const float* grad_out, int B, int N, float eps,
+                                 float* grad_logits, cudaStream_t st);
+int launch_upsample_right_inverse_backward(const float* gx, const float* M, int B, int L_out, int L_in, float* gy,
+                                           cudaStream_t st);
 int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                cudaStream_t st);
 int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float coe, float* revised,
@@ -443,6 +448,26 @@ int attwarp_upsample_right_inverse(const float* y, const float* M, int B, int L_
     AW_REQUIRE(B > 0 && L_out > 0 && L_in > 0, "upsample_right_inverse: sizes must be positive");
     AW_REQUIRE(B <= 65535 && L_out <= 4096, "upsample_right_inverse: B<=65535 and L_out<=4096 required");
     return launch_upsample_right_inverse(y, M, B, L_out, L_in, x, as_stream(stream));
+}
+
+int attwarp_safe_softmax_backward(const float* logits, const float* grad_out, int B, int N, float eps,
+                                  float* grad_logits, void* stream) {
+    AW_REQUIRE(logits && grad_out && grad_logits, "safe_softmax_backward: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "safe_softmax_backward: sizes must be positive");
+    return launch_safe_softmax_backward(logits, grad_out, B, N, eps, grad_logits, as_stream(stream));
+}
+
+int attwarp_mix_with_uniform_backward(const float* grad_out, int B, int N, float alpha, float* grad_p, void* stream) {
+    AW_REQUIRE(grad_out && grad_p, "mix_with_uniform_backward: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "mix_with_uniform_backward: sizes must be positive");
+    return launch_mix_with_uniform_backward(grad_out, B, N, alpha, grad_p, as_stream(stream));
+}
+
+int attwarp_upsample_right_inverse_backward(const float* grad_x, const float* M, int B, int L_out, int L_in,
+                                            float* grad_y, void* stream) {
+    AW_REQUIRE(grad_x && M && grad_y, "upsample_right_inverse_backward: NULL pointer");
+    AW_REQUIRE(B > 0 && L_out > 0 && L_in > 0, "upsample_right_inverse_backward: sizes must be positive");
+    return launch_upsample_right_inverse_backward(grad_x, M, B, L_out, L_in, grad_y, as_stream(stream));
 }
 
 int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,

@@ -222,6 +222,68 @@ adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, in
     }
 }
 
+// ---- backward passes of the three helpers the reference differentiates through (trainer.py:209-250:
+// net -> safe_softmax -> mix_with_uniform -> upsample_pdf_right_inverse -> clamp/normalise -> L1) -------------
+// safe_softmax backward, one CTA per row.  Forward: z' = nan_to_num(z); p = softmax(z'); s = sum p;
+// q = p / max(s, eps).  Backward: g' = s >= eps ? (g - sum g q) / s : g / eps;  dz = p (g' - sum g' p);
+// dz = 0 where z is not finite (nan_to_num has zero slope there).
+__global__ void __launch_bounds__(kRowThreads)
+safe_softmax_backward_kernel(const float* __restrict__ logits, const float* __restrict__ grad_out, int N, float eps,
+                             float* __restrict__ grad_logits) {
+    __shared__ float red[32];
+    const float* row = logits + (int64_t)blockIdx.x * N;
+    const float* g = grad_out + (int64_t)blockIdx.x * N;
+    float* o = grad_logits + (int64_t)blockIdx.x * N;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, nan_inf_to_zero(row[i]));
+    m = block_max(m, red);
+    float e = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) e += expf(nan_inf_to_zero(row[i]) - m);
+    e = block_sum(e, red);
+    float s = 0.f, gp = 0.f;                            // s = sum p, gp = sum g p
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float p = nan_inf_to_zero(expf(nan_inf_to_zero(row[i]) - m) / e);
+        s += p;
+        gp += g[i] * p;
+    }
+    s = block_sum(s, red);
+    gp = block_sum(gp, red);
+    const bool live = s >= eps;
+    const float denom = fmaxf(s, eps);
+    // g'_i = live ? (g_i - gp / denom) / denom : g_i / denom   (q = p / denom)
+    const float shift = live ? gp / denom : 0.f;
+    float gpp = 0.f;                                    // sum g' p
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float p = nan_inf_to_zero(expf(nan_inf_to_zero(row[i]) - m) / e);
+        gpp += (g[i] - shift) / denom * p;
+    }
+    gpp = block_sum(gpp, red);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float z = row[i];
+        const float p = nan_inf_to_zero(expf(nan_inf_to_zero(z) - m) / e);
+        const float gi = (g[i] - shift) / denom;
+        o[i] = (isnan(z) || isinf(z)) ? 0.f : p * (gi - gpp);
+    }
+}
+
+// upsample_pdf_right_inverse backward: x = y M^T  =>  grad_y[b][k] = sum_i grad_x[b][i] M[i][k].
+// One CTA per row b; a warp owns output bins k, k + warps, ... and its lanes stride over i.
+__global__ void __launch_bounds__(kRowThreads)
+upsample_right_inverse_backward_kernel(const float* __restrict__ gx, const float* __restrict__ M, int L_out, int L_in,
+                                       float* __restrict__ gy) {
+    extern __shared__ float gs[];                       // grad_x row
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < L_in; i += blockDim.x) gs[i] = gx[(int64_t)b * L_in + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = wid; k < L_out; k += nw) {
+        float acc = 0.f;
+        for (int i = lane; i < L_in; i += 32) acc = fmaf(gs[i], __ldg(M + (int64_t)i * L_out + k), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) gy[(int64_t)b * L_out + k] = acc;
+    }
+}
+
 }  // namespace
 
 int launch_safe_softmax(const float* logits, int B, int N, float eps, float* out, cudaStream_t st) {
@@ -235,6 +297,14 @@ int launch_mix_with_uniform(const float* p, int B, int N, float alpha, float* ou
     const float c1 = (float)(1.0 - (double)alpha), c2 = (float)((double)alpha / (double)N);
     mix_with_uniform_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total, c1, c2,
                                                                              alpha <= 0.f, out);
+    return check_launch("mix_with_uniform_kernel");
+}
+
+// d/dp [(1 - alpha) p + alpha / N] = (1 - alpha); alpha <= 0 is the identity
+int launch_mix_with_uniform_backward(const float* g, int B, int N, float alpha, float* gp, cudaStream_t st) {
+    const int64_t total = (int64_t)B * N;
+    const float c1 = (float)(1.0 - (double)alpha);
+    mix_with_uniform_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, total, c1, 0.f, alpha <= 0.f, gp);
     return check_launch("mix_with_uniform_kernel");
 }
 
@@ -283,6 +353,23 @@ int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_o
     upsample_right_inverse_kernel<<<dim3((L_in + 127) / 128, B), 128, sizeof(float) * L_out, st>>>(
         y, M, L_out, L_in, x);
     return check_launch("upsample_right_inverse_kernel");
+}
+
+int launch_safe_softmax_backward(const float* logits, const float* grad_out, int B, int N, float eps,
+                                 float* grad_logits, cudaStream_t st) {
+    safe_softmax_backward_kernel<<<B, kRowThreads, 0, st>>>(logits, grad_out, N, eps, grad_logits);
+    return check_launch("safe_softmax_backward_kernel");
+}
+
+int launch_upsample_right_inverse_backward(const float* gx, const float* M, int B, int L_out, int L_in, float* gy,
+                                           cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)L_in;
+    if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "upsample_right_inverse_backward: L_in=%d too long", L_in);
+    if (smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(upsample_right_inverse_backward_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upsample_right_inverse_backward_kernel<<<B, kRowThreads, smem, st>>>(gx, M, L_out, L_in, gy);
+    return check_launch("upsample_right_inverse_backward_kernel");
 }
 
 int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,

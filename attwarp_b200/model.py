@@ -27,26 +27,65 @@ def _rows(t: torch.Tensor, dim: int):
     return rows, restore
 
 
+class _SafeSoftmaxRows(torch.autograd.Function):
+    """rows [B, N] float32 -> safe_softmax rows; backward = what autograd gives model.py:8-14."""
+
+    @staticmethod
+    def forward(ctx, rows, eps):
+        lib = load()
+        out = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_safe_softmax(ptr(rows), rows.shape[0], rows.shape[1], float(eps),
+                                           ptr(out), current_stream(rows.device)))
+        ctx.save_for_backward(rows)
+        ctx.eps = float(eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rows,) = ctx.saved_tensors
+        lib = load()
+        g = grad.contiguous().float()
+        gz = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_safe_softmax_backward(ptr(rows), ptr(g), rows.shape[0], rows.shape[1], ctx.eps,
+                                                    ptr(gz), current_stream(rows.device)))
+        return gz, None
+
+
+class _MixWithUniform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, alpha):
+        lib = load()
+        out = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_mix_with_uniform(ptr(rows), rows.shape[0], rows.shape[1], float(alpha),
+                                               ptr(out), current_stream(rows.device)))
+        ctx.alpha = float(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = load()
+        g = grad.contiguous().float()
+        gp = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            check(lib.attwarp_mix_with_uniform_backward(ptr(g), g.shape[0], g.shape[1], ctx.alpha, ptr(gp),
+                                                        current_stream(g.device)))
+        return gp, None
+
+
 def safe_softmax(logits: torch.Tensor, dim: int = 1, eps: float = 1e-6) -> torch.Tensor:
-    lib = load()
+    """Differentiable like the reference's (MarginalNet.forward ends in it, model.py:93-94)."""
     require_cuda(logits)
     rows, restore = _rows(logits, dim)
-    out = torch.empty_like(rows)
-    with torch.cuda.device(rows.device):
-        check(lib.attwarp_safe_softmax(ptr(rows), rows.shape[0], rows.shape[1], float(eps),
-                                       ptr(out), current_stream(rows.device)))
-    return restore(out)
+    return restore(_SafeSoftmaxRows.apply(rows, eps))
 
 
 def mix_with_uniform(p: torch.Tensor, alpha: float) -> torch.Tensor:
+    """Differentiable like the reference's (trainer.py:213-214 trains through it)."""
     if alpha <= 0:                       # model.py:99-100 returns the input itself
         return p
-    lib = load()
     require_cuda(p)
     assert p.dim() == 2, "mix_with_uniform expects (B, N)"
-    rows = p.contiguous().float()
-    out = torch.empty_like(rows)
-    with torch.cuda.device(rows.device):
-        check(lib.attwarp_mix_with_uniform(ptr(rows), rows.shape[0], rows.shape[1], float(alpha),
-                                           ptr(out), current_stream(rows.device)))
-    return out.to(p.dtype)
+    return _MixWithUniform.apply(p.contiguous().float(), alpha).to(p.dtype)

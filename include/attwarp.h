@@ -260,6 +260,18 @@ int attwarp_gt_marginals(const float* A, int B, int H, int W, void* workspace,
  * (L_in, L_out, eps); the host mirror builds and caches it).  y [B][L_out] -> x [B][L_in]. */
 int attwarp_upsample_right_inverse(const float* y, const float* M, int B, int L_out, int L_in,
                                    float* x, void* stream);
+/* Backward passes of the three helpers the reference trains through (mnfd/trainer.py:209-250: MarginalNet ->
+ * safe_softmax (model.py:93-94) -> mix_with_uniform (:213-214) -> upsample_pdf_right_inverse (:217-218) -> loss);
+ * what torch.autograd computes for the reference's own expressions.
+ *   safe_softmax_backward            : logits, grad_out [B][N] -> grad_logits [B][N]
+ *   mix_with_uniform_backward        : grad_out [B][N] -> grad_p = (1 - alpha) grad_out (alpha <= 0 copies)
+ *   upsample_right_inverse_backward  : grad_x [B][L_in], M [L_in][L_out] -> grad_y = grad_x M  [B][L_out] */
+int attwarp_safe_softmax_backward(const float* logits, const float* grad_out, int B, int N, float eps,
+                                  float* grad_logits, void* stream);
+int attwarp_mix_with_uniform_backward(const float* grad_out, int B, int N, float alpha, float* grad_p,
+                                      void* stream);
+int attwarp_upsample_right_inverse_backward(const float* grad_x, const float* M, int B, int L_out, int L_in,
+                                            float* grad_y, void* stream);
 /* F.adaptive_avg_pool2d(A, (gh,gw)) (mnfd/trainer.py:197): A [B][H][W] -> out [B][gh][gw]. */
 int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                 void* stream);
