@@ -195,6 +195,28 @@ class BatchMaskHookLogger(object):
             self._original_forward = None
 
 
+def hook_logger(model, device, layer_index=20):
+    """Create and register a ``MaskHookLogger`` (llava.py:156-187): turns ``output_attentions`` on in the
+    model config, hooks the layer, and leaves the logger on ``model.hooklogger``."""
+    prs = MaskHookLogger(model, device, layer_index)
+    original_output_attentions = getattr(model.config, "output_attentions", False)
+    model.config.output_attentions = True
+    prs.register_hook()
+    model.hooklogger = prs
+    model._original_output_attentions = original_output_attentions
+    return prs
+
+
+def batch_hook_logger(model, device, layer_index=20):
+    """Create and register a ``BatchMaskHookLogger`` (llava.py:451-462): only the target layer is patched
+    to produce attention weights; ``model.config.output_attentions`` is switched off."""
+    prs = BatchMaskHookLogger(model, device, layer_index)
+    model.config.output_attentions = False
+    prs.register_hook_and_patch()
+    model.batch_hooklogger = prs
+    return prs
+
+
 # ----------------------------------------------------------------------------------------------
 # mask post-processing (llava.py:207-270)
 # ----------------------------------------------------------------------------------------------

@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8

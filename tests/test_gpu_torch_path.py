@@ -213,3 +213,59 @@ def test_hook_loggers(golden_aggregate):
     assert rel_err(ml.finalize().cpu().numpy(), g["single_logger/default_range"]) <= 1e-5
     ml.reinit()
     assert rel_err(ml.finalize().cpu().numpy(), g["single_logger/empty"]) <= 1e-6
+
+
+def test_hook_logger_factories_on_a_stub_model():
+    """hook_logger / batch_hook_logger (llava.py:156-187, 451-462) on a stand-in for the decoder: the
+    registered forward hook must pick the attention weights out of the layer's output tuple and reduce
+    them on the device exactly like _process_attention fed by hand."""
+    need_gpu()
+    import types
+    from attwarp_b200.attention_extraction import (BatchMaskHookLogger, MaskHookLogger, batch_hook_logger,
+                                                  hook_logger)
+
+    class Attn(torch.nn.Module):
+        def forward(self, attn, output_attentions=False):
+            return (attn.sum(), attn if output_attentions else None, None)
+
+    def make_model(n_layers=3):
+        layers = torch.nn.ModuleList([torch.nn.Module() for _ in range(n_layers)])
+        for l in layers:
+            l.self_attn = Attn()
+        m = torch.nn.Module()
+        m.model = torch.nn.Module()
+        m.model.layers = layers
+        m.config = types.SimpleNamespace(output_attentions=False)
+        return m
+
+    gen = torch.Generator().manual_seed(11)
+    B, Hh, q, kv = 3, 4, 5, 640
+    attn = torch.softmax(torch.randn(B, Hh, q, kv, generator=gen), -1).cuda()
+    starts, ends = [1, 7, 30], [577, 583, 606]
+
+    model = make_model()
+    bl = batch_hook_logger(model, "cuda", layer_index=1)
+    assert isinstance(bl, BatchMaskHookLogger) and model.batch_hooklogger is bl
+    assert model.config.output_attentions is False
+    bl.set_batch_image_token_ranges(starts, ends)
+    for _ in range(2):
+        model.model.layers[1].self_attn(attn)             # the patch forces output_attentions=True
+    model.model.layers[0].self_attn(attn)                  # other layers are not hooked
+    ref = BatchMaskHookLogger(None, "cuda")
+    ref.set_batch_image_token_ranges(starts, ends)
+    for _ in range(2):
+        ref._process_attention(attn)
+    for a, b in zip(bl.finalize_batch(), ref.finalize_batch()):
+        assert torch.equal(a, b)
+    bl.remove_hook_and_unpatch()
+
+    model = make_model()
+    sl = hook_logger(model, "cuda", layer_index=2)
+    assert isinstance(sl, MaskHookLogger) and model.hooklogger is sl and model.config.output_attentions is True
+    sl.set_image_token_range(7, 583)
+    model.model.layers[2].self_attn(attn[1:2], output_attentions=True)
+    r2 = MaskHookLogger(None, "cuda")
+    r2.set_image_token_range(7, 583)
+    r2._process_attention(attn[1:2])
+    assert torch.equal(sl.finalize(), r2.finalize())
+    sl.remove_hook()
