@@ -409,6 +409,85 @@ __device__ __forceinline__ void sweep_c3x2(uint32_t* P, int n_slots, uint32_t ca
     }
 }
 
+// Two output columns per thread for single-channel rows (grey images and the planes of CHW images), half a
+// strip apart like sweep_c3x2: the row-table loads and the loop control are most of the one-column sweep
+// when a column is one byte, so sharing them nearly halves the instructions per output byte.
+#define AW_SW1X2_LOAD                                           \
+    "ld.shared.b32 loa, [ca];\n"                                \
+    "ld.shared.b32 mida, [ca+4];\n"                             \
+    "ld.shared.b32 lob, [cb];\n"                                \
+    "ld.shared.b32 midb, [cb+4];\n"
+#define AW_SW1X2_ALIGN(SHA, SHB)                                \
+    "shf.r.wrap.b32 Aa, loa, mida, " SHA ";\n"                  \
+    "shf.r.wrap.b32 Ab, lob, midb, " SHB ";\n"
+#define AW_SW1X2_DOT                                            \
+    "dp4a.u32.u32 h0, Aa, %10, 0;\n"                            \
+    "dp4a.u32.u32 h1, Ab, %11, 0;\n"                            \
+    "prmt.b32 %0, %0, h0, 0x5432;\n"                            \
+    "prmt.b32 %1, %1, h1, 0x5432;\n"
+#define AW_SW1X2_EMIT                                           \
+    "dp2a.lo.u32.u32 r0, %0, ex, ew;\n"                         \
+    "dp2a.lo.u32.u32 r1, %1, ex, ew;\n"                         \
+    "add.u32 o, ey, %8;\n"                                      \
+    "add.u32 o2, o, %13;\n"                                     \
+    "shr.u32 r0, r0, 10;\n shr.u32 r1, r1, 10;\n"               \
+    "st.shared.u8 [o], r0;\n"                                   \
+    "@pb st.shared.u8 [o2], r1;\n"
+#define AW_SW1X2_ADDR_T                                         \
+    "ld.shared.b32 t, [sp];\n"                                  \
+    "add.u32 sp, sp, 4;\n"                                      \
+    "add.u32 ta, t, %3;\n"                                      \
+    "add.u32 tb, t, %4;\n"                                      \
+    "and.b32 ca, ta, 0xfffffffc;\n"                             \
+    "and.b32 cb, tb, 0xfffffffc;\n"                             \
+    "shl.b32 sha, ta, 3;\n"                                     \
+    "shl.b32 shb, tb, 3;\n"
+
+template <bool U>
+__device__ __forceinline__ void sweep_c1x2(uint32_t* P, int n_slots, uint32_t ca, uint32_t cb, uint32_t sha_or_sp,
+                                           uint32_t shb, uint32_t pitch, uint32_t rp, uint32_t ocol,
+                                           const uint32_t* wA, uint32_t rnd, uint32_t bdelta, uint32_t bvalid) {
+    // operands: %0 %1 P | %2 n_slots | %3 ca | %4 cb | %5 sha / sp | %6 pitch | %7 rp | %8 ocol | %9 rnd |
+    //           %10 %11 weights | %12 shb | %13 bdelta | %14 bvalid
+    if (U) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q, pb;\n"
+            ".reg .b32 s, loa, mida, lob, midb, Aa, Ab, h0, h1, t, r0, r1, o, o2, ca, cb, rp, ex, ey, ez, ew;\n"
+            "setp.ne.u32 pb, %14, 0;\n"
+            "mov.b32 ca, %3;\n mov.b32 cb, %4;\n mov.b32 rp, %7;\n" AW_SW_PRE_BEGIN AW_SW1X2_EMIT AW_SW_PRE_END("%2")
+            AW_SW1X2_LOAD
+            "SLOT:\n" AW_SW1X2_ALIGN("%5", "%12")
+            "add.u32 ca, ca, %6;\n add.u32 cb, cb, %6;\n" AW_SW1X2_LOAD AW_SW1X2_DOT
+            AW_SW_ROWCTL_BEGIN AW_SW1X2_EMIT AW_SW_ROWCTL_END("%2")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1])
+            : "r"(n_slots), "r"(ca), "r"(cb), "r"(sha_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(rnd),
+              "r"(wA[0]), "r"(wA[1]), "r"(shb), "r"(bdelta), "r"(bvalid)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q, pb;\n"
+            ".reg .b32 s, loa, mida, lob, midb, Aa, Ab, h0, h1, t, ta, tb, sha, shb, r0, r1, o, o2, ca, cb, sp, rp;\n"
+            ".reg .b32 ex, ey, ez, ew;\n"
+            "setp.ne.u32 pb, %14, 0;\n"
+            "mov.b32 sp, %5;\n mov.b32 rp, %7;\n" AW_SW_PRE_BEGIN AW_SW1X2_EMIT AW_SW_PRE_END("%2")
+            AW_SW1X2_ADDR_T AW_SW1X2_LOAD
+            "SLOT:\n" AW_SW1X2_ALIGN("sha", "shb") AW_SW1X2_ADDR_T AW_SW1X2_LOAD AW_SW1X2_DOT
+            AW_SW_ROWCTL_BEGIN AW_SW1X2_EMIT AW_SW_ROWCTL_END("%2")
+            "@p bra.uni SLOT;\n"
+            "DONE:\n"
+            "}\n"
+            : "+r"(P[0]), "+r"(P[1])
+            : "r"(n_slots), "r"(ca), "r"(cb), "r"(sha_or_sp), "r"(pitch), "r"(rp), "r"(ocol), "r"(rnd),
+              "r"(wA[0]), "r"(wA[1]), "r"(shb), "r"(bdelta), "r"(bvalid)
+            : "memory");
+    }
+}
+
 struct StreamArgs {
     // uniform batch (imgs == nullptr): n_img dense images of one shape, maps [n_img / map_div][..]
     const uint8_t* src;
@@ -494,7 +573,7 @@ constexpr int kTabStore = 32, kTabStrip = 48;
 template <int C, int R, int CPT>
 __global__ void __launch_bounds__(max_threads(CPT), CPT == 2 ? AW_MIN_CTAS : 3)
 remap_u8_stream_kernel(const StreamArgs a) {
-    static_assert(CPT == 1 || (CPT == 2 && C == 3), "two columns per thread are implemented for C = 3");
+    static_assert(CPT == 1 || (CPT == 2 && (C == 3 || C == 1)), "two columns per thread are implemented for C = 1 and 3");
     const int Wt = ((int)blockDim.x - kRoleThreads) * CPT;
     const int tid = threadIdx.x;
     const int out_bytes = R * a.out_pitch;
@@ -865,7 +944,17 @@ remap_u8_stream_kernel(const StreamArgs a) {
             const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
             const int slot_tab = tab + tab_slots<R>();
             const int win0 = arena + (uni ? (int)h0.w : 0);
-            if (CPT == 2 && !warp_b) {
+            if (CPT == 2 && C == 1) {
+                const int win1 = st * a.stage_bytes + wo[CPT - 1] + (uni ? (int)h0.w : 0);
+                if (!warp_b) {
+                    if (uni) sweep_c1<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, rnd);
+                    else sweep_c1<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)slot_tab, 0u, rp_s, ocol_s, wA, rnd);
+                } else if (uni) {
+                    sweep_c1x2<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), smem_s + (uint32_t)(win1 & ~3), (uint32_t)win0 << 3, (uint32_t)win1 << 3, h0.z, rp_s, ocol_s, wA, rnd, (uint32_t)(xstep * C), bvalid);
+                } else {
+                    sweep_c1x2<false>(P, n_slots, smem_s + (uint32_t)win0, smem_s + (uint32_t)win1, smem_s + (uint32_t)slot_tab, 0u, 0u, rp_s, ocol_s, wA, rnd, (uint32_t)(xstep * C), bvalid);
+                }
+            } else if (CPT == 2 && !warp_b) {
                 // no lane of this warp has a second column in this strip (the strip is narrower than the
                 // consumer threads x 2): the one-column sweep does the same work in 3/5 of the instructions
                 if (uni) sweep_c3<true>(P, n_slots, smem_s + (uint32_t)(win0 & ~3), (uint32_t)win0 << 3, h0.z, rp_s, ocol_s, wA, wB, rnd);
@@ -1017,7 +1106,7 @@ int ragged_run(const RaggedImage* host, int n, const RaggedImage* dev_table, cud
     return launch_kernel<C, R, CPT>(a, max_strip, st);
 }
 
-// ATTWARP_REMAP_CPT=1 forces one column per thread for C = 3 (A/B comparisons).
+// ATTWARP_REMAP_CPT=1 forces one column per thread for C = 1 and 3 (A/B comparisons).
 int columns_per_thread_c3() {
     static const int v = [] {
         const char* e = getenv("ATTWARP_REMAP_CPT");
@@ -1035,7 +1124,9 @@ int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, 
     const uint8_t* s = static_cast<const uint8_t*>(src);
     uint8_t* d = static_cast<uint8_t*>(dst);
     switch (C) {
-        case 1: return launch_stream<1, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+        case 1:
+            if (columns_per_thread_c3() == 2) return launch_stream<1, AW_ROWS, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
+            return launch_stream<1, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
         case 3:
             if (columns_per_thread_c3() == 2) return launch_stream<3, AW_ROWS, 2>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
             return launch_stream<3, AW_ROWS, 1>(s, d, n_img, H, W, Ho, Wo, map_x, map_y, map_div, st);
@@ -1046,12 +1137,14 @@ int launch_remap_u8_stream(const void* src, void* dst, int n_img, int C, int H, 
 
 // Ragged batch of HWC uint8 images (every H, W >= 2), see common.cuh.
 int launch_remap_u8_stream_ragged_prepare(RaggedImage* h, int n, int C, RaggedImage* d, cudaStream_t st) {
-    if (C == 3 && columns_per_thread_c3() == 2) return ragged_prepare<AW_ROWS, 2>(h, n, d, st);
+    if ((C == 3 || C == 1) && columns_per_thread_c3() == 2) return ragged_prepare<AW_ROWS, 2>(h, n, d, st);
     return ragged_prepare<AW_ROWS, 1>(h, n, d, st);
 }
 int launch_remap_u8_stream_ragged_run(const RaggedImage* h, int n, int C, const RaggedImage* d, cudaStream_t st) {
     switch (C) {
-        case 1: return ragged_run<1, AW_ROWS, 1>(h, n, d, st);
+        case 1:
+            if (columns_per_thread_c3() == 2) return ragged_run<1, AW_ROWS, 2>(h, n, d, st);
+            return ragged_run<1, AW_ROWS, 1>(h, n, d, st);
         case 3:
             if (columns_per_thread_c3() == 2) return ragged_run<3, AW_ROWS, 2>(h, n, d, st);
             return ragged_run<3, AW_ROWS, 1>(h, n, d, st);
