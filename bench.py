@@ -83,17 +83,81 @@ def ncu_traffic(kernel, workload):
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
+def _gpu_uuid(index):
+    try:
+        import torch
+        return str(torch.cuda.get_device_properties(index).uuid)
+    except Exception:
+        return None
+
+
 class ClockSampler:
+    """SM clock and clock-event (throttle) reasons DURING the timed region.  The region is a few
+    milliseconds long, so the sampler is an NVML polling thread (a sample every ~0.2 ms; every NVML
+    call releases the GIL); `nvidia-smi -lms` (50 ms period) is the fallback when NVML cannot be loaded."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.proc = None
         self.path = None
         self.gpu_index = gpu_index
+        self.uuid = uuid
+        self.thread = None
+        self.samples = []
+        self._stop = False
+        self.nvml = None
+        self.handle = None
+
+    def _nvml_init(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                idx = self.gpu_index
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                try:
+                    if vis:
+                        idx = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    pass
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml, self.handle = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(get_reasons(h)) if get_reasons else 0
+                self.samples.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.0002)
 
     def start(self):
+        if self._nvml_init():
+            import threading
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -105,6 +169,25 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            table = {}
+            for nm, attrs in (("hw_slowdown", ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown")),
+                              ("hw_thermal_slowdown", ("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown")),
+                              ("sw_thermal_slowdown", ("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown")),
+                              ("sw_power_cap", ("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))):
+                for a in attrs:
+                    if hasattr(nv, a):
+                        table[nm] = int(getattr(nv, a))
+                        break
+            if not self.samples:
+                return None
+            sm = sorted(s[0] for s in self.samples)
+            reasons = sorted(nm for nm, bit in table.items() if any(s[1] & bit for s in self.samples))
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "how": "NVML polled during the timed region"}
         if self.proc is None:
             return None
         time.sleep(0.06)
@@ -135,7 +218,7 @@ class ClockSampler:
             return None
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": "nvidia-smi -lms 50 during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -246,7 +329,7 @@ def run_gpu_ragged(args, rank, local_rank, world):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
     if rank == 0:
         sampler.start()
     if world > 1:
@@ -345,7 +428,7 @@ def run_gpu_pdf(args, rank, local_rank, world):
     if ring is not None:
         ring.join()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
     if rank == 0:
         sampler.start()
     if world > 1:
@@ -502,7 +585,7 @@ def run_gpu(args, rank, local_rank, world):
         ring.join()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
     if rank == 0:
         sampler.start()
     if world > 1:
@@ -642,7 +725,7 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="default 50 (c4: 10)")
+    ap.add_argument("--steps", type=int, default=None, help="default 200 (c4: 10)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -654,7 +737,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of by graph replay")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 10 if args.workload == "c4" else 50
+        args.steps = 10 if args.workload == "c4" else 200
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

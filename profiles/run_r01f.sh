@@ -1,4 +1,4 @@
-# round-1 (fifth session, final) measurement pass: GPU tests, bench lines for every workload,
+# round-1 (fifth session, final state) measurement pass: GPU tests, bench lines for every workload,
 # ncu launch list and full captures of the dominant kernels, secondary-kernel survey
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
