@@ -154,6 +154,10 @@ class ClockSampler:
     def start(self):
         if self._nvml_init():
             import threading
+            # the main thread enqueues steps in a tight Python loop: with the default 5 ms GIL switch interval
+            # the polling thread would get one sample per 5 ms
+            self._switch = sys.getswitchinterval()
+            sys.setswitchinterval(1e-4)
             self._stop = False
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
@@ -172,6 +176,7 @@ class ClockSampler:
         if self.thread is not None:
             self._stop = True
             self.thread.join(timeout=2)
+            sys.setswitchinterval(self._switch)
             nv = self.nvml
             table = {}
             for nm, attrs in (("hw_slowdown", ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown")),
