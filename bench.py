@@ -55,6 +55,30 @@ WORKLOADS = {
 }
 
 
+class _StdoutToStderr:
+    """OS-level redirect of fd 1 to fd 2 while libraries that printf() to stdout initialise (NCCL prints its
+    version banner with a raw printf at NCCL_DEBUG=VERSION): stdout must carry the ONE JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def init_nccl(dev):
+    import torch.distributed as dist
+    with _StdoutToStderr():
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()                       # communicator creation (and its banner) happens here at the latest
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -314,7 +338,7 @@ def run_gpu_ragged(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     B, C, grid = wl["B"], wl["C"], wl["grid"]
     sides = np.random.default_rng(1237).integers(224, 2049, size=B)
     shards = sharding.lpt_shard([2.0 * float(s) * float(s) for s in sides], world)
@@ -395,7 +419,7 @@ def run_gpu_pdf(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     B, C, side, N = wl["B"], wl["C"], wl["side"], wl["grid"]
     R = args.rotate if args.rotate > 0 else 3
     gen = torch.Generator(device=dev).manual_seed(1238 + rank)
@@ -517,7 +541,7 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
 
     B, side, C, grid = wl["B"], wl["side"], wl["C"], wl["grid"]
     L, Hh, T = wl["L"], wl["Hh"], wl["grid"] ** 2
@@ -745,6 +769,9 @@ def main():
         args.steps = 10 if args.workload == "c4" else 200
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    # stdout carries the ONE JSON line and nothing else: NCCL's own logging (its version banner, NCCL_DEBUG
+    # output) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if world == 1 and args.gpus > 1:
