@@ -82,6 +82,7 @@ SIGNATURES = {
     "attwarp_gt_marginals": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _vp]),
     "attwarp_upsample_right_inverse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "attwarp_adaptive_avg_pool2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "attwarp_pool_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "attwarp_safe_softmax_backward": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp]),
     "attwarp_mix_with_uniform_backward": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "attwarp_upsample_right_inverse_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

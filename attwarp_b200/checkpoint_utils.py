@@ -192,6 +192,27 @@ def adaptive_avg_pool2d_24(A: torch.Tensor, out_hw=(24, 24)) -> torch.Tensor:
     return out.reshape(B, Cc, gh, gw).to(A.device)
 
 
+def pool_attention(A_full: torch.Tensor, transforms=None, out_hw=(24, 24)) -> torch.Tensor:
+    """The trainer's attention prologue in one pass (trainer.py:172-197): ``A_full`` (B,1,H,W) is
+    ``clamp_min(0)``-ed, samples whose entry of ``transforms`` is ``"sqrt"`` get a square root (the others --
+    ``"iden"``, ``"none"`` -- stay as they are), and the result is pooled to ``out_hw``; the transformed
+    full-resolution map is never written.  ``transforms=None`` is the plain ``adaptive_avg_pool2d`` the
+    reference runs when the batch carries no dataset names."""
+    if transforms is None:
+        return adaptive_avg_pool2d_24(A_full, out_hw)
+    lib = load()
+    B, Cc, H, W = A_full.shape
+    assert Cc == 1 and len(transforms) == B, "pool_attention expects (B,1,H,W) and one transform per sample"
+    dev = _cuda_device(A_full)
+    a = A_full.detach().to(dev).float().reshape(B, H, W).contiguous()
+    mask = torch.tensor([1 if t == "sqrt" else 0 for t in transforms], dtype=torch.uint8, device=dev)
+    gh, gw = out_hw
+    out = torch.empty(B, gh, gw, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.attwarp_pool_attention(ptr(a), ptr(mask), B, H, W, gh, gw, ptr(out), current_stream(dev)))
+    return out.reshape(B, 1, gh, gw).to(A_full.device)
+
+
 def warp_from_cdf_torch(img: torch.Tensor, Fx_img: torch.Tensor, Fy_img: torch.Tensor,
                         out_size: tuple | None = None) -> torch.Tensor:
     """img (B,C,H,W) uint8 or float32; Fx_img (B,W), Fy_img (B,H) CDFs in [0,1];

@@ -26,8 +26,8 @@ int launch_safe_softmax_backward(const float* logits, const float* grad_out, int
                                  float* grad_logits, cudaStream_t st);
 int launch_upsample_right_inverse_backward(const float* gx, const float* M, int B, int L_out, int L_in, float* gy,
                                            cudaStream_t st);
-int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
-                               cudaStream_t st);
+int launch_adaptive_avg_pool2d(const float* A, const uint8_t* sqrt_mask, int B, int H, int W, int gh, int gw,
+                               float* out, cudaStream_t st);
 int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float coe, float* revised,
                        uint8_t* mask_u8, cudaStream_t st);
 int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, int Wo, uint8_t* dst, cudaStream_t st);
@@ -475,7 +475,15 @@ int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int
     AW_REQUIRE(A && out, "adaptive_avg_pool2d: NULL pointer");
     AW_REQUIRE(B > 0 && H > 0 && W > 0 && gh > 0 && gw > 0, "adaptive_avg_pool2d: sizes must be positive");
     AW_REQUIRE(B <= 65535, "adaptive_avg_pool2d: B=%d exceeds 65535", B);
-    return launch_adaptive_avg_pool2d(A, B, H, W, gh, gw, out, as_stream(stream));
+    return launch_adaptive_avg_pool2d(A, nullptr, B, H, W, gh, gw, out, as_stream(stream));
+}
+
+int attwarp_pool_attention(const float* A, const unsigned char* sqrt_mask, int B, int H, int W, int gh, int gw,
+                           float* out, void* stream) {
+    AW_REQUIRE(A && sqrt_mask && out, "pool_attention: NULL pointer");
+    AW_REQUIRE(B > 0 && H > 0 && W > 0 && gh > 0 && gw > 0, "pool_attention: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "pool_attention: B=%d exceeds 65535", B);
+    return launch_adaptive_avg_pool2d(A, sqrt_mask, B, H, W, gh, gw, out, as_stream(stream));
 }
 
 }  // extern "C"

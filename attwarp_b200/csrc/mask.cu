@@ -217,7 +217,10 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
             for (int t = 0; t < TAPS; ++t)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[q] += win[t][q] * c[t];
-            const uint32_t o = clip8(acc[0]) | (clip8(acc[1]) << 8) | (clip8(acc[2]) << 16) | (clip8(acc[3]) << 24);
+            // clip8 x 4 + pack: cvt.pack saturates two int32 to uint8 and packs them under the previous pair
+            uint32_t hi2, o;
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(acc[3] >> kPrecisionBits), "r"(acc[2] >> kPrecisionBits), "r"(0));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o) : "r"(acc[1] >> kPrecisionBits), "r"(acc[0] >> kPrecisionBits), "r"(hi2));
             uint8_t* p = out + (int64_t)yy * Wo + 4 * g;
             if (vec) {
                 *reinterpret_cast<uint32_t*>(p) = o;

@@ -182,13 +182,25 @@ __global__ void interp_linear_rows_kernel(const float* __restrict__ F, int N, in
 // One CTA per (image, output row): the rows of the window are read once, coalesced (float4 per lane, four
 // rows in flight), into float64 column sums; the gw window sums of the row are then taken from shared
 // memory.  Rows shared by two windows (H % gh != 0) are read by two CTAs: + gh / H of traffic.
+// MODE 0: plain pooling.  MODE 1: the trainer's prologue fused in (trainer.py:186-194): every value is
+// clamp_min(0)-ed and, for samples whose sqrt_mask byte is set, replaced by its float32 square root
+// (A_pos.sqrt() * m + A_pos * (1 - m) with m in {0, 1}) before it is pooled.
+template <int MODE>
+__device__ __forceinline__ float pool_value(float v, bool take_sqrt) {
+    if (MODE == 0) return v;
+    v = (v != v) ? v : fmaxf(v, 0.f);                  // clamp_min keeps NaN
+    return take_sqrt ? sqrtf(v) : v;
+}
+template <int MODE>
 __global__ void __launch_bounds__(128)
-adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, int gw, float* __restrict__ out) {
+adaptive_avg_pool2d_kernel(const float* __restrict__ A, const uint8_t* __restrict__ sqrt_mask, int H, int W, int gh,
+                           int gw, float* __restrict__ out) {
     extern __shared__ double cs[];                         // [W] column sums over the window's rows
     const int i = blockIdx.x, b = blockIdx.y;
     const int y0 = (int)(((int64_t)i * H) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
     const float* img = A + (int64_t)b * H * W;
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    const bool sq = MODE == 1 && sqrt_mask != nullptr && sqrt_mask[b] != 0;
     if (vec) {
         for (int x = threadIdx.x * 4; x < W; x += blockDim.x * 4) {
             double a[4] = {0.0, 0.0, 0.0, 0.0};
@@ -200,7 +212,9 @@ adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, in
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    a[0] += (double)v[u].x; a[1] += (double)v[u].y; a[2] += (double)v[u].z; a[3] += (double)v[u].w;
+                    if (MODE == 1 && !(y + u < y1)) continue;          // (MODE 0 adds the zeros it loaded)
+                    a[0] += (double)pool_value<MODE>(v[u].x, sq); a[1] += (double)pool_value<MODE>(v[u].y, sq);
+                    a[2] += (double)pool_value<MODE>(v[u].z, sq); a[3] += (double)pool_value<MODE>(v[u].w, sq);
                 }
             }
 #pragma unroll
@@ -209,7 +223,7 @@ adaptive_avg_pool2d_kernel(const float* __restrict__ A, int H, int W, int gh, in
     } else {
         for (int x = threadIdx.x; x < W; x += blockDim.x) {
             double a = 0.0;
-            for (int y = y0; y < y1; ++y) a += (double)__ldg(img + (int64_t)y * W + x);
+            for (int y = y0; y < y1; ++y) a += (double)pool_value<MODE>(__ldg(img + (int64_t)y * W + x), sq);
             cs[x] = a;
         }
     }
@@ -372,14 +386,16 @@ int launch_upsample_right_inverse_backward(const float* gx, const float* M, int 
     return check_launch("upsample_right_inverse_backward_kernel");
 }
 
-int launch_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
-                               cudaStream_t st) {
+// sqrt_mask == nullptr: plain F.adaptive_avg_pool2d; else [B] bytes, the trainer's clamp + per-sample sqrt first
+int launch_adaptive_avg_pool2d(const float* A, const uint8_t* sqrt_mask, int B, int H, int W, int gh, int gw,
+                               float* out, cudaStream_t st) {
     if (gh > 65535 || B > 65535) return fail(ATTWARP_ERR_UNSUPPORTED, "adaptive_avg_pool2d: grid too large");
     const size_t smem = sizeof(double) * (size_t)W;
     if (smem > 200 * 1024) return fail(ATTWARP_ERR_UNSUPPORTED, "adaptive_avg_pool2d: W=%d too wide", W);
+    auto kern = sqrt_mask ? adaptive_avg_pool2d_kernel<1> : adaptive_avg_pool2d_kernel<0>;
     if (smem > 48 * 1024)
-        AW_CUDA(cudaFuncSetAttribute(adaptive_avg_pool2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    adaptive_avg_pool2d_kernel<<<dim3(gh, B), 128, smem, st>>>(A, H, W, gh, gw, out);
+        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(gh, B), 128, smem, st>>>(A, sqrt_mask, H, W, gh, gw, out);
     return check_launch("adaptive_avg_pool2d_kernel");
 }
 

@@ -275,6 +275,11 @@ int attwarp_upsample_right_inverse_backward(const float* grad_x, const float* M,
 /* F.adaptive_avg_pool2d(A, (gh,gw)) (mnfd/trainer.py:197): A [B][H][W] -> out [B][gh][gw]. */
 int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                 void* stream);
+/* The trainer's prologue in one pass (mnfd/trainer.py:186-197): A.clamp_min(0), float32 sqrt for the samples
+ * whose sqrt_mask byte is non-zero (device array [B]; "sqrt" vs "iden"/"none" transform of the sample), then
+ * adaptive_avg_pool2d to (gh, gw).  The transformed full-resolution map is never written. */
+int attwarp_pool_attention(const float* A, const unsigned char* sqrt_mask, int B, int H, int W, int gh, int gw,
+                           float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -269,3 +269,21 @@ def test_hook_logger_factories_on_a_stub_model():
     r2._process_attention(attn[1:2])
     assert torch.equal(sl.finalize(), r2.finalize())
     sl.remove_hook()
+
+
+def test_pool_attention_prologue():
+    """trainer.py:172-197: clamp_min(0), per-sample sqrt mask, adaptive_avg_pool2d -- fused, against the
+    reference's own torch expressions."""
+    need_gpu()
+    from attwarp_b200 import checkpoint_utils as cu
+    gen = torch.Generator().manual_seed(21)
+    for (H, W) in [(512, 512), (97, 54)]:
+        A = torch.randn(5, 1, H, W, generator=gen) * 0.5 + 0.3          # some negatives
+        tf = ["sqrt", "iden", "none", "sqrt", "iden"]
+        m = torch.tensor([1.0 if t == "sqrt" else 0.0 for t in tf]).view(5, 1, 1, 1)
+        pos = A.clamp_min(0.0)
+        ref = torch.nn.functional.adaptive_avg_pool2d(pos.sqrt() * m + pos * (1.0 - m), (24, 24)).numpy()
+        got = cu.pool_attention(A.cuda(), tf).cpu().numpy()
+        assert rel_err(got, ref, floor=1e-6) <= 1e-5, (H, W)
+        plain = cu.pool_attention(A.cuda(), None).cpu().numpy()
+        assert rel_err(plain, torch.nn.functional.adaptive_avg_pool2d(A, (24, 24)).numpy(), floor=1e-6) <= 1e-4
