@@ -260,8 +260,9 @@ marginals_u8_identity_kernel(const uint8_t* __restrict__ att, int H, int W, int 
         for (int k = 0; k < 8; ++k) acc[s][k] = 0u;
     double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
     const double row_base = (double)tile_cols * kBaseAttention;
-    for (int y = y0 + wid; y < y1; y += U * kWarps) {
-        uint4 v[U][STEPS];
+    // Double-buffered: the loads of the next group of U rows are in flight while this group is summed (the
+    // arithmetic of a group, ~30 instructions per load, takes about as long as the loads' latency).
+    auto fetch = [&](int y, uint4 (&v)[U][STEPS]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool row_in = y + u * kWarps < y1;
@@ -273,6 +274,11 @@ marginals_u8_identity_kernel(const uint8_t* __restrict__ att, int H, int W, int 
                                                     : make_uint4(0u, 0u, 0u, 0u);
             }
         }
+    };
+    uint4 v[U][STEPS], nx[U][STEPS];
+    fetch(y0 + wid, v);
+    for (int y = y0 + wid; y < y1; y += U * kWarps) {
+        fetch(y + U * kWarps, nx);                         // rows past y1 load nothing
         uint32_t rs[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -293,6 +299,10 @@ marginals_u8_identity_kernel(const uint8_t* __restrict__ att, int H, int W, int 
             const uint32_t t = __reduce_add_sync(0xffffffffu, rs[u]);
             if (lane == 0 && y + u * kWarps < y1) rp[y + u * kWarps] = (double)t + row_base;
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) v[u][s] = nx[u][s];
     }
 #pragma unroll
     for (int s = 0; s < STEPS; ++s)
@@ -351,8 +361,8 @@ marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[s][k] = 0.0;
     double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
-    for (int y = y0 + wid; y < y1; y += U * kWarps) {
-        float4 v[U][kSteps];
+    // double-buffered like (P2b): the next two rows are in flight while these two are summed
+    auto fetch = [&](int y, float4 (&v)[U][kSteps]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool row_in = y + u * kWarps < y1;
@@ -364,6 +374,11 @@ marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+    };
+    float4 v[U][kSteps], nx[U][kSteps];
+    fetch(y0 + wid, v);
+    for (int y = y0 + wid; y < y1; y += U * kWarps) {
+        fetch(y + U * kWarps, nx);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool row_in = y + u * kWarps < y1;
@@ -382,6 +397,10 @@ marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_
             rs = warp_sum(rs);
             if (lane == 0 && row_in) rp[y + u * kWarps] = rs;
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int s = 0; s < kSteps; ++s) v[u][s] = nx[u][s];
     }
 #pragma unroll
     for (int s = 0; s < kSteps; ++s)
@@ -558,8 +577,8 @@ static int launch_marginals(const void* att, int B, int H, int W, const Transfor
         static_assert(kU8MaxRows / (kMargThreads / 32) * 255 < 65536, "16-bit column lanes would overflow");
         const int nct = (W + kU8TileCols - 1) / kU8TileCols;
         const int cols = W < kU8TileCols ? W : kU8TileCols;
-        auto kern = cols <= 512 ? marginals_u8_identity_kernel<1, 8>
-                  : cols <= 1024 ? marginals_u8_identity_kernel<2, 4> : marginals_u8_identity_kernel<3, 4>;
+        auto kern = cols <= 512 ? marginals_u8_identity_kernel<1, 4>
+                  : cols <= 1024 ? marginals_u8_identity_kernel<2, 2> : marginals_u8_identity_kernel<3, 2>;
         static thread_local int occ[3] = {0, 0, 0};
         int& o = occ[cols <= 512 ? 0 : cols <= 1024 ? 1 : 2];
         if (o == 0) {
