@@ -3,13 +3,15 @@ upsample_pdf_right_inverse -> clamp / normalise -> L1) must stay differentiable 
 gradients of the library's backward kernels against torch.autograd on the reference's own expressions
 (restated below with their file:line), float32, <= 1e-5 relative to the largest gradient."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from gpu_util import need_gpu
 
-pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "autograd.npz")
 
 
 def ref_safe_softmax(logits, dim=1, eps=1e-6):          # model.py:8-14
@@ -52,6 +54,7 @@ def _close(a, b, tol=1e-5):
     return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-12)
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("alpha,L_in", [(0.0, 512), (0.1, 512), (0.3, 336)])
 def test_training_chain_gradients(alpha, L_in):
     need_gpu()
@@ -76,6 +79,7 @@ def test_training_chain_gradients(alpha, L_in):
     assert zg.grad is not None and _close(zg.grad, zr.grad, 2e-4)
 
 
+@pytest.mark.gpu
 def test_each_backward_kernel():
     need_gpu()
     from attwarp_b200 import checkpoint_utils as CU, model as M
@@ -117,3 +121,48 @@ def test_each_backward_kernel():
     # no_grad callers (trainer.py:284-296) are unaffected
     with torch.no_grad():
         assert not CU.upsample_pdf_right_inverse(torch.rand(2, 24, device="cuda"), 512).requires_grad
+
+
+def _chain(ss, mix, up, z, gt, alpha, L):
+    p = mix(ss(z, dim=1, eps=1e-6), alpha)
+    x = up(p, L).clamp_min(0)
+    x = x / x.sum(dim=1, keepdim=True).clamp_min(1e-6)
+    return torch.nn.functional.l1_loss(x, gt), x
+
+
+def test_restated_expressions_match_the_reference_gradients():
+    """CPU: the expressions restated at the top of this file reproduce values AND gradients recorded from
+    the unmodified reference (tests/golden/make_golden_autograd.py), so they are a valid yardstick."""
+    g = np.load(GOLD)
+    for k in range(int(g["n_chain"])):
+        z = torch.from_numpy(g[f"chain{k}/z"]).requires_grad_(True)
+        loss, x = _chain(ref_safe_softmax, ref_mix_with_uniform, ref_upsample, z, torch.from_numpy(g[f"chain{k}/gt"]),
+                         float(g[f"chain{k}/alpha"]), int(g[f"chain{k}/L"]))
+        loss.backward()
+        assert _close(x, torch.from_numpy(g[f"chain{k}/x"]), 1e-5)
+        assert _close(z.grad, torch.from_numpy(g[f"chain{k}/grad_z"]), 2e-4)
+    p = torch.from_numpy(g["cdf/p"]).requires_grad_(True)
+    (ref_cdf(p) * torch.from_numpy(g["cdf/w"])).sum().backward()
+    assert _close(p.grad, torch.from_numpy(g["cdf/grad_p"]), 1e-5)
+
+
+@pytest.mark.gpu
+def test_library_gradients_match_the_reference_golden():
+    """GPU: forward values and d loss / d logits of the mirrors against the gradients torch.autograd
+    produced on the unmodified reference functions."""
+    need_gpu()
+    from attwarp_b200 import checkpoint_utils as CU, model as M
+    g = np.load(GOLD)
+    for k in range(int(g["n_chain"])):
+        z = torch.from_numpy(g[f"chain{k}/z"]).cuda().requires_grad_(True)
+        loss, x = _chain(M.safe_softmax, M.mix_with_uniform, CU.upsample_pdf_right_inverse, z,
+                         torch.from_numpy(g[f"chain{k}/gt"]).cuda(), float(g[f"chain{k}/alpha"]), int(g[f"chain{k}/L"]))
+        loss.backward()
+        assert _close(x, torch.from_numpy(g[f"chain{k}/x"]), 1e-5)
+        assert abs(float(loss.detach()) - float(g[f"chain{k}/loss"])) <= 1e-6
+        assert _close(z.grad, torch.from_numpy(g[f"chain{k}/grad_z"]), 2e-4)
+    p = torch.from_numpy(g["cdf/p"]).cuda().requires_grad_(True)
+    Fp = CU.cdf_from_density(p)
+    (Fp * torch.from_numpy(g["cdf/w"]).cuda()).sum().backward()
+    assert _close(Fp, torch.from_numpy(g["cdf/F"]), 1e-5)
+    assert _close(p.grad, torch.from_numpy(g["cdf/grad_p"]), 1e-4)
