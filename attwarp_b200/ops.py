@@ -24,19 +24,22 @@ _RAGGED_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("H", np.int32
                           ("Ho", np.int32), ("Wo", np.int32)])
 
 
-_ws_scope = 0        # > 0 while a GraphedCall warms up / captures: that graph's private scratch
+_ws_scope = None     # a dict while a GraphedCall warms up / captures: that graph's private scratch
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     """A reusable uint8 scratch tensor of at least ``nbytes`` on ``device`` (stream-ordered
     reuse is safe because all kernels of this package run on the caller's current stream).
-    A captured graph keeps scratch of its own: graphs may be replayed concurrently on different
-    streams, whatever stream they were captured on."""
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream if _ws_scope == 0 else -1, _ws_scope)
-    buf = _ws_cache.get(key)
+    A captured graph keeps scratch of its own (it lives and dies with the GraphedCall object): graphs may
+    be replayed concurrently on different streams, whatever stream they were captured on."""
+    if _ws_scope is not None:
+        cache, key = _ws_scope, torch.device(device).index
+    else:
+        cache, key = _ws_cache, (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
+        cache[key] = buf
     return buf
 
 
@@ -51,16 +54,13 @@ class GraphedCall:
     stream, on pre-allocated tensors -- into a CUDA graph; ``replay()`` launches the whole
     sequence with one driver call (the per-kernel launch gaps of a 150 us step disappear)."""
 
-    _n = 0
-
     def __init__(self, fn, warmup: int = 2, device=None):
         global _ws_scope
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        GraphedCall._n += 1
-        self._scope = GraphedCall._n
+        self._scratch = {}                   # device index -> this graph's scratch tensor
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        prev, _ws_scope = _ws_scope, self._scope
+        prev, _ws_scope = _ws_scope, self._scratch
         try:
             with torch.cuda.stream(side):
                 for _ in range(warmup):          # kernel attribute opt-ins, this graph's scratch
@@ -71,8 +71,6 @@ class GraphedCall:
                 fn()
         finally:
             _ws_scope = prev
-        # the scratch tensors this graph baked in stay alive with it
-        self._scratch = [v for k, v in _ws_cache.items() if k[2] == self._scope]
 
     def replay(self):
         self.graph.replay()
