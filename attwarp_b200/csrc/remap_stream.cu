@@ -8,7 +8,7 @@
 //
 //   * work = column strips (<= 352 output columns) of images, split over a persistent grid (three CTAs
 //     per SM) in units of kTileRows output rows; every CTA walks a contiguous range of units.  The units
-//     it owns in one strip form a SEGMENT that is streamed top to bottom in CHUNKS of <= R (12) output
+//     it owns in one strip form a SEGMENT that is streamed top to bottom in CHUNKS of <= R (16) output
 //     rows through a ring of shared-memory source stages and a ring of output tiles;
 //   * the PRODUCER warp plans a chunk -- the contiguous range of source rows its output rows tap,
 //     minus the (at most two) rows whose horizontal blends the consumers still hold in registers
