@@ -29,20 +29,43 @@ class _RunningAttention:
     def __init__(self):
         self.sum = None
         self.steps = 0
+        self._starts_key = None          # (device, tuple of starts) of the cached offset tensor
+        self._starts = None
+
+    def _start_tensor(self, starts, device):
+        """int32 device tensor of the per-sample offsets, rebuilt only when they change: generate() calls
+        the hook once per decoding step with the same ranges, and a host->device copy per step was most of
+        the hooked step's cost."""
+        key = (device, tuple(starts))
+        if key != self._starts_key:
+            self._starts = torch.tensor(key[1], dtype=torch.int32, device=device)
+            self._starts_key = key
+        return self._starts
 
     def add_step(self, attn_weights: torch.Tensor, starts, ends):
         B, Hh, q, kv = attn_weights.shape
+        starts = [int(s) for s in starts]
         ends = [min(int(e), kv) for e in ends]
-        lens = sorted({e - int(s) for s, e in zip(starts, ends)})
+        lens = sorted({e - s for s, e in zip(starts, ends)})
         if len(lens) != 1:
             raise ValueError(f"per-sample image-token spans differ in length: {lens}")
         T = lens[0]
+        if T <= 0:
+            raise ValueError(f"empty image-token span (start {starts[0]}, end {ends[0]}, kv length {kv})")
+        if len(starts) != B:
+            raise ValueError(f"{len(starts)} image-token ranges for a batch of {B}")
+        if min(starts) < 0:
+            raise ValueError(f"negative image-token start in {starts}")
         rows = attn_weights[:, :, -1, :].unsqueeze(1)          # [B, 1, Hh, kv] view, no copy
         if rows.stride(3) != 1:
             rows = rows.contiguous()
-        st = torch.as_tensor([int(s) for s in starts], dtype=torch.int32, device=rows.device)
         if self.sum is None:
             self.sum = torch.zeros(B, T, dtype=torch.float32, device=rows.device)
+        elif tuple(self.sum.shape) != (B, T) or self.sum.device != rows.device:
+            # the reference fails in torch.stack / torch.cat when steps disagree (llava.py:131, 409)
+            raise ValueError(f"attention step of shape (B={B}, T={T}) on {rows.device} does not match the running "
+                             f"sum {tuple(self.sum.shape)} on {self.sum.device}; call reinit() between batches")
+        st = self._start_tensor(starts, rows.device)
         ops.aggregate_attention(rows, tok_start=st, num_tokens=T, out=self.sum, accumulate=True)
         self.steps += 1
 

@@ -212,10 +212,16 @@ int launch(const void* attn, int B, int n_rows, int Tlen, int64_t sb, int rows_p
     const size_t smem = (size_t)kAggStages * kRowsPerStage * Tlen * sizeof(T) +
                         (size_t)kConsumerWarps * Tlen * sizeof(float) + 2 * kAggStages * sizeof(uint64_t);
     auto kern = aggregate_rows_tma_kernel<T, NP, EXACT>;
-    static thread_local size_t set_for = 0;
-    if (smem > 48 * 1024 && set_for != smem) {
-        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
+    // the opt-in is a per-device function attribute: the cache is keyed on (device, bytes)
+    struct OptIn { int dev; size_t smem; };
+    static thread_local OptIn set_for = {-1, 0};
+    if (smem > 48 * 1024) {
+        int dev = 0;
+        AW_CUDA(cudaGetDevice(&dev));
+        if (set_for.dev != dev || set_for.smem != smem) {
+            AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_for = OptIn{dev, smem};
+        }
     }
     kern<<<dim3(nsplit, B), kThreads, smem, st>>>(static_cast<const T*>(attn), n_rows, Tlen, sb, rows_per_cta,
                                                    eps, partial);

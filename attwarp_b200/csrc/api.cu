@@ -83,17 +83,34 @@ struct HostArena {
     void* dev = nullptr;
     size_t cap = 0;
     int device = -1;
+    // Device memory and the stream belong to `device`: they are released when the calling thread moves to
+    // another device and when the thread exits (errors ignored: at process exit the runtime may be gone).
+    void release() {
+        if (device >= 0 && (dev != nullptr || stream != nullptr)) {
+            int cur = -1;
+            const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device &&
+                                  cudaSetDevice(device) == cudaSuccess;
+            if (stream != nullptr) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+            if (dev != nullptr) cudaFree(dev);
+            if (switched) cudaSetDevice(cur);
+            (void)cudaGetLastError();
+        }
+        stream = nullptr;
+        dev = nullptr;
+        cap = 0;
+        device = -1;
+    }
+    ~HostArena() { release(); }
     int ensure(size_t bytes) {
         int cur = 0;
         AW_CUDA(cudaGetDevice(&cur));
         if (stream == nullptr || cur != device) {
-            if (dev != nullptr) cudaFree(dev);
-            dev = nullptr;
-            cap = 0;
+            release();
             AW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
             device = cur;
         }
         if (bytes > cap) {
+            AW_CUDA(cudaStreamSynchronize(stream));
             if (dev != nullptr) AW_CUDA(cudaFree(dev));
             dev = nullptr;
             cap = 0;
@@ -102,6 +119,11 @@ struct HostArena {
             cap = want;
         }
         return ATTWARP_OK;
+    }
+    // error path of a host call: nothing of this call may still be pending when the next one reuses the arena
+    int drain(int rc) {
+        if (stream != nullptr) cudaStreamSynchronize(stream);
+        return rc;
     }
 };
 static thread_local HostArena g_arena;
@@ -343,9 +365,23 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
     return launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
 }
 
+static int warp_image_host_impl(const void* image_host, int img_dtype, int C, int H, int W,
+                                const void* att_host, int att_dtype, int Wo, int Ho,
+                                const attwarp_transform_params* tp, void* out_host, int* used_fallback);
+
 int attwarp_warp_image_host(const void* image_host, int img_dtype, int C, int H, int W,
                             const void* att_host, int att_dtype, int Wo, int Ho,
                             const attwarp_transform_params* tp, void* out_host, int* used_fallback) {
+    const int rc = warp_image_host_impl(image_host, img_dtype, C, H, W, att_host, att_dtype, Wo, Ho, tp, out_host,
+                                        used_fallback);
+    // an early return leaves transfers or kernels of this call pending on the arena stream: drain them before
+    // the next call reuses the arena (and before the caller frees its host buffers)
+    return rc == ATTWARP_OK ? rc : g_arena.drain(rc);
+}
+
+static int warp_image_host_impl(const void* image_host, int img_dtype, int C, int H, int W,
+                                const void* att_host, int att_dtype, int Wo, int Ho,
+                                const attwarp_transform_params* tp, void* out_host, int* used_fallback) {
     AW_REQUIRE(image_host && att_host && out_host, "warp_image_host: NULL pointer");
     AW_REQUIRE(C > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "warp_image_host: sizes must be positive");
     AW_REQUIRE(img_dtype == ATTWARP_U8 || img_dtype == ATTWARP_F32, "warp_image_host: image dtype must be u8/f32");

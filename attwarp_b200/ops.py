@@ -43,6 +43,14 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+def _check_out(name, t, shape, dtype, device):
+    """Caller-provided output / scratch tensors are written through raw pointers: anything but the exact
+    dense tensor would corrupt memory silently."""
+    if (tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device or not t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous {dtype} tensor of shape {tuple(shape)} on {device}, got "
+                         f"{t.dtype} {tuple(t.shape)} on {t.device} (contiguous={t.is_contiguous()})")
+
+
 def _tp(transform, exp_scale, exp_divisor, apply_inverse):
     if isinstance(transform, _lib.TransformParams):
         return transform
@@ -98,6 +106,8 @@ def aggregate_attention(attn: torch.Tensor, tok_start: torch.Tensor | None = Non
     if out is None:
         out = torch.empty(B, T, dtype=torch.float32, device=attn.device)
         accumulate = False
+    else:
+        _check_out("aggregate_attention: out", out, (B, T), torch.float32, attn.device)
     wsb = lib.attwarp_aggregate_workspace_bytes(B, L, Hh, T)
     ws = _workspace(wsb, attn.device)
     with torch.cuda.device(attn.device):
@@ -184,7 +194,8 @@ def maps_from_tokens(tok: torch.Tensor, image_size, out_size=None, transform="id
     tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
     if out is not None:
         map_x, map_y = out
-        assert tuple(map_x.shape) == (B, Wo) and tuple(map_y.shape) == (B, Ho)
+        _check_out("maps_from_tokens: out[0] (map_x)", map_x, (B, Wo), torch.float32, tok.device)
+        _check_out("maps_from_tokens: out[1] (map_y)", map_y, (B, Ho), torch.float32, tok.device)
     else:
         map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)
         map_y = torch.empty(B, Ho, dtype=torch.float32, device=tok.device)
@@ -238,7 +249,7 @@ def remap_bilinear(img: torch.Tensor, map_x: torch.Tensor, map_y: torch.Tensor,
     if out is None:
         out = torch.empty(shape, dtype=img.dtype, device=img.device)
     else:
-        assert tuple(out.shape) == shape and out.dtype == img.dtype and out.is_contiguous()
+        _check_out("remap_bilinear: out", out, shape, img.dtype, img.device)
     with torch.cuda.device(img.device):
         check(lib.attwarp_remap_bilinear(ptr(img), ptr(out), TORCH_DTYPE_IDS[img.dtype], lay, B, Cc,
                                          H, W, Ho, Wo, ptr(map_x), ptr(map_y),
@@ -276,11 +287,17 @@ def warp_from_attention_tokens(attn: torch.Tensor, images: torch.Tensor, grid_hw
     assert Bi == B
     Ho, Wo = (H, W) if out_size is None else out_size
     shape = (B, Ho, Wo, Cc) if layout == "hwc" else (B, Cc, Ho, Wo)
-    if out is None:
-        out = torch.empty(shape, dtype=images.dtype, device=images.device)
     dev = images.device
+    if out is None:
+        out = torch.empty(shape, dtype=images.dtype, device=dev)
+    else:
+        _check_out("warp_from_attention_tokens: out", out, shape, images.dtype, dev)
     if aux is not None:                      # caller-provided (tok, map_x, map_y) buffers
         tok, map_x, map_y = aux
+        _check_out("warp_from_attention_tokens: aux[0] (token map)", tok.view(B, -1) if tok.is_contiguous() else tok,
+                   (B, gh * gw), torch.float32, dev)
+        _check_out("warp_from_attention_tokens: aux[1] (map_x)", map_x, (B, Wo), torch.float32, dev)
+        _check_out("warp_from_attention_tokens: aux[2] (map_y)", map_y, (B, Ho), torch.float32, dev)
     else:
         tok = torch.empty(B, gh * gw, dtype=torch.float32, device=dev)
         map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)
@@ -329,9 +346,11 @@ def warp_from_pdfs(img: torch.Tensor, px: torch.Tensor, py: torch.Tensor, alpha:
     assert px.shape[0] == B and py.shape[0] == B and px.dim() == 2 and py.dim() == 2
     Mx = right_inverse_matrix(W, px.shape[1], eps, dev)
     My = right_inverse_matrix(H, py.shape[1], eps, dev)
+    shape = (B, Cc, Ho, Wo) if layout == "chw" else (B, Ho, Wo, Cc)
     if out is None:
-        shape = (B, Cc, Ho, Wo) if layout == "chw" else (B, Ho, Wo, Cc)
         out = torch.empty(shape, dtype=img.dtype, device=dev)
+    else:
+        _check_out("warp_from_pdfs: out", out, shape, img.dtype, dev)
     Fx = torch.empty(B, W, dtype=torch.float32, device=dev)
     Fy = torch.empty(B, H, dtype=torch.float32, device=dev)
     map_x = torch.empty(B, Wo, dtype=torch.float32, device=dev)

@@ -36,8 +36,9 @@ def lpt_shard(costs: Sequence[float], world: int) -> List[List[int]]:
 
 
 def checksum64(t: torch.Tensor) -> int:
-    """Order-independent 64-bit checksum (sum of the bytes' int64 values weighted by position
-    parity) -- cheap, runs on the tensor's device, used to compare sharded vs unsharded runs."""
+    """Position-weighted (so order-DEPENDENT) 64-bit checksum: sum of the bytes' values times
+    ``(position % 251) + 1``.  Cheap, runs on the tensor's device; two runs that produce the same bytes in
+    the same order -- a sharded and an unsharded pass over the same image -- give the same value."""
     flat = t.reshape(-1).view(torch.uint8).to(torch.int64)
     w = (torch.arange(flat.numel(), device=flat.device, dtype=torch.int64) % 251) + 1
     return int((flat * w).sum().item())
