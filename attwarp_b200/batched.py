@@ -78,10 +78,21 @@ class HostBatchPipeline:
                      torch.empty(chunk, self.Ho, dtype=torch.float32, device=self.device))))
         self.kernel_launches = 0
 
-    def run(self, attn_host: torch.Tensor, images_host: torch.Tensor, out_host: torch.Tensor):
+    def run(self, attn_host: torch.Tensor, images_host: torch.Tensor, out_host: torch.Tensor,
+            tok_host: torch.Tensor | None = None):
         """attn_host [B,L,Hh,T], images_host [B,H,W,C], out_host [B,Ho,Wo,C]: host tensors
-        (pinned for real overlap).  Returns after everything is enqueued; call ``sync()``."""
+        (pinned for real overlap); ``tok_host`` [B,T] float32 optionally receives the stage-1 token maps (the
+        attention map the reference drivers save next to the warped image, main.py:371).  Returns after
+        everything is enqueued; call ``sync()``."""
         B = attn_host.shape[0]
+        T = self.gh * self.gw
+        if (tuple(attn_host.shape) != (B, self.L, self.Hh, T) or tuple(images_host.shape) != (B, self.H, self.W, self.C)
+                or tuple(out_host.shape) != (B, self.Ho, self.Wo, self.C)
+                or (tok_host is not None and (tuple(tok_host.shape) != (B, T) or tok_host.dtype != torch.float32))):
+            raise ValueError("HostBatchPipeline.run: tensor shapes do not match the pipeline's configuration")
+        if attn_host.dtype != self.slots[0]["attn"].dtype or images_host.dtype != self.slots[0]["img"].dtype \
+                or out_host.dtype != self.slots[0]["out"].dtype:
+            raise ValueError("HostBatchPipeline.run: tensor dtypes do not match the pipeline's configuration")
         caller = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(caller)
@@ -98,6 +109,8 @@ class HostBatchPipeline:
                     transform=self.transform, out=slot["out"][:n],
                     aux=tuple(a[:n] for a in slot["aux"]))
                 out_host[lo:hi].copy_(slot["out"][:n], non_blocking=True)
+                if tok_host is not None:
+                    tok_host[lo:hi].copy_(slot["aux"][0][:n], non_blocking=True)
             self.kernel_launches += 3
             k += 1
         for s in self.streams:

@@ -310,3 +310,31 @@ def upsample_tokens_nearest(tok, H, W):
     yi = (np.arange(H) * gh) // H
     xi = (np.arange(W) * gw) // W
     return tok[yi][:, xi]
+
+
+# --------------------------------------------------------------------------------------
+# the wrapper the drivers call (new_method.py:405-506), array level
+# --------------------------------------------------------------------------------------
+def save_warped_image_arrays(image_rgb, att_map, width=500, height=500, transform="identity", exp_scale=1.0,
+                             exp_divisor=1.0, apply_inverse=False, remap_backend="restated"):
+    """What ``save_warped_image`` hands to ``cv2.imwrite(output_path, ...)`` for an image given as a PIL / RGB
+    array: RGB -> BGR (new_method.py:421-422; a 2-D image is replicated to three channels by cvtColor), the
+    attention map coerced to 2-D (:432-452: list -> first element, [h,w,c] -> mean over c), the IMAGE resized to
+    the attention map's size with ``cv2.resize(INTER_LINEAR)`` when they differ (:478, :355-376 -- the real cv2
+    call: this step is host-side scaffolding in the product too), then ``warp_image_by_attention`` with the
+    named transform (:483-486).  Returns the BGR array."""
+    import cv2
+    image = np.asarray(image_rgb)
+    bgr = np.repeat(image[..., None], 3, -1) if image.ndim == 2 else image[..., ::-1]
+    bgr = np.ascontiguousarray(bgr)
+    if isinstance(att_map, list):
+        att_map = np.asarray(att_map[0]) if len(att_map) > 0 else np.ones((height, width), np.float32) * 128
+    att = np.asarray(att_map)
+    if att.ndim == 3:
+        att = np.mean(att, axis=2)
+    elif att.ndim != 2:
+        raise ValueError(f"Attention map must be 2D, got shape {att.shape}")
+    if bgr.shape[:2] != att.shape[:2]:
+        bgr = cv2.resize(bgr, (att.shape[1], att.shape[0]), interpolation=cv2.INTER_LINEAR)
+    return warp_image_by_attention(bgr, att, width, height, resolve_transform(transform), exp_scale, exp_divisor,
+                                   apply_inverse, remap_backend)

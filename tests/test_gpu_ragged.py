@@ -92,3 +92,31 @@ def test_ragged_mixed_resolution_c4_sample():
     _check(imgs, toks, sizes, outs, "identity")
     for a, b in zip(outs, again):
         assert torch.equal(a, b)
+
+
+def test_ragged_c4_nonsquare_resized():
+    """BASELINE configs[3] with what real mixed-resolution batches look like: non-square images, widths that
+    are not multiples of 16 (row pitches off the 16-byte phase: the per-row copy path), output sizes different
+    from the input sizes (up- and down-scaling per axis) -- every image against the oracle, and the same images
+    one by one through the uniform entry points (bit-equal)."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(4242)
+    n = 14
+    hs, ws = rng.integers(224, 2049, size=n), rng.integers(224, 2049, size=n)
+    ws[:4] = [333, 1001, 2047, 225]                      # 3 W mod 16 != 0
+    hos = np.clip((hs * rng.uniform(0.6, 1.5, n)).astype(int), 64, 2048)
+    wos = np.clip((ws * rng.uniform(0.6, 1.5, n)).astype(int), 64, 2048)
+    wos[:3] = [500, 777, 1919]
+    assert any((3 * int(w)) % 16 for w in ws) and any((3 * int(w)) % 16 for w in wos)
+    imgs = [rng.integers(0, 256, (int(h), int(w), 3), dtype=np.uint8) for h, w in zip(hs, ws)]
+    out_sizes = [(int(a), int(b)) for a, b in zip(hos, wos)]
+    toks = _tokens(n, 24, seed=4242)
+    d_imgs = [dev(i) for i in imgs]
+    outs = ops.warp_ragged_from_tokens(dev(toks), d_imgs, out_sizes)
+    torch.cuda.synchronize()
+    _check(imgs, toks, out_sizes, outs, "identity")
+    for i in (0, 3, n - 1):
+        mx, my = ops.maps_from_tokens(dev(toks[i:i + 1]), imgs[i].shape[:2], out_sizes[i])
+        one = ops.remap_bilinear(d_imgs[i][None], mx, my, "hwc")[0]
+        assert torch.equal(one, outs[i])

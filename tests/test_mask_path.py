@@ -88,27 +88,53 @@ def test_gpu_lanczos_vs_pillow_batched():
 
 
 @pytest.mark.gpu
-def test_gpu_c1_driver_chain(gm):
+@pytest.mark.parametrize("name,out_hw", [("c1_336", (500, 500)), ("c1_336", (336, 336)), ("wide_500x333", (500, 500)),
+                                         ("big_1344", (1344, 1344))])
+def test_gpu_c1_driver_chain(gm, name, out_hw, record_property):
     """BASELINE configs[0] the way main.py runs it: 24 x 24 attention -> blend_mask's uint8 mask at image
-    size -> save_warped_image(att_map=mask, 500 x 500, 'identity')."""
+    size -> save_warped_image(att_map=mask, 500 x 500, 'identity').
+
+    The only inexact link of the chain is revise_mask's float32 arithmetic (min-max, z-score x 10, sigmoid, box
+    filter) ahead of ToPILImage's truncation of v * 255: a token whose v * 255 sits within an ulp of an integer may
+    come out one byte lower or higher than torch's CPU kernels make it.  The test SAYS which case it is in:
+      * no token byte differs from the reference's -> the mask is bit-equal and the warped image must be within
+        +-1 LSB of the oracle chain on every pixel (the BASELINE.md bar);
+      * otherwise at most 2 of the gh*gw token bytes may differ, each by 1, the mask by <= 2 LSB on <= 2 % of the
+        pixels, and the warped image is compared with the oracle run on the GPU's OWN mask (+-1 LSB): the rest of
+        the chain is still held to the bar."""
     _need_gpu()
     from attwarp_b200 import attention_extraction as AE, ops
     from PIL import Image
-    tok = gm["c1_336/tok"]
+    tok, ref_mask, ref_u8 = gm[name + "/tok"], gm[name + "/mask"], gm[name + "/u8_24"]
+    H, W = ref_mask.shape
     rng = np.random.default_rng(1234)
-    img = rng.integers(0, 256, (336, 336, 3), dtype=np.uint8)
-    mask = ops.mota_mask(torch.from_numpy(tok)[None].cuda(), (336, 336))
-    mx, my = ops.maps_from_attention(mask, (500, 500), "identity")
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    d_tok = torch.from_numpy(tok)[None].cuda()
+    _, u8 = ops.revise_mask(d_tok, 3, 10, return_u8=True)
+    mask = ops.mota_mask(d_tok, (H, W))
+    mx, my = ops.maps_from_attention(mask, out_hw, "identity")
     out = ops.remap_bilinear(torch.from_numpy(img)[None].cuda(), mx, my, "hwc")[0].cpu().numpy()
-    ref_mask = gm["c1_336/mask"]
-    ref = ON.warp_image_by_attention(img, ref_mask, 500, 500, "identity")
-    if np.array_equal(mask[0].cpu().numpy(), ref_mask):
-        assert np.abs(out.astype(int) - ref.astype(int)).max() <= 1
-    else:                                   # a flipped token byte moves the maps by a few 1e-3 px
-        assert (np.abs(out.astype(int) - ref.astype(int)) > 1).mean() <= 0.02
-    # the mirror of blend_mask returns the same mask as a PIL image
-    overlay, pil_mask = AE.blend_mask(Image.fromarray(img, mode="RGB"), torch.from_numpy(tok), 10, 3, Image.LANCZOS, 0)
-    assert pil_mask.mode == "L" and pil_mask.size == (336, 336) and overlay.size == (336, 336)
-    assert np.array_equal(np.array(pil_mask), mask[0].cpu().numpy())
-    rev = AE.revise_mask(torch.from_numpy(tok), 3, 10)
-    assert rev.shape == (24, 24) and rev.device.type == "cpu"
+    mask_h = mask[0].cpu().numpy()
+    tok_diff = np.abs(u8[0].cpu().numpy().astype(int) - ref_u8.astype(int))
+    flipped = int((tok_diff != 0).sum())
+    record_property("flipped_token_bytes", flipped)
+    print(f"[c1 chain {name} -> {out_hw}] token bytes differing from the reference: {flipped} of {tok_diff.size}")
+    if flipped == 0:
+        assert np.array_equal(mask_h, ref_mask)
+        ref = ON.warp_image_by_attention(img, ref_mask, out_hw[1], out_hw[0], "identity")
+        record_property("branch", "mask bit-equal: whole chain held to +-1 LSB")
+    else:
+        assert flipped <= 2 and tok_diff.max() <= 1
+        d = np.abs(mask_h.astype(int) - ref_mask.astype(int))
+        assert d.max() <= 2 and (d != 0).mean() <= 0.02
+        ref = ON.warp_image_by_attention(img, mask_h, out_hw[1], out_hw[0], "identity")
+        record_property("branch", f"{flipped} token byte(s) flipped: stages 2b-5 held to +-1 LSB on the GPU's mask")
+    diff = np.abs(out.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+    if name == "c1_336" and out_hw == (500, 500):
+        # the mirror of blend_mask returns the same mask as a PIL image
+        overlay, pil_mask = AE.blend_mask(Image.fromarray(img, mode="RGB"), torch.from_numpy(tok), 10, 3, Image.LANCZOS, 0)
+        assert pil_mask.mode == "L" and pil_mask.size == (336, 336) and overlay.size == (336, 336)
+        assert np.array_equal(np.array(pil_mask), mask_h)
+        rev = AE.revise_mask(torch.from_numpy(tok), 3, 10)
+        assert rev.shape == (24, 24) and rev.device.type == "cpu"
