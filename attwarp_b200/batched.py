@@ -118,3 +118,92 @@ class HostBatchPipeline:
 
     def sync(self):
         torch.cuda.current_stream(self.device).synchronize()
+
+
+class HostTokenPipeline:
+    """The same host-buffer pipeline for batches whose token maps already exist (BASELINE configs[2]: a [B,gh,gw]
+    float32 token map per image instead of the attention tensor):  per chunk, on alternating streams,
+    H2D(token maps) -> H2D(images) -> stages 2-5 (``maps_from_tokens`` + ``remap_bilinear``) -> D2H(warped
+    images).  The images travel once in each direction, so the two PCIe directions work at the same time."""
+
+    def __init__(self, chunk: int, grid_hw, image_hwc, out_hw=None, img_dtype=torch.uint8, transform="identity",
+                 n_streams: int = 2, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.chunk = chunk
+        self.gh, self.gw = grid_hw
+        self.H, self.W, self.C = image_hwc
+        self.Ho, self.Wo = (self.H, self.W) if out_hw is None else out_hw
+        self.transform = transform
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self.slots = []
+        for _ in range(n_streams):
+            self.slots.append(dict(
+                tok=torch.empty(chunk, self.gh, self.gw, dtype=torch.float32, device=self.device),
+                img=torch.empty(chunk, self.H, self.W, self.C, dtype=img_dtype, device=self.device),
+                out=torch.empty(chunk, self.Ho, self.Wo, self.C, dtype=img_dtype, device=self.device),
+                maps=(torch.empty(chunk, self.Wo, dtype=torch.float32, device=self.device),
+                      torch.empty(chunk, self.Ho, dtype=torch.float32, device=self.device))))
+        self.kernel_launches = 0
+
+    def run(self, tok_host: torch.Tensor, images_host: torch.Tensor, out_host: torch.Tensor):
+        """tok_host [B,gh,gw] float32, images_host [B,H,W,C], out_host [B,Ho,Wo,C] (pinned host tensors).
+        Returns after everything is enqueued; call ``sync()``."""
+        B = tok_host.shape[0]
+        if (tuple(tok_host.shape) != (B, self.gh, self.gw) or tok_host.dtype != torch.float32
+                or tuple(images_host.shape) != (B, self.H, self.W, self.C)
+                or tuple(out_host.shape) != (B, self.Ho, self.Wo, self.C)
+                or images_host.dtype != self.slots[0]["img"].dtype or out_host.dtype != self.slots[0]["out"].dtype):
+            raise ValueError("HostTokenPipeline.run: tensors do not match the pipeline's configuration")
+        caller = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(caller)
+        k = 0
+        for lo in range(0, B, self.chunk):
+            hi = min(lo + self.chunk, B)
+            n = hi - lo
+            slot, st = self.slots[k % len(self.slots)], self.streams[k % len(self.streams)]
+            with torch.cuda.stream(st):
+                slot["tok"][:n].copy_(tok_host[lo:hi], non_blocking=True)
+                slot["img"][:n].copy_(images_host[lo:hi], non_blocking=True)
+                mx, my = slot["maps"][0][:n], slot["maps"][1][:n]
+                ops.maps_from_tokens(slot["tok"][:n], (self.H, self.W), (self.Ho, self.Wo), self.transform,
+                                     out=(mx, my))
+                ops.remap_bilinear(slot["img"][:n], mx, my, "hwc", out=slot["out"][:n])
+                out_host[lo:hi].copy_(slot["out"][:n], non_blocking=True)
+            self.kernel_launches += 2
+            k += 1
+        for s in self.streams:
+            caller.wait_stream(s)
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+class HostCopyProbe:
+    """The copies of a host pipeline WITHOUT its kernels: the same chunks, byte counts, streams and pinned
+    buffers, so that ``bench.py`` can report how far ``e2e`` is from what the box's PCIe / host memory delivers
+    when every rank copies at the same time (``e2e.copy_only_ms_per_step``)."""
+
+    def __init__(self, pipeline):
+        self.p = pipeline
+
+    def run(self, inputs_host, out_host):
+        """inputs_host: the host tensors ``run`` copies in, in order, matched to the slot buffers by name."""
+        p = self.p
+        names = ("attn", "img") if "attn" in p.slots[0] else ("tok", "img")
+        B = inputs_host[0].shape[0]
+        caller = torch.cuda.current_stream(p.device)
+        for s in p.streams:
+            s.wait_stream(caller)
+        k = 0
+        for lo in range(0, B, p.chunk):
+            hi = min(lo + p.chunk, B)
+            n = hi - lo
+            slot, st = p.slots[k % len(p.slots)], p.streams[k % len(p.streams)]
+            with torch.cuda.stream(st):
+                for nm, h in zip(names, inputs_host):
+                    slot[nm][:n].copy_(h[lo:hi], non_blocking=True)
+                out_host[lo:hi].copy_(slot["out"][:n], non_blocking=True)
+            k += 1
+        for s in p.streams:
+            caller.wait_stream(s)

@@ -250,26 +250,54 @@ class ClockSampler:
                 "samples": len(sm), "how": "nvidia-smi -lms 50 during the timed region"}
 
 
+
 # ------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference)
+# workload descriptions (identical in both arms: `config` is a function of the workload and the world size)
 # ------------------------------------------------------------------------------------------
-def cpu_arm(wl_key, steps, warmup, budget_s, full_steps):
-    """Times the oracle port on the host cores.  Each step = one pass over a bounded sample of
+def workload_config(wl_key, world):
+    wl = WORKLOADS[wl_key]
+    B, side, C = wl["B"], wl["side"], wl["C"]
+    if wl.get("ragged"):
+        return {"workload": wl["name"], "images_total": B, "transform": "identity",
+                "l2_policy": "inputs larger than L2: a rank's shard is >= 1.2 GB in + as much out (126 MB L2)",
+                "parallelism": f"one batch of {B} images LPT-sharded by pixels in + out over {world} GPU(s) "
+                               "(strong scaling), no data-path collective"}
+    if wl.get("pdf"):
+        by = B * C * side * side * 4 * 2
+        return {"workload": wl["name"], "images_per_step_per_gpu": B, "transform": "n/a (PDFs in)",
+                "l2_policy": f"inputs larger than L2: one batch is {by / 1e6:.0f} MB in+out > 126 MB L2; the GPU arm "
+                             "rotates over resident buffer sets",
+                "parallelism": f"images sharded by index over {world} GPU(s) (weak scaling), no data-path collective"}
+    by = B * side * side * C * 2 + (B * wl["L"] * wl["Hh"] * wl["grid"] ** 2 * 2 if wl["has_attention"] else 0)
+    return {"workload": wl["name"], "images_per_step_per_gpu": B, "transform": "identity",
+            "l2_policy": f"inputs larger than L2: one batch ({'attention + ' if wl['has_attention'] else ''}images in + out) "
+                         f"is {by / 1e6:.0f} MB > 126 MB L2; the GPU arm rotates over resident buffer sets",
+            "parallelism": f"images sharded by index over {world} GPU(s) (weak scaling: every rank its own batch), "
+                           "no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (the reference's own CPU path: unmodified reference from baseline/_ref when present, else the oracle port)
+# ------------------------------------------------------------------------------------------
+def cpu_arm(wl_key, steps, warmup, budget_s, rows=False):
+    """Times the reference CPU path on the host cores.  Each step = one pass over a bounded sample of
     the workload (the full batch when it is cheap enough)."""
     from oracle import cpu_baseline as CB
     wl = WORKLOADS[wl_key]
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # calibrate on a couple of images, single process
+    # calibrate on a few images, single process
     if wl["has_attention"]:
-        attn, imgs = CB.make_c2_sample(2, wl["L"], wl["Hh"], wl["grid"], wl["side"])
+        attn, imgs = CB.make_c2_sample(4, wl["L"], wl["Hh"], wl["grid"], wl["side"])
         tok = None
     else:
-        tok, imgs = CB.make_c3_sample(2, wl["grid"], wl["side"])
+        tok, imgs = CB.make_c3_sample(4, wl["grid"], wl["side"])
         attn = None
     r = CB.CpuRunner(attn, tok, imgs, wl["grid"], (wl["side"], wl["side"]), workers=1)
+    kind = r.kind
+    thread_rows = r.threading_rows(4, 2) if rows else None
     r.step()
     t1, _ = r.step()
-    per_img = t1 / 2
+    per_img = t1 / 4
     r.close()
     total_steps = steps + warmup
     # images per step so that the whole run fits the budget (assume ~70 % parallel efficiency)
@@ -290,263 +318,132 @@ def cpu_arm(wl_key, steps, warmup, budget_s, full_steps):
     value = n * steps / t
     import cv2
     import numpy
-    info = {"value": value, "unit": UNIT, "cores": runner.workers, "kind": "port",
-            "sample": f"{n} of {wl['B']} images per step x {steps} steps ({warmup} warm-up), "
-                      f"{runner.workers} fork()ed workers x 1 image at a time, cv2.setNumThreads(1); "
+    what = ("the UNMODIFIED reference functions (MaskHookLogger._process_attention/finalize, set_transform_function, "
+            "warp_image_by_attention) imported from baseline/_ref" if kind == "reference"
+            else "the oracle port (no copy of the reference present)")
+    info = {"value": value, "unit": UNIT, "cores": runner.workers, "kind": kind,
+            "sample": f"{n} of {wl['B']} images per step x {steps} steps ({warmup} warm-up); {what}; "
+                      f"{runner.workers} fork()ed workers x 1 image at a time, cv2.setNumThreads(1), torch 1 thread; "
                       f"single-process cost {per_img * 1e3:.2f} ms/image; numpy {numpy.__version__}, "
                       f"cv2 {cv2.__version__}; host cpus visible {avail}"}
+    if thread_rows is not None:
+        info["rows"] = thread_rows
     return info, t / steps * 1e3
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
-    wl = WORKLOADS[args.workload]
+    key = "c2" if args.workload == "all" else args.workload
+    wl = WORKLOADS[key]
     if wl.get("ragged") or wl.get("pdf"):
         print(json.dumps({"impl": "reference", "unavailable": "the CPU arm covers the bench workloads c2 and c3; "
                           "c4 and c5 are parity/scaling configurations"}), flush=True)
         return 0
-    info, ms_per_step = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0,
-                                full_steps=True)
+    info, ms_per_step = cpu_arm(key, args.steps, args.warmup, budget_s=100.0 if args.workload == "all" else 120.0,
+                                rows=True)
     line = {"impl": "reference", "metric": METRIC, "value": info["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
-            "config": {"workload": wl["name"], "timing": "wall clock around each CPU step"},
+            "vs_baseline": None, "dtype": DTYPES[key], "data": "synthetic",
+            "config": workload_config(key, world),
+            "run": {"timing": "wall clock around each CPU step", "arm": "reference CPU path on the host cores"},
             "cpu_baseline": info,
             "e2e": {"value": info["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload == "all":
+        # 1344^2 (configs[2]) on the same host cores, a smaller sample
+        i3, ms3 = cpu_arm("c3", max(2, min(args.steps, 3)), 1, budget_s=40.0)
+        line["workloads"] = {"c3": {"metric": METRIC, "value": i3["value"], "unit": UNIT, "ms_per_step": ms3,
+                                    "config": workload_config("c3", world), "cpu_baseline": i3,
+                                    "e2e": {"value": i3["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                            "d2h_bytes_per_step": 0}}}
     print(json.dumps(line), flush=True)
     return 0
+
+
+DTYPES = {"c2": "bf16->fp32 (stage 1), f64 (stages 2-4), u8 fixed-point (stage 5)",
+          "c3": "f64 (stages 2-4), u8 fixed-point (stage 5)",
+          "c4": "f64 (stages 2-4), u8 fixed-point (stage 5)",
+          "c5": "f32 (PDF/CDF rows), f64 (inversion), f32 (resample)"}
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def run_gpu_ragged(args, rank, local_rank, world):
-    """configs[3]: ONE batch of 1024 mixed-resolution images split over the ranks by greedy LPT on
-    pixels in + pixels out (strong scaling, no data-path collective); a step = stages 2-5 over the
-    rank's shard through the ragged entry point (one launch per stage)."""
-    import numpy as np
+class Ctx:
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            init_nccl(self.dev)
+        self.peak, self.peak_src = measured_peak()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+
+def timed_steps(ctx, step, n_steps, first_index, fork=None, join=None):
+    """barrier + synchronize, CUDA events around exactly n_steps calls of step(i), synchronize + barrier.
+    Returns (elapsed ms on this rank, launches)."""
     import torch
-    import torch.distributed as dist
-
-    from attwarp_b200 import ops, sharding
-
-    wl = WORKLOADS[args.workload]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        init_nccl(dev)
-    B, C, grid = wl["B"], wl["C"], wl["grid"]
-    sides = np.random.default_rng(1237).integers(224, 2049, size=B)
-    shards = sharding.lpt_shard([2.0 * float(s) * float(s) for s in sides], world)
-    mine = shards[rank]
-    gen = torch.Generator(device=dev).manual_seed(1237 + rank)
-    imgs = [torch.randint(0, 256, (int(sides[i]), int(sides[i]), C), device=dev, dtype=torch.uint8, generator=gen)
-            for i in mine]
-    outs = [torch.empty_like(t) for t in imgs]
-    tok = torch.rand(len(mine), grid, grid, device=dev, generator=gen) ** 3
-    tok = (tok / tok.sum(dim=(1, 2), keepdim=True)).contiguous()
-    my_bytes = 2 * sum(t.numel() for t in imgs)
-
-    def step():
-        ops.warp_ragged_from_tokens(tok, imgs, outs=outs)
-        return 2
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
-    if rank == 0:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    ctx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     ev0.record()
-    for _ in range(args.steps):
-        launches += step()
+    if fork is not None:
+        fork()                                    # every ring stream starts after ev0 ...
+    for i in range(n_steps):
+        launches += step(first_index + i)
+    if join is not None:
+        join()                                    # ... and ev1 waits for all of them
     ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = ev0.elapsed_time(ev1)
-    chk = sharding.checksum64(outs[0])
-    stats = sharding.gather_stats(elapsed_ms, len(mine) * args.steps, chk, dev)
-    bstats = sharding.gather_stats(elapsed_ms, my_bytes // 1024, 0, dev)
-    value = sharding.aggregate_throughput(stats)
-    worst_ms = max(s[0] for s in stats)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return 0
-    peak, peak_src = measured_peak()
-    total_bytes = sum(b[1] for b in bstats) * 1024
-    gbs = total_bytes / (worst_ms / args.steps) / 1e6 / world
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (stages 2-4), u8 fixed-point (stage 5)",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "images_total": B,
-                       "images_per_rank": [len(s) for s in shards],
-                       "l2_policy": f"each rank's shard is {my_bytes / 1e6:.0f} MB in+out > 126 MB L2",
-                       "parallelism": f"LPT shards over {world} GPU(s), no data-path collective",
-                       "launch": "one maps + one resample launch per step (descriptor table built on the host each step)"},
-            "clocks": clocks, "e2e": None, "gpu_launches": launches * world,
-            "roofline": {"bound": "hbm", "kernel": "maps_from_tokens + remap_u8_stream (whole step, host table build included)",
-                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": total_bytes // world},
-            "cpu_baseline": None, "per_rank_ms": [s[0] for s in stats]}
-    print(json.dumps(line), flush=True)
-    return 0
+    ctx.barrier()
+    return ev0.elapsed_time(ev1), launches
 
 
-def run_gpu_pdf(args, rank, local_rank, world):
-    """configs[4]: predicted PDFs feeding the fused CDF + resample path (trainer.py:212-218, 285-289 chain):
-    a step = attwarp_warp_from_pdfs over one batch of 128 float32 NCHW images (three launches)."""
+def pick_roofline(ctx, kernels, workload, total_bytes):
+    """`roofline` = the kernel that dominates the step; when two kernels are within 10 % of each other in time,
+    the one FURTHER from the peak.  `worst` = the kernel furthest below peak of all, `worst_streaming` = among the
+    kernels that move >= 5 % of the step's bytes (the others are latency-bound: a few KB per image)."""
+    streaming = {k: v for k, v in kernels.items() if v["algorithmic_bytes"] >= 0.05 * total_bytes}
+    dom_ms = max(v["ms"] for v in streaming.values())
+    cands = [k for k, v in streaming.items() if v["ms"] >= 0.9 * dom_ms]
+    dom = min(cands, key=lambda k: kernels[k]["frac"])
+    worst = min(kernels, key=lambda k: kernels[k]["frac"])
+    worst_s = min(streaming, key=lambda k: kernels[k]["frac"])
+    return {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": ctx.peak,
+            "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, workload),
+            "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+            "kernel_ms": kernels[dom]["ms"],
+            "selection": "dominant kernel by CUDA-event time; of kernels within 10 % in time, the lower fraction",
+            "worst": {"kernel": worst, "frac": kernels[worst]["frac"], "achieved": kernels[worst]["achieved_gbs"],
+                      "note": "latency-bound launch (a few KB per image)" if worst not in streaming else "streaming kernel"},
+            "worst_streaming": {"kernel": worst_s, "frac": kernels[worst_s]["frac"],
+                                "achieved": kernels[worst_s]["achieved_gbs"]}}
+
+
+def bench_uniform(ctx, wl_key, with_clocks=True):
+    """configs[1] / configs[2]: uniform batches, every rank its own batch (weak scaling)."""
     import torch
-    import torch.distributed as dist
 
     from attwarp_b200 import ops, sharding
-    from attwarp_b200.batched import StreamRing
+    from attwarp_b200.batched import HostBatchPipeline, HostCopyProbe, HostTokenPipeline, StreamRing
 
-    wl = WORKLOADS[args.workload]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        init_nccl(dev)
-    B, C, side, N = wl["B"], wl["C"], wl["side"], wl["grid"]
-    R = args.rotate if args.rotate > 0 else 3
-    gen = torch.Generator(device=dev).manual_seed(1238 + rank)
-    sets = []
-    for _ in range(R):
-        sets.append(dict(px=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
-                         py=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
-                         img=torch.rand(B, C, side, side, device=dev, generator=gen),
-                         out=torch.empty(B, C, side, side, device=dev)))
-
-    def enqueue(s):
-        ops.warp_from_pdfs(s["img"], s["px"], s["py"], alpha=0.1, layout="chw", out=s["out"])
-
-    graphs = None if args.no_graph else [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
-    n_streams = max(1, min(args.streams if args.streams > 0 else 3, R))
-    ring = StreamRing(n_streams, dev) if n_streams > 1 else None
-
-    def run_step(i):
-        if graphs is not None:
-            graphs[i % R].replay()
-        else:
-            enqueue(sets[i % R])
-
-    def step(i):
-        if ring is not None:
-            ring.submit(lambda: run_step(i))
-        else:
-            run_step(i)
-        return 3
-
-    if ring is not None:
-        ring.fork()
-    for i in range(args.warmup):
-        step(i)
-    if ring is not None:
-        ring.join()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
-    if rank == 0:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    ev0.record()
-    if ring is not None:
-        ring.fork()
-    for i in range(args.steps):
-        launches += step(args.warmup + i)
-    if ring is not None:
-        ring.join()
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = ev0.elapsed_time(ev1)
-    chk = int(sets[(args.warmup + args.steps - 1) % R]["out"][:2].double().sum().item() * 1e3)
-    stats = sharding.gather_stats(elapsed_ms, B * args.steps, chk, dev)
-    value = sharding.aggregate_throughput(stats)
-    worst_ms = max(s[0] for s in stats)
-    # the resample kernel alone: back-to-back launches with the maps of the last step
-    _, _, _, mx, my = ops.warp_from_pdfs(sets[0]["img"], sets[0]["px"], sets[0]["py"], alpha=0.1, layout="chw",
-                                         out=sets[0]["out"], return_aux=True)
-    kreps = max(10, min(args.steps, 30))
-    for i in range(3):
-        ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(kreps):
-        ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
-    e1.record()
-    torch.cuda.synchronize()
-    kms = e0.elapsed_time(e1) / kreps
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return 0
-    peak, peak_src = measured_peak()
-    by = B * C * side * side * 4 * 2
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (PDF/CDF rows), f64 (inversion), f32 (resample)",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "images_per_step_per_gpu": B,
-                       "l2_policy": f"inputs rotate over {R} resident buffer sets; one batch is {by / 1e6:.0f} MB in+out > 126 MB L2",
-                       "parallelism": f"images sharded by index over {world} GPU(s), no data-path collective",
-                       "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
-                                 (f"; consecutive steps round-robin over {n_streams} CUDA streams" if ring is not None else "")},
-            "clocks": clocks, "e2e": None, "gpu_launches": launches * world,
-            "roofline": {"bound": "hbm", "kernel": "remap_f32_rows_kernel", "achieved": by / kms / 1e6, "peak": peak,
-                         "unit": "GB/s", "frac": by / kms / 1e6 / peak, "traffic": ncu_traffic("remap_f32_rows_kernel", "c5"),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": by, "kernel_ms": kms},
-            "cpu_baseline": None, "per_rank_ms": [s[0] for s in stats]}
-    print(json.dumps(line), flush=True)
-    return 0
-
-
-def run_gpu(args, rank, local_rank, world):
-    wl = WORKLOADS[args.workload]
-    if wl.get("ragged"):
-        return run_gpu_ragged(args, rank, local_rank, world)
-    if wl.get("pdf"):
-        return run_gpu_pdf(args, rank, local_rank, world)
-    cpu_info = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # before CUDA is initialised (the pool forks)
-        cpu_info, _ = cpu_arm(args.workload, steps=3, warmup=1, budget_s=20.0, full_steps=False)
-
-    import torch
-    import torch.distributed as dist
-
-    from attwarp_b200 import ops, sharding
-    from attwarp_b200.batched import HostBatchPipeline, StreamRing
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        init_nccl(dev)
-
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    wl = WORKLOADS[wl_key]
     B, side, C, grid = wl["B"], wl["side"], wl["C"], wl["grid"]
     L, Hh, T = wl["L"], wl["Hh"], wl["grid"] ** 2
     R = args.rotate if args.rotate > 0 else (8 if wl["has_attention"] else 4)
-    gen = torch.Generator(device=dev).manual_seed(1235 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1235 + rank + (0 if wl["has_attention"] else 7919))
     sets = []
     for _ in range(R):
         s = {}
@@ -565,8 +462,6 @@ def run_gpu(args, rank, local_rank, world):
         s["aux"] = (torch.empty(B, T, device=dev), torch.empty(B, side, device=dev),
                     torch.empty(B, side, device=dev))
         sets.append(s)
-
-    n_steps_total = args.warmup + args.steps
     side_hw = (side, side)
 
     def enqueue(s, evs=None):
@@ -606,65 +501,44 @@ def run_gpu(args, rank, local_rank, world):
             run_step(i)
         return launches_per_step
 
-    if ring is not None:
-        ring.fork()
+    fork = ring.fork if ring is not None else None
+    join = ring.join if ring is not None else None
+    if fork:
+        fork()
     for i in range(args.warmup):
         step(i)
-    if ring is not None:
-        ring.join()
+    if join:
+        join()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank, _gpu_uuid(local_rank))
-    if rank == 0:
+    sampler = ClockSampler(ctx.local_rank, _gpu_uuid(ctx.local_rank))
+    if rank == 0 and with_clocks:
         sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    ev0.record()
-    if ring is not None:
-        ring.fork()                               # every ring stream starts after ev0 ...
-    for i in range(args.steps):
-        launches += step(args.warmup + i)
-    if ring is not None:
-        ring.join()                               # ... and ev1 waits for all of them
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms, launches = timed_steps(ctx, step, args.steps, args.warmup, fork, join)
+    # the same steps again, for >= 120 ms: the contract's K steps last a couple of milliseconds, too short for more
+    # than one NVML clock sample; this region reports the sustained rate and gives the sampler its samples
+    sus_steps = int(min(max(args.steps, 0.12e3 / max(elapsed_ms / args.steps, 1e-3)), 4000))
+    sus_ms, _ = timed_steps(ctx, step, sus_steps, args.warmup + args.steps, fork, join)
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
 
-    chk = sharding.checksum64(sets[(n_steps_total - 1) % R]["out"][:8])
+    n_done = args.warmup + args.steps + sus_steps
+    chk = sharding.checksum64(sets[(n_done - 1) % R]["out"][:8])
     stats = sharding.gather_stats(elapsed_ms, B * args.steps, chk, dev)
+    sus_stats = sharding.gather_stats(sus_ms, B * sus_steps, 0, dev)
     value = sharding.aggregate_throughput(stats)
     worst_ms = max(s[0] for s in stats)
 
+    # single-stream figure (one batch at a time: nothing of another step to overlap with)
+    one_ms, _ = timed_steps(ctx, lambda i: (run_step(i), launches_per_step)[1], max(args.steps, 20), 0)
+    one_stats = sharding.gather_stats(one_ms, B * max(args.steps, 20), 0, dev)
+
     # ---- per-kernel durations, outside the timed region ---------------------------------------------
-    # (a) stage breakdown of the fused call: CUDA events the library records between its kernels;
-    # (b) the resample kernel alone, launched back to back over the rotating sets (the launch of
-    #     kernel n+1 overlaps kernel n, so events around the whole run / N is the kernel duration).
-    peak, peak_src = measured_peak()
+    # each kernel alone, launched back to back over the rotating sets (the launch of kernel n+1 overlaps
+    # kernel n, so events around the whole run / N is the kernel duration, fill and drain included)
     kernels = {}
     kreps = max(10, min(args.steps, 30))
-    if wl["has_attention"]:
-        stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(kreps)]
-        for evs in stage_ev:
-            for e in evs:
-                e.record()                              # materialise the cudaEvent_t handles
-        for i in range(kreps):
-            enqueue(sets[i % R], stage_ev[i])
-        torch.cuda.synchronize()
-        names = ["aggregate_rows_tma_kernel", "maps_from_tokens_kernel", "remap_u8_stream_kernel"]
-        byts = [B * (L * Hh * T * 2 + T * 4), B * (T * 4 + 2 * side * 4), B * side * side * C * 2]
-        for k, (nm, by) in enumerate(zip(names, byts)):
-            ms = sum(evs[k].elapsed_time(evs[k + 1]) for evs in stage_ev) / kreps
-            kernels[nm] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
-                           "frac": by / ms / 1e6 / peak, "how": "library stage events inside the fused call"}
+
     def back_to_back(fn):
-        """Average duration of one launch of a kernel launched kreps times in a row over the rotating
-        sets (the launch of kernel n+1 overlaps kernel n, so there is no launch gap in the figure)."""
         for i in range(3):
             fn(sets[i % R])
         torch.cuda.synchronize()
@@ -677,76 +551,363 @@ def run_gpu(args, rank, local_rank, world):
         return e0.elapsed_time(e1) / kreps
 
     how = f"{kreps} back-to-back launches over the rotating sets"
-    ms = back_to_back(lambda s: ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"]))
-    by = B * side * side * C * 2
-    kernels["remap_u8_stream_kernel"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
-                                        "frac": by / ms / 1e6 / peak, "how": how}
+
+    def add(name, ms, by, extra=None):
+        kernels[name] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
+                         "frac": by / ms / 1e6 / ctx.peak, "how": how}
+        if extra:
+            kernels[name].update(extra)
+
     if wl["has_attention"]:
-        # stage 1 alone (the stage events above include the gap between the event and the kernel start)
-        k1 = kernels["aggregate_rows_tma_kernel"]
-        ms = back_to_back(lambda s: ops.aggregate_attention(s["attn"], out=s["aux"][0]))
-        by = k1["algorithmic_bytes"]
-        kernels["aggregate_rows_tma_kernel"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
-                                                "frac": by / ms / 1e6 / peak, "how": how,
-                                                "ms_between_stage_events": k1["ms"]}
-    dom = max(kernels, key=lambda k: kernels[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, args.workload),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                "kernel_ms": kernels[dom]["ms"]}
+        add("aggregate_rows_tma_kernel", back_to_back(lambda s: ops.aggregate_attention(s["attn"], out=s["aux"][0])),
+            B * (L * Hh * T * 2 + T * 4), {"note": "includes its 4 us finalize launch"})
+        tokmap = lambda s: s["aux"][0].view(B, grid, grid)          # noqa: E731
+    else:
+        tokmap = lambda s: s["tok"]                                  # noqa: E731
+    add("maps_from_tokens_kernel",
+        back_to_back(lambda s: ops.maps_from_tokens(tokmap(s), side_hw, None, "identity", out=(s["aux"][1], s["aux"][2]))),
+        B * (T * 4 + 2 * side * 4))
+    add("remap_u8_stream_kernel",
+        back_to_back(lambda s: ops.remap_bilinear(s["img"], s["aux"][1], s["aux"][2], "hwc", out=s["out"])),
+        B * side * side * C * 2)
+    step_bytes = sum(k["algorithmic_bytes"] for k in kernels.values())
+    roofline = pick_roofline(ctx, kernels, wl_key, step_bytes)
+    roofline["whole_step"] = {"algorithmic_bytes": step_bytes,
+                              "achieved": step_bytes / (worst_ms / args.steps) / 1e6,
+                              "frac": step_bytes / (worst_ms / args.steps) / 1e6 / ctx.peak,
+                              "note": f"all kernels of a step, {n_streams} steps in flight"}
 
     # ---- e2e: pinned host buffers -> H2D -> kernels -> D2H, per step -----------------------------
     e2e = None
-    if wl["has_attention"] and not args.no_e2e:
-        h_attn = torch.empty(B, L, Hh, T, dtype=torch.bfloat16).pin_memory()
+    if not args.no_e2e:
         h_img = torch.empty(B, side, side, C, dtype=torch.uint8).pin_memory()
         h_out = torch.empty(B, side, side, C, dtype=torch.uint8).pin_memory()
-        h_attn.copy_(sets[0]["attn"])
         h_img.copy_(sets[0]["img"])
-        pipe = HostBatchPipeline(args.e2e_chunk, L, Hh, (grid, grid), (side, side, C), device=dev)
-        for _ in range(2):
-            pipe.run(h_attn, h_img, h_out)
-        pipe.sync()
+        chunk = args.e2e_chunk if args.e2e_chunk > 0 else (64 if wl["has_attention"] else 16)
+        if wl["has_attention"]:
+            h_in = torch.empty(B, L, Hh, T, dtype=torch.bfloat16).pin_memory()
+            h_in.copy_(sets[0]["attn"])
+            pipe = HostBatchPipeline(chunk, L, Hh, (grid, grid), (side, side, C), device=dev)
+            api = "attwarp_b200.batched.HostBatchPipeline.run (pinned host in/out)"
+        else:
+            h_in = torch.empty(B, grid, grid, dtype=torch.float32).pin_memory()
+            h_in.copy_(sets[0]["tok"])
+            pipe = HostTokenPipeline(chunk, (grid, grid), (side, side, C), device=dev)
+            api = "attwarp_b200.batched.HostTokenPipeline.run (pinned host in/out)"
+        probe = HostCopyProbe(pipe)
         ke = max(3, min(args.steps, 10))
+
+        def time_e2e(fn):
+            for _ in range(2):
+                fn()
+            ms, _ = timed_steps(ctx, lambda i: (fn(), 0)[1], ke, 0)
+            return ms
+
+        ems = time_e2e(lambda: pipe.run(h_in, h_img, h_out))
+        est = sharding.gather_stats(ems, B * ke, int(h_out[:4].to(torch.int64).sum()), dev)
+        cms = time_e2e(lambda: probe.run((h_in, h_img), h_out))
+        cst = sharding.gather_stats(cms, B * ke, 0, dev)
+        e2e_ms, copy_ms = max(s[0] for s in est) / ke, max(s[0] for s in cst) / ke
+        e2e = {"value": sharding.aggregate_throughput(est), "unit": UNIT,
+               "h2d_bytes_per_step": h_in.numel() * h_in.element_size() + h_img.numel(),
+               "d2h_bytes_per_step": h_out.numel(), "steps": ke, "chunk": chunk,
+               "ms_per_step": e2e_ms, "api": api,
+               "copy_only_ms_per_step": copy_ms, "frac_of_copy_ceiling": copy_ms / e2e_ms,
+               "copy_only_note": "the same chunks, bytes, streams and pinned buffers without the kernels, all ranks "
+                                 "copying at the same time: what PCIe + host memory deliver on this box at this N",
+               "pcie_gbs_per_gpu": {"h2d": (h_in.numel() * h_in.element_size() + h_img.numel()) / e2e_ms / 1e6,
+                                    "d2h": h_out.numel() / e2e_ms / 1e6}}
+        if wl["has_attention"]:
+            # second variant, labelled: in the real pipeline the attention tensor is born on the GPU (it is the
+            # output of the model's attention layer); only the images cross PCIe
+            d_attn = sets[0]["attn"]
+            tpipe = HostBatchPipeline(chunk, L, Hh, (grid, grid), (side, side, C), device=dev)
+
+            def run_resident():
+                caller = torch.cuda.current_stream(dev)
+                for s_ in tpipe.streams:
+                    s_.wait_stream(caller)
+                k = 0
+                for lo in range(0, B, chunk):
+                    hi = min(lo + chunk, B)
+                    slot, st = tpipe.slots[k % 2], tpipe.streams[k % 2]
+                    with torch.cuda.stream(st):
+                        slot["img"][:hi - lo].copy_(h_img[lo:hi], non_blocking=True)
+                        ops.warp_from_attention_tokens(d_attn[lo:hi], slot["img"][:hi - lo], (grid, grid), None, "hwc",
+                                                       transform="identity", out=slot["out"][:hi - lo],
+                                                       aux=tuple(a[:hi - lo] for a in slot["aux"]))
+                        h_out[lo:hi].copy_(slot["out"][:hi - lo], non_blocking=True)
+                    k += 1
+                for s_ in tpipe.streams:
+                    caller.wait_stream(s_)
+
+            rms = time_e2e(run_resident)
+            rst = sharding.gather_stats(rms, B * ke, 0, dev)
+            e2e["attention_device_resident"] = {
+                "value": sharding.aggregate_throughput(rst), "unit": UNIT, "ms_per_step": max(s[0] for s in rst) / ke,
+                "h2d_bytes_per_step": h_img.numel(), "d2h_bytes_per_step": h_out.numel(),
+                "note": "NOT the headline e2e: attention already in HBM (as inside a real generate()), images only over PCIe"}
+            del tpipe
+        del pipe, probe, h_in, h_img, h_out
+
+    res = {"value": value, "ms_per_step": worst_ms / args.steps, "per_rank_ms": [s[0] for s in stats],
+           "launches": launches * world, "kernels": kernels, "roofline": roofline, "e2e": e2e, "clocks": clocks,
+           "sustained": {"steps": sus_steps, "ms_per_step": max(s[0] for s in sus_stats) / sus_steps,
+                         "value": sharding.aggregate_throughput(sus_stats)},
+           "single_stream": {"ms_per_step": max(s[0] for s in one_stats) / max(args.steps, 20),
+                             "value": sharding.aggregate_throughput(one_stats),
+                             "note": "one batch at a time on one stream (no overlap between steps)"},
+           "run": {"rotate": R, "streams": n_streams,
+                   "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
+                             (f"; consecutive steps round-robin over {n_streams} CUDA streams (independent batches: "
+                              "the early stages of one step overlap stage 5 of the previous one)" if ring is not None else "")}}
+    del sets, graphs
+    torch.cuda.empty_cache()
+    return res
+
+
+def c4_image(i, side, C, dev, gen):
+    """Image i of the configs[3] batch: the same bytes whichever rank generates it."""
+    import torch
+    gen.manual_seed(1237 * 1000003 + int(i))
+    return torch.randint(0, 256, (int(side), int(side), C), device=dev, dtype=torch.uint8, generator=gen)
+
+
+def bench_ragged(ctx):
+    """configs[3]: ONE batch of 1024 mixed-resolution images split over the ranks by greedy LPT on
+    pixels in + pixels out (strong scaling, no data-path collective); a step = stages 2-5 over the
+    rank's shard through the ragged entry point (one launch per stage).  After the timed region the per-image
+    checksums of all ranks are merged and compared with an UNSHARDED pass over the whole batch."""
+    import numpy as np
+    import torch
+
+    from attwarp_b200 import multi_gpu, ops, sharding
+
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    wl = WORKLOADS["c4"]
+    B, C, grid = wl["B"], wl["C"], wl["grid"]
+    steps = args.steps if args.c4_steps <= 0 else args.c4_steps
+    sides = np.random.default_rng(1237).integers(224, 2049, size=B)
+    sizes = [(int(s), int(s)) for s in sides]
+    plan = multi_gpu.plan_ragged(sizes, world=world)
+    mine = plan.shards[rank]
+    gen = torch.Generator(device=dev)
+    imgs = [c4_image(i, sides[i], C, dev, gen) for i in mine]
+    outs = [torch.empty_like(t) for t in imgs]
+    tok_all = torch.rand(B, grid, grid, generator=torch.Generator().manual_seed(1237)) ** 3
+    tok_all = (tok_all / tok_all.sum(dim=(1, 2), keepdim=True)).contiguous()
+    tok = tok_all[torch.as_tensor(mine)].to(dev)
+    my_bytes = 2 * sum(t.numel() for t in imgs)
+
+    def step(i):
+        ops.warp_ragged_from_tokens(tok, imgs, outs=outs)
+        return 2
+
+    for i in range(args.warmup):
+        step(i)
+    elapsed_ms, launches = timed_steps(ctx, step, steps, 0)
+    stats = sharding.gather_stats(elapsed_ms, len(mine) * steps, 0, dev)
+    bstats = sharding.gather_stats(elapsed_ms, my_bytes // 1024, 0, dev)
+    value = sharding.aggregate_throughput(stats)
+    worst_ms = max(s[0] for s in stats)
+
+    # ---- sharded == unsharded -------------------------------------------------------------------
+    table = multi_gpu.gather_image_checksums(plan, mine, outs)
+    check = {"images_checked": 0}
+    if rank == 0:
         if world > 1:
-            dist.barrier()
+            del imgs, outs
+            torch.cuda.empty_cache()
+            whole_in = [c4_image(i, sides[i], C, dev, gen) for i in range(B)]
+            whole = ops.warp_ragged_from_tokens(tok_all.to(dev), whole_in)
+            ref = torch.tensor([sharding.checksum64(o) for o in whole], dtype=torch.int64)
+            how = f"rank 0 re-ran the whole batch in one unsharded launch and compared {B} per-image checksums"
+        else:
+            # one rank: compare against the two shards of a 2-way LPT plan run one after the other
+            plan2 = multi_gpu.plan_ragged(sizes, world=2)
+            ref = torch.zeros(B, dtype=torch.int64)
+            for r in range(2):
+                idx = plan2.shards[r]
+                o2 = ops.warp_ragged_from_tokens(tok_all[torch.as_tensor(idx)].to(dev), [imgs[i] for i in idx])
+                for i, o in zip(idx, o2):
+                    ref[i] = sharding.checksum64(o)
+                del o2
+            how = "one rank: its single launch compared with the two shards of a 2-way LPT plan run in turn"
+        same = bool(torch.equal(ref.cpu(), table.cpu()))
+        if not same:
+            bad = (ref.cpu() != table.cpu()).nonzero().flatten().tolist()[:8]
+            raise RuntimeError(f"c4: sharded and unsharded results differ for images {bad}")
+        check = {"images_checked": B, "sharded_equals_unsharded": same, "how": how}
+    ctx.barrier()
+    total_bytes = sum(b[1] for b in bstats) * 1024
+    gbs = total_bytes / (worst_ms / steps) / 1e6 / world
+    loads = plan.load()
+    res = {"value": value, "ms_per_step": worst_ms / steps, "per_rank_ms": [s[0] / steps for s in stats],
+           "steps": steps, "launches": launches * world, "images_per_rank": [len(s) for s in plan.shards],
+           "shard_imbalance": max(loads) / (sum(loads) / world),
+           "roofline": {"bound": "hbm", "kernel": "maps_from_tokens_ragged + remap_u8_stream (whole step, host table "
+                                                   "build included)",
+                        "achieved": gbs, "peak": ctx.peak, "unit": "GB/s", "frac": gbs / ctx.peak, "traffic": None,
+                        "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": total_bytes // world,
+                        "note": "per GPU: the slowest rank's step time over its share of the bytes"},
+           "check": check, "e2e": None,
+           "run": {"launch": "one maps + one resample launch per step over the rank's shard (descriptor table built "
+                             "on the host each step)"}}
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_pdf(ctx):
+    """configs[4]: predicted PDFs feeding the fused CDF + resample path (trainer.py:212-218, 285-289 chain):
+    a step = attwarp_warp_from_pdfs over one batch of 128 float32 NCHW images (three launches)."""
+    import torch
+
+    from attwarp_b200 import ops, sharding
+    from attwarp_b200.batched import StreamRing
+
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    wl = WORKLOADS["c5"]
+    B, C, side, N = wl["B"], wl["C"], wl["side"], wl["grid"]
+    R = args.rotate if args.rotate > 0 else 3
+    gen = torch.Generator(device=dev).manual_seed(1238 + rank)
+    sets = []
+    for _ in range(R):
+        sets.append(dict(px=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
+                         py=torch.softmax(torch.randn(B, N, device=dev, generator=gen) * 1.5, -1),
+                         img=torch.rand(B, C, side, side, device=dev, generator=gen),
+                         out=torch.empty(B, C, side, side, device=dev)))
+
+    def enqueue(s):
+        ops.warp_from_pdfs(s["img"], s["px"], s["py"], alpha=0.1, layout="chw", out=s["out"])
+
+    graphs = None if args.no_graph else [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
+    n_streams = max(1, min(args.streams if args.streams > 0 else 3, R))
+    ring = StreamRing(n_streams, dev) if n_streams > 1 else None
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            enqueue(sets[i % R])
+
+    def step(i):
+        if ring is not None:
+            ring.submit(lambda: run_step(i))
+        else:
+            run_step(i)
+        return 3
+
+    fork = ring.fork if ring is not None else None
+    join = ring.join if ring is not None else None
+    if fork:
+        fork()
+    for i in range(args.warmup):
+        step(i)
+    if join:
+        join()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.local_rank, _gpu_uuid(ctx.local_rank))
+    if rank == 0:
+        sampler.start()
+    elapsed_ms, launches = timed_steps(ctx, step, args.steps, args.warmup, fork, join)
+    sus_steps = int(min(max(args.steps, 0.12e3 / max(elapsed_ms / args.steps, 1e-3)), 2000))
+    sus_ms, _ = timed_steps(ctx, step, sus_steps, args.warmup + args.steps, fork, join)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = sharding.gather_stats(elapsed_ms, B * args.steps, 0, dev)
+    sus_stats = sharding.gather_stats(sus_ms, B * sus_steps, 0, dev)
+    value = sharding.aggregate_throughput(stats)
+    worst_ms = max(s[0] for s in stats)
+    by = B * C * side * side * 4 * 2
+    kreps = max(10, min(args.steps, 30))
+
+    def kernel_ms(mx, my):
+        for i in range(3):
+            ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(ke):
-            pipe.run(h_attn, h_img, h_out)
+        for i in range(kreps):
+            ops.remap_bilinear(sets[i % R]["img"], mx, my, "chw", out=sets[i % R]["out"])
         e1.record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ems = e0.elapsed_time(e1)
-        est = sharding.gather_stats(ems, B * ke, int(h_out[:4].to(torch.int64).sum()), dev)
-        e2e = {"value": sharding.aggregate_throughput(est), "unit": UNIT,
-               "h2d_bytes_per_step": h_attn.numel() * 2 + h_img.numel(),
-               "d2h_bytes_per_step": h_out.numel(), "steps": ke, "chunk": args.e2e_chunk,
-               "ms_per_step": max(s[0] for s in est) / ke,
-               "api": "attwarp_b200.batched.HostBatchPipeline.run (pinned host in/out)"}
+        return e0.elapsed_time(e1) / kreps
 
+    # the resample kernel alone on two families of maps: the PDF maps of the step (softmax PDFs mixed with
+    # alpha = 0.1: close to the identity) and the harder maps of rand^3 token grids (strong local scale changes)
+    _, _, _, mx, my = ops.warp_from_pdfs(sets[0]["img"], sets[0]["px"], sets[0]["py"], alpha=0.1, layout="chw",
+                                         out=sets[0]["out"], return_aux=True)
+    tokr = torch.rand(B, N, N, device=dev, generator=gen) ** 3
+    hx, hy = ops.maps_from_tokens((tokr / tokr.sum(dim=(1, 2), keepdim=True)).contiguous(), (side, side))
+    kms, hms = kernel_ms(mx, my), kernel_ms(hx, hy)
+    kernels = {"remap_f32_rows_kernel": {"ms": kms, "algorithmic_bytes": by, "achieved_gbs": by / kms / 1e6,
+                                         "frac": by / kms / 1e6 / ctx.peak, "maps": "PDF maps of the step (alpha = 0.1)"},
+               "remap_f32_rows_kernel@rand3_token_maps": {"ms": hms, "algorithmic_bytes": by,
+                                                          "achieved_gbs": by / hms / 1e6, "frac": by / hms / 1e6 / ctx.peak,
+                                                          "maps": "maps of rand^3 24x24 token grids"}}
+    hard = max(kernels, key=lambda k: kernels[k]["ms"])
+    res = {"value": value, "ms_per_step": worst_ms / args.steps, "per_rank_ms": [s[0] for s in stats],
+           "launches": launches * world, "kernels": kernels, "clocks": clocks, "e2e": None,
+           "sustained": {"steps": sus_steps, "ms_per_step": max(s[0] for s in sus_stats) / sus_steps,
+                         "value": sharding.aggregate_throughput(sus_stats)},
+           "roofline": {"bound": "hbm", "kernel": "remap_f32_rows_kernel", "achieved": kernels[hard]["achieved_gbs"],
+                        "peak": ctx.peak, "unit": "GB/s", "frac": kernels[hard]["frac"],
+                        "traffic": ncu_traffic("remap_f32_rows_kernel", "c5"), "peak_source": ctx.peak_src,
+                        "algorithmic_bytes_per_launch": by, "kernel_ms": kernels[hard]["ms"],
+                        "selection": "the slower of the two map families (" + kernels[hard]["maps"] + ")"},
+           "run": {"rotate": R, "streams": n_streams,
+                   "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
+                             (f"; consecutive steps round-robin over {n_streams} CUDA streams" if ring is not None else "")}}
+    del sets, graphs
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu(args, rank, local_rank, world):
+    head_key = "c2" if args.workload == "all" else args.workload
+    cpu_info = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not WORKLOADS[head_key].get("ragged") \
+            and not WORKLOADS[head_key].get("pdf"):
+        # before CUDA is initialised (the pool forks)
+        cpu_info, _ = cpu_arm(head_key, steps=3, warmup=1, budget_s=20.0, rows=True)
+
+    import torch.distributed as dist
+
+    ctx = Ctx(args, rank, local_rank, world)
+    wl = WORKLOADS[head_key]
+    if wl.get("ragged"):
+        head = bench_ragged(ctx)
+    elif wl.get("pdf"):
+        head = bench_pdf(ctx)
+    else:
+        head = bench_uniform(ctx, head_key)
+    extra = {}
+    if args.workload == "all":
+        for key in ("c3", "c4"):
+            r = bench_uniform(ctx, key, with_clocks=False) if key == "c3" else bench_ragged(ctx)
+            entry = {"metric": METRIC, "unit": UNIT, "value": r["value"], "ms_per_step": r["ms_per_step"],
+                     "scaling": "strong" if key == "c4" else "weak", "dtype": DTYPES[key],
+                     "config": workload_config(key, world), "roofline": r["roofline"], "e2e": r["e2e"],
+                     "per_rank_ms": r["per_rank_ms"], "gpu_launches": r["launches"], "run": r["run"]}
+            for k in ("kernels", "sustained", "single_stream", "images_per_rank", "shard_imbalance", "check", "steps"):
+                if k in r:
+                    entry[k] = r[k]
+            extra[key] = entry
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16->fp32 (stage 1), f64 (stages 2-4), u8 fixed-point (stage 5)",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "images_per_step_per_gpu": B,
-                       "l2_policy": f"inputs rotate over {R} resident buffer sets; one batch "
-                                    f"(attention+images) is {sum(t.numel() * t.element_size() for t in sets[0].values() if hasattr(t, 'numel')) / 1e6:.0f} MB > 126 MB L2",
-                       "parallelism": f"images sharded by index over {world} GPU(s), no data-path collective",
-                       "transform": "identity",
-                       "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
-                                 (f"; consecutive steps round-robin over {n_streams} CUDA streams (independent batches: "
-                                  "the early stages of one step overlap stage 5 of the previous one)" if ring is not None else "")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_info,
-            "per_rank_ms": [s[0] for s in stats]}
+    line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world,
+            "steps": head.get("steps", args.steps), "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong" if wl.get("ragged") else "weak", "vs_baseline": None,
+            "dtype": DTYPES[head_key], "data": "synthetic", "config": workload_config(head_key, world),
+            "run": head["run"], "clocks": head.get("clocks"), "e2e": head["e2e"], "gpu_launches": head["launches"],
+            "roofline": head["roofline"], "cpu_baseline": cpu_info, "per_rank_ms": head["per_rank_ms"]}
+    for k in ("kernels", "sustained", "single_stream", "images_per_rank", "shard_imbalance", "check"):
+        if k in head:
+            line[k] = head[k]
+    if extra:
+        line["workloads"] = extra
     print(json.dumps(line), flush=True)
     return 0
 
@@ -754,19 +915,24 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="default 200 (c4: 10)")
+    ap.add_argument("--steps", type=int, default=None, help="default 200 (a single c4 run: 10)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all"],
+                    help="all (default): c2 is the headline line, c3 (1344^2) and c4 (mixed resolutions) ride in "
+                         "`workloads`; or one workload alone")
     ap.add_argument("--rotate", type=int, default=0, help="resident input buffer sets to rotate over (default 8 with attention, else 4)")
     ap.add_argument("--streams", type=int, default=0, help="CUDA streams consecutive steps alternate over (default 4 with attention, else 3)")
-    ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="images per host-pipeline chunk (default 64 at 336^2, 16 at 1344^2)")
+    ap.add_argument("--c4-steps", type=int, default=0, help="steps of the c4 workload (default: min(--steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of by graph replay")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 10 if args.workload == "c4" else 200
+    if args.c4_steps <= 0:
+        args.c4_steps = min(args.steps, 10)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     # stdout carries the ONE JSON line and nothing else: NCCL's own logging (its version banner, NCCL_DEBUG

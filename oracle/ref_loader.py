@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference from ``/root/reference`` (build container only).
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box, so this module is
-used only by ``tests/golden/make_golden.py`` (fixture generation) and by CPU tests that are
-skipped when the tree is absent.  Nothing is copied: the reference files are imported from where
+TEST / BENCH INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box; there the module
+falls back to ``baseline/_ref/`` (the same files, placed by ``oracle/make_ref.py``).  Used by the
+``tests/golden/make_golden*.py`` fixture generators, by CPU tests that are skipped when no tree is
+present, and by the CPU arm of ``bench.py`` (``oracle/cpu_baseline.py``).  Nothing is copied: the reference files are imported from where
 they lie, after stubbing the packages they import at module scope but which are not installed
 (``matplotlib``, ``llava``) -- SURVEY.md Appendix A.
 """
@@ -13,7 +14,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ATTWARP_REFERENCE_ROOT", "/root/reference")
+_TRAVEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _pick_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copy of the hot-path files that
+    ``oracle/make_ref.py`` placed under the git-ignored ``baseline/_ref/``."""
+    env = os.environ.get("ATTWARP_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _TRAVEL):
+        if os.path.isfile(os.path.join(cand, "Attention Guided Warping", "new_method.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 _AGW = os.path.join(REF_ROOT, "Attention Guided Warping")
 _MNFD = os.path.join(REF_ROOT, "model", "marginalnet_full_dataset")
 

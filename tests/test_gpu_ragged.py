@@ -120,3 +120,28 @@ def test_ragged_c4_nonsquare_resized():
         mx, my = ops.maps_from_tokens(dev(toks[i:i + 1]), imgs[i].shape[:2], out_sizes[i])
         one = ops.remap_bilinear(d_imgs[i][None], mx, my, "hwc")[0]
         assert torch.equal(one, outs[i])
+
+
+def test_sharded_equals_unsharded_ragged():
+    """multi_gpu.warp_ragged_sharded: the shards of a 2-, 3- and 8-way LPT plan (run one after the other on this
+    GPU, as the ranks of a box would run them side by side) produce, image by image, exactly the bytes of the
+    unsharded launch -- the per-image checksum table the multi-GPU bench gathers must not depend on the split."""
+    need_gpu()
+    from attwarp_b200 import multi_gpu, ops, sharding
+    rng = np.random.default_rng(99)
+    n = 20
+    sizes = [(int(h), int(w)) for h, w in rng.integers(64, 700, (n, 2))]
+    out_sizes = [(int(h), int(w)) for h, w in rng.integers(64, 700, (n, 2))]
+    imgs = [dev(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in sizes]
+    toks = dev(_tokens(n, 24, seed=99))
+    whole = ops.warp_ragged_from_tokens(toks, imgs, out_sizes)
+    ref = [sharding.checksum64(o) for o in whole]
+    for world in (2, 3, 8):
+        plan = multi_gpu.plan_ragged(sizes, out_sizes, world=world)
+        table = [None] * n
+        for r in range(world):
+            idx, outs = multi_gpu.warp_ragged_sharded(plan, toks, lambda i: imgs[i], rank=r)
+            for i, o in zip(idx, outs):
+                assert torch.equal(o, whole[i])
+                table[i] = sharding.checksum64(o)
+        assert table == ref
