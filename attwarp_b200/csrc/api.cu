@@ -358,11 +358,14 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
         return ATTWARP_OK;
     }
     // the strip plan of stage 5 is part of the table both kernels read: plan + upload, maps, resample
-    rc = launch_remap_u8_stream_ragged_prepare(host.data(), n, C, dev_table, st);
+    const bool quad = C == 3 && remap_quad_enabled();
+    rc = quad ? launch_remap_u8_quad_ragged_prepare(host.data(), n, dev_table, st)
+              : launch_remap_u8_stream_ragged_prepare(host.data(), n, C, dev_table, st);
     if (rc != ATTWARP_OK) return rc;
     rc = launch_maps_from_tokens_ragged(tok, n, gh, gw, dev_table, max_h, max_w, *tp, nullptr, st);
     if (rc != ATTWARP_OK) return rc;
-    return launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
+    return quad ? launch_remap_u8_quad_ragged_run(host.data(), n, dev_table, st)
+                : launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
 }
 
 static int warp_image_host_impl(const void* image_host, int img_dtype, int C, int H, int W,

@@ -77,6 +77,13 @@ int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, cons
 int launch_remap_u8_stream_ragged_prepare(RaggedImage* host_table, int n, int C, RaggedImage* dev_table, cudaStream_t st);
 int launch_remap_u8_stream_ragged_run(const RaggedImage* host_table, int n, int C, const RaggedImage* dev_table, cudaStream_t st);
 
+// the same for 3-channel images through remap_quad.cu (four adjacent pixels per thread)
+bool remap_quad_enabled();
+int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, int Ho, int Wo, const float* map_x,
+                         const float* map_y, cudaStream_t st);
+int launch_remap_u8_quad_ragged_prepare(RaggedImage* host_table, int n, RaggedImage* dev_table, cudaStream_t st);
+int launch_remap_u8_quad_ragged_run(const RaggedImage* host_table, int n, const RaggedImage* dev_table, cudaStream_t st);
+
 #if defined(__CUDACC__)
 // ---- warp / block reductions -----------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -17,6 +17,7 @@ from attwarp_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--dbg", action="store_true")
 ap.add_argument("--reps", type=int, default=30)
+ap.add_argument("--only", default="")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(0)
@@ -33,6 +34,8 @@ def maps(B, side, grid, kind):
 
 
 def run(name, B, side, grid, kind, layout="hwc", C=3, R=4):
+    if args.only and not name.strip().startswith(args.only):
+        return
     shape = (B, side, side, C) if layout == "hwc" else (B, C, side, side)
     imgs = [torch.randint(0, 256, shape, device=dev, dtype=torch.uint8, generator=gen) for _ in range(R)]
     outs = [torch.empty_like(i) for i in imgs]
