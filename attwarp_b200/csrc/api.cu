@@ -300,7 +300,8 @@ int attwarp_warp_from_pdfs(const float* px, const float* py, int B, int Nx, int 
 
 // ---------------------------------------------------------------------------------------------
 // Ragged batch: descriptor table (n + 1 entries) followed by the map rows of every image.
-static size_t ragged_table_bytes(int n) { return align_up(sizeof(RaggedImage) * (size_t)(n + 1), 256); }
+// (n + 1 entries in batch order, then n + kRaggedClasses entries grouped by width class for the stage-5 launches)
+static size_t ragged_table_bytes(int n) { return align_up(sizeof(RaggedImage) * (size_t)(2 * n + 1 + kRaggedClasses), 256); }
 
 size_t attwarp_ragged_workspace_bytes(const attwarp_ragged_image* images, int n) {
     if (images == nullptr || n <= 0) return 0;
@@ -359,12 +360,14 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
     }
     // the strip plan of stage 5 is part of the table both kernels read: plan + upload, maps, resample
     const bool quad = C == 3 && remap_quad_enabled();
-    rc = quad ? launch_remap_u8_quad_ragged_prepare(host.data(), n, dev_table, st)
+    RaggedQuadPlan plan;
+    RaggedImage* dev_sorted = dev_table + (n + 1);
+    rc = quad ? launch_remap_u8_quad_ragged_prepare(host.data(), n, dev_table, dev_sorted, &plan, st)
               : launch_remap_u8_stream_ragged_prepare(host.data(), n, C, dev_table, st);
     if (rc != ATTWARP_OK) return rc;
     rc = launch_maps_from_tokens_ragged(tok, n, gh, gw, dev_table, max_h, max_w, *tp, nullptr, st);
     if (rc != ATTWARP_OK) return rc;
-    return quad ? launch_remap_u8_quad_ragged_run(host.data(), n, dev_table, st)
+    return quad ? launch_remap_u8_quad_ragged_run(plan, dev_sorted, st)
                 : launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
 }
 
@@ -523,6 +526,41 @@ int attwarp_pool_attention(const float* A, const unsigned char* sqrt_mask, int B
     AW_REQUIRE(B > 0 && H > 0 && W > 0 && gh > 0 && gw > 0, "pool_attention: sizes must be positive");
     AW_REQUIRE(B <= 65535, "pool_attention: B=%d exceeds 65535", B);
     return launch_adaptive_avg_pool2d(A, sqrt_mask, B, H, W, gh, gw, out, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t attwarp_pdf_l1_loss_workspace_bytes(int B) { return B > 0 ? sizeof(double) * 2 * (size_t)B + 16 : 0; }
+
+static int check_pdf_loss_args(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny,
+                               int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy,
+                               int W, int H) {
+    AW_REQUIRE(px && py && gx && gy && Mx && My && Mgx && Mgy, "pdf_l1_loss: NULL pointer");
+    AW_REQUIRE(B > 0 && Nx > 0 && Ny > 0 && Ngx > 0 && Ngy > 0 && W > 0 && H > 0, "pdf_l1_loss: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "pdf_l1_loss: B=%d exceeds 65535", B);
+    return ATTWARP_OK;
+}
+
+int attwarp_pdf_l1_loss(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny,
+                        int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy, int W,
+                        int H, void* workspace, size_t workspace_bytes, float* loss, void* stream) {
+    int rc = check_pdf_loss_args(px, py, gx, gy, B, Nx, Ny, Ngx, Ngy, Mx, My, Mgx, Mgy, W, H);
+    if (rc != ATTWARP_OK) return rc;
+    AW_REQUIRE(loss, "pdf_l1_loss: NULL pointer");
+    if (workspace == nullptr || workspace_bytes < attwarp_pdf_l1_loss_workspace_bytes(B))
+        return fail(ATTWARP_ERR_WORKSPACE, "pdf_l1_loss: workspace too small");
+    return launch_pdf_l1_loss(px, py, gx, gy, B, Nx, Ny, Ngx, Ngy, Mx, My, Mgx, Mgy, W, H, workspace, loss,
+                              as_stream(stream));
+}
+
+int attwarp_pdf_l1_loss_backward(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx,
+                                 int Ny, int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx,
+                                 const float* Mgy, int W, int H, const float* upstream, float* grad_px, float* grad_py,
+                                 void* stream) {
+    int rc = check_pdf_loss_args(px, py, gx, gy, B, Nx, Ny, Ngx, Ngy, Mx, My, Mgx, Mgy, W, H);
+    if (rc != ATTWARP_OK) return rc;
+    AW_REQUIRE(upstream && grad_px && grad_py, "pdf_l1_loss_backward: NULL pointer");
+    return launch_pdf_l1_loss_backward(px, py, gx, gy, B, Nx, Ny, Ngx, Ngy, Mx, My, Mgx, Mgy, W, H, upstream, grad_px,
+                                       grad_py, as_stream(stream));
 }
 
 }  // extern "C"

@@ -77,12 +77,27 @@ int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, cons
 int launch_remap_u8_stream_ragged_prepare(RaggedImage* host_table, int n, int C, RaggedImage* dev_table, cudaStream_t st);
 int launch_remap_u8_stream_ragged_run(const RaggedImage* host_table, int n, int C, const RaggedImage* dev_table, cudaStream_t st);
 
+// fused image-resolution PDF-L1 loss (pdf_loss.cu); workspace: 2 B doubles + a zeroed 32-bit counter
+int launch_pdf_l1_loss(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny, int Ngx,
+                       int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy, int W, int H,
+                       void* workspace, float* loss, cudaStream_t st);
+int launch_pdf_l1_loss_backward(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny,
+                                int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy,
+                                int W, int H, const float* upstream, float* dpx, float* dpy, cudaStream_t st);
 // the same for 3-channel images through remap_quad.cu (four adjacent pixels per thread)
 bool remap_quad_enabled();
 int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, int Ho, int Wo, const float* map_x,
                          const float* map_y, cudaStream_t st);
-int launch_remap_u8_quad_ragged_prepare(RaggedImage* host_table, int n, RaggedImage* dev_table, cudaStream_t st);
-int launch_remap_u8_quad_ragged_run(const RaggedImage* host_table, int n, const RaggedImage* dev_table, cudaStream_t st);
+// ragged: images grouped into width classes (one launch each); dev_main holds n + 1 entries in batch order,
+// dev_sorted n + kRaggedClasses entries grouped by class
+constexpr int kRaggedClasses = 3;
+struct RaggedQuadPlan {
+    int count[kRaggedClasses], offset[kRaggedClasses], total_units[kRaggedClasses], max_strip[kRaggedClasses],
+        geo[kRaggedClasses];
+};
+int launch_remap_u8_quad_ragged_prepare(RaggedImage* host_table, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
+                                        RaggedQuadPlan* plan, cudaStream_t st);
+int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImage* dev_sorted, cudaStream_t st);
 
 #if defined(__CUDACC__)
 // ---- warp / block reductions -----------------------------------------------------------------

@@ -32,6 +32,8 @@
 // total), ragged batches run in one launch over a descriptor table.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "bulk_ptx.cuh"
 #include "common.cuh"
 
@@ -40,8 +42,7 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kStages = 2;            // source-row stages (chunks whose loads are in flight) per CTA
-constexpr int kTiles = 2;             // output tiles per CTA
+constexpr int kMaxRing = 4;            // source-row stages / output tiles per CTA are launch parameters (2 .. 4)
 constexpr int kMaxRows = 16;          // capacity of a chunk table; the rows per chunk are a launch parameter
 constexpr int kRoleThreads = 64;      // producer warp + store warp
 constexpr int kC = 3;
@@ -147,6 +148,28 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "add.u32 o, ez, %38;\n"                                     \
     AWQ_SB1(a, 0, 0) AWQ_SB1(a, 1, 1) AWQ_SB1(a, 2, 2) AWQ_SB1(b, 0, 3) AWQ_SB1(b, 1, 4) AWQ_SB1(b, 2, 5)  \
     AWQ_SB1(c, 0, 6) AWQ_SB1(c, 1, 7) AWQ_SB1(c, 2, 8) AWQ_SB1(d, 0, 9) AWQ_SB1(d, 1, 10) AWQ_SB1(d, 2, 11)
+// LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
+// 128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict whatever the
+// local scale of the map.  The output bytes change hands through a per-warp scratch (two 512-byte buffers used
+// alternately: one bar.warp.sync per row): 4-byte RGBX per pixel in, the 16 bytes of four adjacent pixels out,
+// squeezed to 12 bytes -- the tile stores are the same three aligned words as in the QUAD mapping.
+#define AWQ_EMIT_L                                              \
+    AWQ_VBLEND                                                  \
+    "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
+    "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
+    "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
+    "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
+    "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.v4.b32 {q0, q1, q2, q3}, [sq];\n"                \
+    "xor.b32 sx, sx, 512;\n xor.b32 sq, sq, 512;\n"             \
+    "prmt.b32 q4, q0, q1, 0x4210;\n"                            \
+    "prmt.b32 q5, q1, q2, 0x5421;\n"                            \
+    "prmt.b32 q1, q2, q3, 0x6542;\n"                            \
+    "add.u32 o, ez, %38;\n"                                     \
+    "@pv st.shared.b32 [o], q4;\n"                              \
+    "@pv st.shared.b32 [o+4], q5;\n"                            \
+    "@pv st.shared.b32 [o+8], q1;\n"
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  The entry of the row AFTER the
 // one being emitted is requested before the emit, so the loop-carried compare never waits for a shared-memory load
 // (the entry after the sentinel is read too: still inside the CTA's shared memory, never used)
@@ -165,7 +188,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
     ".reg .pred p, q, pv, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o;\n"                 \
+    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
     ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
     ".reg .b32 ka, kb, kc, kd, ua, ub, uc, ud, sa, sb, sc, sd, ma, mb, mc, md, na, nb, nc, nd;\n" \
@@ -175,7 +198,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     ".reg .b32 va0, va1, va2, vb0, vb1, vb2, vc0, vc1, vc2, vd0, vd1, vd2;\n"   \
     ".reg .b32 q0, q1, q2, q3, q4, q5;\n"
 // operands: %0-%11 E, %12-%23 O (read/write) | %24-%27 window address (a..d) | %28-%31 shift (a..d) |
-//           %32 n_slots | %33-%35 unused weights slot | %36 pitch | %37 rp | %38 ocol | %39 first slot odd |
+//           %32 n_slots | %33, %34 LANE mapping: scratch addresses (write, read) | %35 unused | %36 pitch | %37 rp | %38 ocol | %39 first slot odd |
 //           %40 store predicate | %41-%48 weight words (la, ha, lb, hb, lc, hc, ld, hd)
 #define AWQ_PROLOGUE                                            \
     "mov.b32 Ea0, %0;\n mov.b32 Ea1, %1;\n mov.b32 Ea2, %2;\n mov.b32 Eb0, %3;\n mov.b32 Eb1, %4;\n mov.b32 Eb2, %5;\n" \
@@ -184,6 +207,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 Oc0, %18;\n mov.b32 Oc1, %19;\n mov.b32 Oc2, %20;\n mov.b32 Od0, %21;\n mov.b32 Od1, %22;\n mov.b32 Od2, %23;\n" \
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
+    "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
     "setp.ne.u32 pv, %40, 0;\n"                                 \
     "setp.ne.u32 podd, %39, 0;\n"                               \
     "mov.b32 rp, %37;\n"                                        \
@@ -237,21 +261,25 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
       "+r"(E[8]), "+r"(E[9]), "+r"(E[10]), "+r"(E[11]), "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]),     \
       "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "+r"(O[9]), "+r"(O[10]), "+r"(O[11])      \
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
-      "r"(n_slots), "r"(0), "r"(0), "r"(0), "r"(pitch), "r"(rp), "r"(ocol), "r"(odd_first), "r"(store_ok),  \
+      "r"(n_slots), "r"(sx), "r"(sq), "r"(0), "r"(pitch), "r"(rp), "r"(ocol), "r"(odd_first), "r"(store_ok),  \
       "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3])        \
     : "memory"
 
-// FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).  WORDS: aligned word stores.
-template <bool FIXED, bool WORDS>
+// FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
+// EMIT: 0 = QUAD mapping, aligned word stores; 1 = QUAD mapping, byte stores; 2 = LANE mapping (word stores).
+template <bool FIXED, int EMIT>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
                                            const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
-                                           uint32_t rp, uint32_t ocol, uint32_t odd_first, uint32_t store_ok) {
+                                           uint32_t rp, uint32_t ocol, uint32_t odd_first, uint32_t store_ok,
+                                           uint32_t sx, uint32_t sq) {
     if (FIXED) {
-        if (WORDS) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (EMIT == 0) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        else if (EMIT == 1) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
     } else {
-        if (WORDS) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (EMIT == 0) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        else if (EMIT == 1) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
     }
 }
 
@@ -271,6 +299,9 @@ struct QuadArgs {
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int out_pitch;           // bytes per row of an output tile
     int rows;                // output rows per chunk (<= kMaxRows)
+    int stages, tiles;       // ring depths: source-row stages (chunks whose loads are in flight), output tiles
+    int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
+                             // 1: always QUAD, 2: LANE wherever word stores apply
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
 };
 
@@ -308,8 +339,8 @@ __device__ __forceinline__ View get_view(const QuadArgs& a, int img) {
 
 // Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
 // blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads + 32 store threads.
-// Shared memory: [kStages source arenas][kTiles output tiles][kStages chunk tables][kTiles tile headers][mbarriers].
-// Chunk c lives in source stage c % kStages and output tile c % kTiles.  mbarriers:
+// Shared memory: [stages source arenas][tiles output tiles][stages chunk tables][tiles tile headers][mbarriers].
+// Chunk c lives in source stage c % stages and output tile c % tiles.  mbarriers:
 //   full[s]  producer -> consumers   table written, source rows landed (transaction bytes)
 //   sfree[s] consumers -> producer   every consumer warp is done with the stage's rows and table
 //   odone[o] consumers -> store warp every consumer warp has written its columns of the tile
@@ -318,6 +349,7 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArgs a) {
     const int tid = threadIdx.x;
     const int R = a.rows;
+    const int kStages = a.stages, kTiles = a.tiles;
     const int out_bytes = R * a.out_pitch;
     const int out_off0 = kStages * a.stage_bytes;
     const int tab_off0 = out_off0 + kTiles * out_bytes;
@@ -329,6 +361,9 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const uint32_t odone_s = sfree_s + 8u * kStages;
     const uint32_t ofree_s = odone_s + 8u * kTiles;
     const int n_cons_warps = ((int)blockDim.x - kRoleThreads) >> 5;
+    // LANE-mapping scratch: 1 KB per consumer warp at a 1 KB aligned shared address (the two 512-byte halves are
+    // toggled with xor)
+    const uint32_t scratch_s = (ofree_s + 8u * kTiles + 1023u) & ~1023u;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -583,8 +618,10 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     }
 
     // =============================== consumer warps ==============================================
-    // this thread's output columns inside the strip: 4 tid .. 4 tid + 3
+    // this thread's output columns inside the strip.  QUAD mapping: 4 tid .. 4 tid + 3.  LANE mapping: columns
+    // 32 j + lane of the warp's 128-column block (the STORES are those of the QUAD mapping in both cases).
     const int x0 = tid * 4;
+    const int xw = (tid & ~31) * 4;   // first column of the warp's block
     int wo[4];                        // byte offset of each column's window inside a staged row span
     uint32_t wl[4], wh[4], E[12], O[12];
 #pragma unroll
@@ -592,8 +629,11 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
 #pragma unroll
     for (int j = 0; j < 4; ++j) { wo[j] = 0; wl[j] = wh[j] = 0u; }
     bool warp_live = false;           // some lane of this warp owns a column of the strip
-    uint32_t store_ok = 0u;           // this thread owns at least one column
+    bool lane_map = false;            // this warp runs the LANE mapping in the current strip
+    uint32_t store_ok = 0u;           // this thread stores at least one column (QUAD position)
     const int out_col = x0 * kC;
+    const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
+    const uint32_t sq_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 16);    //          my four adjacent pixels out
 
     int st = 0, ot = 0;               // source stage / output tile of the current chunk
     uint32_t sph = 0u, oph = 1u;      // parities to wait for: stage filled / tile shipped and free
@@ -619,14 +659,37 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             store_ok = x0 < ncols ? 1u : 0u;
             warp_live = __any_sync(0xffffffffu, store_ok != 0u);
             int xb = (int)h1.w;
+            int xb_first = xb;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 // a column past the strip's end keeps the previous column's window and gets zero weights
                 int w0 = 0, w1 = 0;
                 if (x0 + j < ncols) column_taps(__ldg(mx + x0 + j), W, xb, w0, w1);
+                if (j == 0) xb_first = xb;
                 wo[j] = (xb - (int)h1.w) * kC;
                 wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
                 wh[j] = wl[j] << 16;
+            }
+            // QUAD loads are conflict-free only while the lanes' windows stay 3 words apart: when the source column
+            // of some lane's first pixel has drifted two or more pixels from "4 per lane", switch the warp to the
+            // LANE mapping (needs word stores: the scratch round trip ends in the QUAD mapping's aligned stores)
+            lane_map = false;
+            if (warp_live && (flags & kFlagWordStores) && a.map_policy != 1) {
+                const int xb_lane0 = __shfl_sync(0xffffffffu, xb_first, 0);
+                const int dev = store_ok ? abs(xb_first - xb_lane0 - 4 * lane) : 0;
+                lane_map = a.map_policy == 2 || __any_sync(0xffffffffu, dev >= 2);
+            }
+            if (lane_map) {
+                xb = (int)h1.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = xw + 32 * j + lane;
+                    int w0 = 0, w1 = 0;
+                    if (x < ncols) column_taps(__ldg(mx + x), W, xb, w0, w1);
+                    wo[j] = (xb - (int)h1.w) * kC;
+                    wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
+                    wh[j] = wl[j] << 16;
+                }
             }
         }
         if (tid == 0) {                                      // what the store warp needs to ship the tile
@@ -664,6 +727,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             const uint32_t base = smem_s + (uint32_t)(st * a.stage_bytes) + h0.w;    // first byte of slot 0
             const uint32_t odd = (flags & kFlagOddFirst) ? 1u : 0u;
             uint32_t win[4], sh[4];
+            const int emit = lane_map ? 2 : ((flags & kFlagWordStores) ? 0 : 1);
             if (flags & kFlagFixedShift) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -671,13 +735,15 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (flags & kFlagWordStores) sweep_quad<true, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok);
-                else sweep_quad<true, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok);
+                if (emit == 0) sweep_quad<true, 0>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else if (emit == 1) sweep_quad<true, 1>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else sweep_quad<true, 2>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (flags & kFlagWordStores) sweep_quad<false, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok);
-                else sweep_quad<false, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok);
+                if (emit == 0) sweep_quad<false, 0>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else if (emit == 1) sweep_quad<false, 1>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else sweep_quad<false, 2>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
             }
         }
         // publish this warp's part of the tile to the async proxy, then count the warp in
@@ -731,18 +797,27 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
     a.dbg = env_int("ATTWARP_REMAP_DBG", 0);
     a.out_pitch = (cols * kC + 15 + 15) & ~15;              // + the 16-byte phase of the destination
     const int unit_pitch = (((cols + 1) * kC + 45 + 15) & ~15) + 16;      // a slot at unit scale
-    // rows per chunk: as many as the shared memory of 1 / ctas of an SM holds (2 stages of R + 2 slots, 2 tiles of
-    // R rows), at most kMaxRows
-    const int budget = (227 * 1024) / kGeo[G].ctas - 1024 - kStages * kTabBytes - kTiles * 32 - 64 - 256;
-    int R = (budget / 2 - 2 * unit_pitch - 64) / (unit_pitch + a.out_pitch);
+    // ring depths (ATTWARP_QUAD_RING = stages * 10 + tiles, tuning experiments) and rows per chunk: as many as the
+    // shared memory of 1 / ctas of an SM holds (stages of R + 2 slots, tiles of R rows), at most kMaxRows
+    int stages = 2, tiles = 2;
+    {
+        const int ring = env_int("ATTWARP_QUAD_RING", 0);
+        if (ring / 10 >= 2 && ring / 10 <= kMaxRing && ring % 10 >= 2 && ring % 10 <= kMaxRing) { stages = ring / 10; tiles = ring % 10; }
+    }
+    a.stages = stages;
+    a.tiles = tiles;
+    const int budget = (227 * 1024) / kGeo[G].ctas - 1024 - stages * kTabBytes - tiles * 32 - 16 * kMaxRing - 256 -
+                       1024 * (kGeo[G].warps + 1);
+    int R = (budget - stages * (2 * unit_pitch + 64 + 128)) / (stages * unit_pitch + tiles * a.out_pitch);
     R = R > kMaxRows ? kMaxRows : R;
     const int forced = env_int("ATTWARP_QUAD_ROWS", 0);
     if (forced >= 2 && forced <= R) R = forced;
     if (R < 2) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: strips of %d columns do not fit shared memory", cols);
     a.rows = R;
     a.stage_bytes = ((R + 2) * unit_pitch + 64 + 127) & ~127;
-    const size_t smem_bytes = (size_t)kStages * (a.stage_bytes + kTabBytes) + (size_t)kTiles * ((size_t)R * a.out_pitch + 32) +
-                              2 * (kStages + kTiles) * sizeof(uint64_t) + 16;
+    const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + (size_t)tiles * ((size_t)R * a.out_pitch + 32) +
+                              2 * (size_t)(stages + tiles) * sizeof(uint64_t) + 16 + 1024 * (size_t)(kGeo[G].warps + 1);
+    a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     struct Cfg { size_t smem; int dev, occ; };
     static thread_local Cfg c = {0, -1, 0};
     int dev = 0;
@@ -806,44 +881,66 @@ int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, in
     return launch_by_geometry(g, a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
 }
 
-// Ragged batch, step 1: strip plan and cost prefix of host[0..n) (host[n] only carries the total), upload.
-// A tile (one output row of a strip) weighs as many units as it keeps consumer warps busy.
-int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_table, cudaStream_t st) {
-    int max_wo = 0;
-    for (int i = 0; i < n; ++i) max_wo = host[i].Wo > max_wo ? host[i].Wo : max_wo;
-    const int g = pick_geometry(max_wo);
-    int64_t total = 0;
+// Ragged batch.  Images are grouped into width classes, one launch per class with the geometry that fits it
+// (a 300-wide image in a CTA built for 1408 columns would leave eight of its eleven consumer warps idle):
+//   class 0: Wo <= 352 (3 consumer warps per CTA), class 1: Wo <= 704 (6), class 2: wider (11; strips of <= 1408).
+// Step 1: `host` (n + 1 entries, batch order) gets each image's strip plan and is uploaded to dev_main (the maps
+// kernel reads shapes and map pointers from it); a copy grouped by class, every group followed by an entry that
+// carries its unit total, is uploaded to dev_sorted (n + 3 entries).
+constexpr int kClassGeo[kRaggedClasses] = {0, 1, 2};
+inline int width_class(int Wo) { return Wo <= kGeo[kClassGeo[0]].max_cols ? 0 : (Wo <= kGeo[kClassGeo[1]].max_cols ? 1 : 2); }
+
+int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
+                                        RaggedQuadPlan* plan, cudaStream_t st) {
+    static thread_local std::vector<RaggedImage> sorted;
+    sorted.assign((size_t)n + kRaggedClasses, RaggedImage{});
+    *plan = RaggedQuadPlan{};
+    const int forced = env_int("ATTWARP_QUAD_GEO", -1);
+    for (int i = 0; i < n; ++i) plan->count[forced >= 0 ? 2 : width_class(host[i].Wo)]++;
+    int pos = 0;
+    for (int c = 0; c < kRaggedClasses; ++c) {
+        plan->offset[c] = pos;
+        plan->geo[c] = forced >= 0 && forced <= 5 ? forced : kClassGeo[c];
+        pos += plan->count[c] + 1;
+    }
+    int fill[kRaggedClasses] = {0, 0, 0};
+    int64_t total[kRaggedClasses] = {0, 0, 0};
     for (int i = 0; i < n; ++i) {
-        const StripPlan sp = plan_strips(host[i].Wo, kGeo[g].max_cols);
+        const int c = forced >= 0 ? 2 : width_class(host[i].Wo);
+        const StripPlan sp = plan_strips(host[i].Wo, kGeo[plan->geo[c]].max_cols);
         const int cols = host[i].Wo < sp.strip_cols ? host[i].Wo : sp.strip_cols;
         const int units = (cols + 127) / 128;
         if (sp.n_strips > 0xffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: image %d is too wide", i);
         host[i].strips_units = sp.n_strips | (units << 16);
         host[i].strip_cols = sp.strip_cols;
         host[i].n_rowtiles = host[i].Ho;
-        host[i].unit_begin = (int)total;
-        total += (int64_t)sp.n_strips * host[i].n_rowtiles * units;
-        if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
+        host[i].unit_begin = (int)total[c];
+        total[c] += (int64_t)sp.n_strips * host[i].n_rowtiles * units;
+        if (total[c] > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
+        if (cols > plan->max_strip[c]) plan->max_strip[c] = cols;
+        sorted[(size_t)(plan->offset[c] + fill[c]++)] = host[i];
+    }
+    for (int c = 0; c < kRaggedClasses; ++c) {
+        plan->total_units[c] = (int)total[c];
+        sorted[(size_t)(plan->offset[c] + plan->count[c])].unit_begin = (int)total[c];
     }
     host[n] = RaggedImage{};
-    host[n].unit_begin = (int)total;
-    host[n].strip_cols = g;                 // the geometry the plan was made for (read back by `run`)
-    AW_CUDA(cudaMemcpyAsync(dev_table, host, sizeof(RaggedImage) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    AW_CUDA(cudaMemcpyAsync(dev_main, host, sizeof(RaggedImage) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    AW_CUDA(cudaMemcpyAsync(dev_sorted, sorted.data(), sizeof(RaggedImage) * sorted.size(), cudaMemcpyHostToDevice, st));
     return ATTWARP_OK;
 }
-// Step 2: the launch.
-int launch_remap_u8_quad_ragged_run(const RaggedImage* host, int n, const RaggedImage* dev_table, cudaStream_t st) {
-    int max_strip = 0;
-    for (int i = 0; i < n; ++i) {
-        const int cols = host[i].Wo < host[i].strip_cols ? host[i].Wo : host[i].strip_cols;
-        if (cols > max_strip) max_strip = cols;
+// Step 2: one launch per non-empty class.
+int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImage* dev_sorted, cudaStream_t st) {
+    for (int c = 0; c < kRaggedClasses; ++c) {
+        if (plan.count[c] == 0 || plan.total_units[c] == 0) continue;
+        QuadArgs a{};
+        a.imgs = dev_sorted + plan.offset[c];
+        a.n_img = plan.count[c];
+        a.total_units = plan.total_units[c];
+        const int rc = launch_by_geometry(plan.geo[c], a, plan.max_strip[c], st);
+        if (rc != ATTWARP_OK) return rc;
     }
-    QuadArgs a{};
-    a.imgs = dev_table;
-    a.n_img = n;
-    a.total_units = host[n].unit_begin;
-    if (a.total_units == 0) return ATTWARP_OK;
-    return launch_by_geometry(host[n].strip_cols, a, max_strip, st);
+    return ATTWARP_OK;
 }
 
 }  // namespace aw

@@ -415,3 +415,65 @@ def warp_ragged_from_tokens(tok: torch.Tensor, images, out_sizes=None, grid_hw=N
         check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), n, gh, gw, table_p, Cc, C.byref(tp),
                                                   ptr(ws), ws.numel(), current_stream(dev)))
     return outs
+
+
+class RaggedBatch:
+    """A mixed-resolution batch whose buffers stay put across calls (the steady state of a driver that re-uses its
+    image and output buffers): the descriptor table, the output tensors and a private workspace are built ONCE,
+    ``run(tok)`` is a single library call with no per-image Python work (building the table for 1024 images costs
+    more host time than the GPU needs to warp them).
+
+        batch = RaggedBatch(images, out_sizes)        # uint8 HWC device tensors
+        warped = batch.run(tok)                       # tok [n, gh, gw] float32 on the device -> batch.outs
+    """
+
+    def __init__(self, images, out_sizes=None, outs=None):
+        lib = load()
+        n = len(images)
+        assert n > 0
+        require_cuda(*images)
+        self.device = images[0].device
+        self.C = int(images[0].shape[2])
+        self.images = [im.contiguous() for im in images]
+        if out_sizes is None:
+            out_sizes = [(im.shape[0], im.shape[1]) for im in self.images]
+        self.out_sizes = [(int(h), int(w)) for h, w in out_sizes]
+        if outs is None:
+            outs = [torch.empty(ho, wo, self.C, dtype=torch.uint8, device=self.device) for ho, wo in self.out_sizes]
+        self.outs = list(outs)
+        for im, o, (ho, wo) in zip(self.images, self.outs, self.out_sizes):
+            if (im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != self.C or im.device != self.device
+                    or o.dtype != torch.uint8 or tuple(o.shape) != (ho, wo, self.C) or not o.is_contiguous()
+                    or o.device != self.device):
+                raise ValueError("RaggedBatch: images must be uint8 HWC tensors with the same channel count on one "
+                                 "device, outputs contiguous [Ho, Wo, C]")
+        table = np.empty(n, dtype=_RAGGED_DTYPE)
+        table["src"] = [im.data_ptr() for im in self.images]
+        table["dst"] = [o.data_ptr() for o in self.outs]
+        table["H"] = [im.shape[0] for im in self.images]
+        table["W"] = [im.shape[1] for im in self.images]
+        table["Ho"] = [hw[0] for hw in self.out_sizes]
+        table["Wo"] = [hw[1] for hw in self.out_sizes]
+        self._table = table
+        self._table_p = table.ctypes.data_as(C.c_void_p)
+        self.n = n
+        self._ws = torch.empty(max(int(lib.attwarp_ragged_workspace_bytes(self._table_p, n)), 256), dtype=torch.uint8,
+                               device=self.device)
+
+    def run(self, tok: torch.Tensor, grid_hw=None, transform="identity", exp_scale=1.0, exp_divisor=1.0,
+            apply_inverse=False):
+        """Stages 2-5 over the batch, enqueued on the current stream; returns ``self.outs``."""
+        lib = load()
+        if tok.dim() == 3:
+            gh, gw = tok.shape[1], tok.shape[2]
+        else:
+            gh, gw = grid_hw
+        if tok.shape[0] != self.n or tok.device != self.device:
+            raise ValueError(f"RaggedBatch.run: {self.n} token maps on {self.device} expected")
+        if tok.dtype != torch.float32 or not tok.is_contiguous():
+            tok = tok.to(torch.float32).contiguous()
+        tp = _tp(transform, exp_scale, exp_divisor, apply_inverse)
+        with torch.cuda.device(self.device):
+            check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), self.n, gh, gw, self._table_p, self.C, C.byref(tp),
+                                                      ptr(self._ws), self._ws.numel(), current_stream(self.device)))
+        return self.outs

@@ -272,6 +272,25 @@ int attwarp_mix_with_uniform_backward(const float* grad_out, int B, int N, float
                                       void* stream);
 int attwarp_upsample_right_inverse_backward(const float* grad_x, const float* M, int B, int L_out, int L_in,
                                             float* grad_y, void* stream);
+/* The image-resolution PDF-L1 loss MarginalNet is trained with, forward and backward in one launch each
+ * (mnfd/trainer.py:217-250):
+ *     p_img = upsample_pdf_right_inverse(p_s, L).clamp_min(0);  p_img /= p_img.sum(1).clamp_min(1e-6)
+ *     g_img = upsample_pdf_right_inverse(g,   L).clamp_min(0);  g_img /= g_img.sum(1).clamp_min(1e-6)
+ *     loss  = F.l1_loss(px_img, gx_img) + F.l1_loss(py_img, gy_img)
+ * px [B][Nx], py [B][Ny]: predicted PDFs (after mix_with_uniform); gx [B][Ngx], gy [B][Ngy]: gt_marginals of the
+ * pooled attention; Mx [W][Nx], My [H][Ny], Mgx [W][Ngx], Mgy [H][Ngy]: right-inverse matrices.  The [B][L] rows
+ * never reach global memory.  workspace: attwarp_pdf_l1_loss_workspace_bytes(B) bytes, ZEROED once by the caller
+ * (the kernel leaves it ready for the next launch); loss: one float.
+ * backward: upstream = d(objective)/d(loss), one float ON THE DEVICE; grad_px [B][Nx], grad_py [B][Ny] (the ground
+ * truth carries no gradient). */
+size_t attwarp_pdf_l1_loss_workspace_bytes(int B);
+int attwarp_pdf_l1_loss(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny,
+                        int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy, int W,
+                        int H, void* workspace, size_t workspace_bytes, float* loss, void* stream);
+int attwarp_pdf_l1_loss_backward(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx,
+                                 int Ny, int Ngx, int Ngy, const float* Mx, const float* My, const float* Mgx,
+                                 const float* Mgy, int W, int H, const float* upstream, float* grad_px, float* grad_py,
+                                 void* stream);
 /* F.adaptive_avg_pool2d(A, (gh,gw)) (mnfd/trainer.py:197): A [B][H][W] -> out [B][gh][gw]. */
 int attwarp_adaptive_avg_pool2d(const float* A, int B, int H, int W, int gh, int gw, float* out,
                                 void* stream);

@@ -220,3 +220,17 @@ def warp_from_cdf(img, Fx, Fy, out_size=None, remap_backend="restated"):
             w = w[..., None]
         out[b] = np.transpose(w, (2, 0, 1))
     return out
+
+
+def pdf_l1_loss(px_s, py_s, px_gt, py_gt, image_hw, eps=1e-8):
+    """``L_pdf`` of trainer.py:217-250 (forward value): up-sample predicted and ground-truth PDFs to image
+    resolution, ``clamp_min(0)``, divide by the row sum ``clamp_min(1e-6)``, mean absolute difference per axis."""
+    H, W = image_hw
+    tot = 0.0
+    for p, g, L in ((px_s, px_gt, W), (py_s, py_gt, H)):
+        a = np.maximum(upsample_pdf_right_inverse(np.asarray(p, F32), L, eps), 0).astype(F32)
+        b = np.maximum(upsample_pdf_right_inverse(np.asarray(g, F32), L, eps), 0).astype(F32)
+        a = a / np.maximum(a.sum(axis=1, keepdims=True, dtype=F32), F32(1e-6))
+        b = b / np.maximum(b.sum(axis=1, keepdims=True, dtype=F32), F32(1e-6))
+        tot += float(np.mean(np.abs(a - b), dtype=np.float64))
+    return tot

@@ -145,3 +145,22 @@ def test_sharded_equals_unsharded_ragged():
                 assert torch.equal(o, whole[i])
                 table[i] = sharding.checksum64(o)
         assert table == ref
+
+
+def test_ragged_batch_object_matches_call():
+    """ops.RaggedBatch (descriptor table built once, re-used across calls) == warp_ragged_from_tokens, for two
+    different token-map sets through the same object."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(21)
+    sizes = [(224, 224), (336, 336), (97, 53), (500, 333), (240, 400), (701, 18), (900, 1500)]
+    out_sizes = [(224, 224), (500, 500), (64, 200), (500, 333), (300, 800), (350, 40), (700, 1100)]
+    imgs = [dev(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in sizes]
+    batch = ops.RaggedBatch(imgs, out_sizes)
+    for seed in (1, 2):
+        toks = dev(_tokens(len(sizes), 24, seed=seed))
+        ref = ops.warp_ragged_from_tokens(toks, imgs, out_sizes)
+        got = batch.run(toks)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)

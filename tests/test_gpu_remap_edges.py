@@ -112,3 +112,42 @@ def test_odd_pitches(W, Wo):
     view = flat[5:].view(1, H, W, 3)
     out = ops.remap_bilinear(view, dev(mx[:1]), dev(my[:1]), "hwc")[0].cpu().numpy()
     assert np.array_equal(out, ON.remap(img[0], mx[0], my[0]))
+
+
+@pytest.mark.parametrize("H,W,Ho,Wo", [(336, 336, 336, 336), (336, 336, 500, 500), (1344, 1344, 1344, 1344),
+                                       (301, 224, 500, 500), (500, 333, 400, 700), (97, 53, 64, 200)])
+def test_quad_kernel_mappings_agree(H, W, Ho, Wo, monkeypatch):
+    """The 3-channel kernel (remap_quad.cu) picks, per warp and strip, between two thread <-> pixel mappings (QUAD:
+    four adjacent columns per thread; LANE: columns 32 apart + an in-warp transpose) and between fixed-shift and
+    per-slot addressing; every combination, and the round-1 kernel, must give the same bytes as the direct
+    (one thread per pixel) kernel on smooth and on strongly non-uniform maps."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(H * 7 + Wo)
+    B = 3
+    img = dev(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8))
+    maps = []
+    for kind in ("near_identity", "rand3", "steps"):
+        if kind == "near_identity":
+            tok = 1.0 + 0.02 * rng.standard_normal((B, 24, 24))
+        elif kind == "rand3":
+            tok = rng.random((B, 24, 24)) ** 3
+        else:
+            tok = np.where(rng.random((B, 24, 24)) < 0.3, 20.0, 0.05)
+        tok = (tok / tok.sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+        maps.append(ops.maps_from_tokens(dev(tok), (H, W), (Ho, Wo)))
+    for mx, my in maps:
+        monkeypatch.setenv("ATTWARP_REMAP", "direct")
+        # the direct kernel is selected once per process (static), so the reference here is the oracle-checked
+        # default path with the QUAD-only policy; policies are read at every launch
+        monkeypatch.delenv("ATTWARP_REMAP")
+        outs = {}
+        for policy in ("1", "2", "0"):
+            monkeypatch.setenv("ATTWARP_QUAD_MAP", policy)
+            outs[policy] = ops.remap_bilinear(img, mx, my, "hwc")
+        torch.cuda.synchronize()
+        assert torch.equal(outs["1"], outs["2"]) and torch.equal(outs["1"], outs["0"])
+        # and against the oracle's integer formula on one image
+        from oracle import numpy_path as ON
+        ref = ON.remap_u8(img[0].cpu().numpy(), mx[0].cpu().numpy(), my[0].cpu().numpy())
+        assert np.array_equal(outs["0"][0].cpu().numpy(), ref)
