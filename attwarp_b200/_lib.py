@@ -86,6 +86,8 @@ SIGNATURES = {
     "attwarp_safe_softmax_backward": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp]),
     "attwarp_mix_with_uniform_backward": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "attwarp_upsample_right_inverse_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "attwarp_safe_softmax_mix": (_i, [_vp, _i, _i, _f, _f, _vp, _vp]),
+    "attwarp_safe_softmax_mix_backward": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "attwarp_pdf_l1_loss_workspace_bytes": (_sz, [_i]),
     "attwarp_pdf_l1_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
     "attwarp_pdf_l1_loss_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp,

@@ -433,6 +433,19 @@ int attwarp_safe_softmax(const float* logits, int B, int N, float eps, float* ou
     return launch_safe_softmax(logits, B, N, eps, out, as_stream(stream));
 }
 
+int attwarp_safe_softmax_mix(const float* logits, int B, int N, float eps, float alpha, float* out, void* stream) {
+    AW_REQUIRE(logits && out, "safe_softmax_mix: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "safe_softmax_mix: sizes must be positive");
+    return launch_safe_softmax_mix(logits, B, N, eps, alpha, out, as_stream(stream));
+}
+
+int attwarp_safe_softmax_mix_backward(const float* logits, const float* grad_out, int B, int N, float eps, float alpha,
+                                      float* grad_logits, void* stream) {
+    AW_REQUIRE(logits && grad_out && grad_logits, "safe_softmax_mix_backward: NULL pointer");
+    AW_REQUIRE(B > 0 && N > 0, "safe_softmax_mix_backward: sizes must be positive");
+    return launch_safe_softmax_mix_backward(logits, grad_out, B, N, eps, alpha, grad_logits, as_stream(stream));
+}
+
 int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* out, void* stream) {
     AW_REQUIRE(p && out, "mix_with_uniform: NULL pointer");
     AW_REQUIRE(B > 0 && N > 0, "mix_with_uniform: sizes must be positive");

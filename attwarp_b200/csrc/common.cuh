@@ -77,6 +77,9 @@ int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, cons
 int launch_remap_u8_stream_ragged_prepare(RaggedImage* host_table, int n, int C, RaggedImage* dev_table, cudaStream_t st);
 int launch_remap_u8_stream_ragged_run(const RaggedImage* host_table, int n, int C, const RaggedImage* dev_table, cudaStream_t st);
 
+int launch_safe_softmax_mix(const float* logits, int B, int N, float eps, float alpha, float* out, cudaStream_t st);
+int launch_safe_softmax_mix_backward(const float* logits, const float* grad_out, int B, int N, float eps, float alpha,
+                                     float* grad_logits, cudaStream_t st);
 // fused image-resolution PDF-L1 loss (pdf_loss.cu); workspace: 2 B doubles + a zeroed 32-bit counter
 int launch_pdf_l1_loss(const float* px, const float* py, const float* gx, const float* gy, int B, int Nx, int Ny, int Ngx,
                        int Ngy, const float* Mx, const float* My, const float* Mgx, const float* Mgy, int W, int H,

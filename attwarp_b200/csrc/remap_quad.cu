@@ -30,6 +30,7 @@
 // Maps need not be monotone (a chunk ends before the first output row that taps an earlier source row than its
 // predecessor), a strip whose source span does not fit a stage is gathered from global memory (the kernel is
 // total), ragged batches run in one launch over a descriptor table.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -60,14 +61,16 @@ __device__ __forceinline__ void st128(int off, uint4 v) { *reinterpret_cast<uint
 //   +32  uint4 {address of the chunk's first output byte (lo, hi), bytes per tile row, Wo * 3}
 //   +48  uint4 {address of map_x[x_first] (lo, hi), W, columns in the strip}      (new strip only)
 //   +64  uint4 row[kMaxRows + 1]:  x = wE << 14, y = wO << 14  (weights of the even / odd source row)
-//                                  z = byte offset of the row inside the output tile
+//                                  z = byte offset of the row inside the output tile: row * pitch + (address of the
+//                                      row's first destination byte & 12) -- always 4-byte aligned for the
+//                                      consumers' word stores; the store warp bridges the remaining 0..3 bytes
 //                                  w = slot after which the row is emitted (= slot of its LOWER tap);
 //                                      0xffffffff: both taps are the carried pair, emit before slot 0;
 //                                      the entry after the last row is a sentinel
 constexpr int kTabStore = 32, kTabStrip = 48, kTabRows = 64;
 constexpr int kTabBytes = kTabRows + 16 * (kMaxRows + 1);
 constexpr uint32_t kRowSentinel = 0x7fffffffu;
-constexpr uint32_t kFlagNewStrip = 1u, kFlagFixedShift = 2u, kFlagWordStores = 4u, kFlagOddFirst = 8u;
+constexpr uint32_t kFlagNewStrip = 1u, kFlagFixedShift = 2u, kFlagOddFirst = 8u;
 constexpr int kNoCarry = -(1 << 29);
 
 // base source column and tap weights of one output column (border replicate folded into weights)
@@ -139,15 +142,6 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "@pv st.shared.b32 [o], q0;\n"                              \
     "@pv st.shared.b32 [o+4], q2;\n"                            \
     "@pv st.shared.b32 [o+8], q4;\n"
-// tile rows that are not 4-byte aligned: byte stores of the top bytes
-#define AWQ_SB1(J, K, OFF)                                      \
-    "shr.u32 v" #J #K ", v" #J #K ", 24;\n"                     \
-    "@pv st.shared.u8 [o+" #OFF "], v" #J #K ";\n"
-#define AWQ_EMIT_B                                              \
-    AWQ_VBLEND                                                  \
-    "add.u32 o, ez, %38;\n"                                     \
-    AWQ_SB1(a, 0, 0) AWQ_SB1(a, 1, 1) AWQ_SB1(a, 2, 2) AWQ_SB1(b, 0, 3) AWQ_SB1(b, 1, 4) AWQ_SB1(b, 2, 5)  \
-    AWQ_SB1(c, 0, 6) AWQ_SB1(c, 1, 7) AWQ_SB1(c, 2, 8) AWQ_SB1(d, 0, 9) AWQ_SB1(d, 1, 10) AWQ_SB1(d, 2, 11)
 // LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
 // 128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict whatever the
 // local scale of the map.  The output bytes change hands through a per-warp scratch (two 512-byte buffers used
@@ -266,19 +260,17 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     : "memory"
 
 // FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
-// EMIT: 0 = QUAD mapping, aligned word stores; 1 = QUAD mapping, byte stores; 2 = LANE mapping (word stores).
-template <bool FIXED, int EMIT>
+// LANE: false = QUAD mapping, true = LANE mapping (both end in three aligned word stores per thread and row).
+template <bool FIXED, bool LANE>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
                                            const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
                                            uint32_t rp, uint32_t ocol, uint32_t odd_first, uint32_t store_ok,
                                            uint32_t sx, uint32_t sq) {
     if (FIXED) {
-        if (EMIT == 0) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else if (EMIT == 1) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (!LANE) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
         else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
     } else {
-        if (EMIT == 0) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else if (EMIT == 1) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_B) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (!LANE) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
         else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
     }
 }
@@ -300,10 +292,20 @@ struct QuadArgs {
     int out_pitch;           // bytes per row of an output tile
     int rows;                // output rows per chunk (<= kMaxRows)
     int stages, tiles;       // ring depths: source-row stages (chunks whose loads are in flight), output tiles
+    int wave, skew_ppm;      // CTAs per wave (= SMs) and the share skew between the first and the last wave, 1e-6 units
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
                              // 1: always QUAD, 2: LANE wherever word stores apply
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
+    unsigned long long* trace;   // ATTWARP_REMAP_TRACE: 8 global-timer stamps per CTA (nullptr: off)
 };
+
+__device__ __forceinline__ void trace_stamp(const QuadArgs& a, int slot) {
+    if (a.trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 struct View {
     const uint8_t* src;
@@ -335,6 +337,23 @@ __device__ __forceinline__ View get_view(const QuadArgs& a, int img) {
         v.tile_units = 1;
     }
     return v;
+}
+
+// the image whose tiles contain unit u0: the last one whose first unit is <= u0 (32-ary search over the table;
+// called by whole warps)
+__device__ __forceinline__ int first_image(const QuadArgs& a, int u0, int lane) {
+    if (a.imgs == nullptr) return u0 / (a.n_strips * a.n_rowtiles);
+    int lo = 0, hi = a.n_img;                              // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) / 32;
+        const int probe = min(lo + (lane + 1) * step, hi);
+        const bool le = probe < hi && __ldg(&a.imgs[probe].unit_begin) <= u0;
+        const int k = __popc(__ballot_sync(0xffffffffu, le));       // probes are monotone
+        const int nlo = lo + k * step;
+        hi = min(lo + (k + 1) * step, hi);
+        lo = nlo;
+    }
+    return lo;
 }
 
 // Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
@@ -375,12 +394,33 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             mbar_init(ofree_s + 8u * s, 1);
         }
         mbar_init_fence();
+        trace_stamp(a, 0);                                   // CTA started
     }
     __syncthreads();
 
-    // contiguous, balanced range of the cost axis for this CTA: it owns the tiles that START inside it
-    const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
-    const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
+    // Contiguous range of the cost axis for this CTA: it owns the tiles that START inside it.  The ranges are equal
+    // up to a measured skew: with several CTAs per SM the hardware favours the warps of the CTA that arrived first
+    // (CTAs 0 .. SMs-1 finish ~15 % ahead of CTAs 3 SMs .. 4 SMs-1 when all get the same rows, and the SM idles
+    // behind its last CTA), so CTA b of wave q = b / wave gets a share proportional to 1 + skew (1 - 2 q / (waves-1)).
+    int u0, u1;
+    if (a.skew_ppm == 0 || a.wave <= 0 || (int)gridDim.x <= a.wave) {
+        u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
+        u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
+    } else {
+        const int waves = ((int)gridDim.x + a.wave - 1) / a.wave;
+        auto cum = [&](int b) -> double {           // cumulative share of CTAs [0, b)
+            double c = 0.0;
+            for (int q = 0; q < waves; ++q) {
+                const int lo = q * a.wave, hi = min((q + 1) * a.wave, (int)gridDim.x);
+                const int n = max(0, min(b, hi) - lo);
+                c += n * (1.0 + a.skew_ppm * 1e-6 * (1.0 - 2.0 * q / (waves - 1)));
+            }
+            return c;
+        };
+        const double tot = cum((int)gridDim.x);
+        u0 = (int)((double)a.total_units * cum((int)blockIdx.x) / tot);
+        u1 = blockIdx.x + 1 == gridDim.x ? a.total_units : (int)((double)a.total_units * cum((int)blockIdx.x + 1) / tot);
+    }
 
     const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
@@ -390,22 +430,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             // =========================== producer warp =========================================
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
-            int img;
-            if (a.imgs == nullptr) {
-                img = u0 / (a.n_strips * a.n_rowtiles);
-            } else {
-                int lo = 0, hi = a.n_img;                              // answer in [lo, hi)
-                while (hi - lo > 1) {
-                    const int step = (hi - lo + 31) / 32;
-                    const int probe = min(lo + (lane + 1) * step, hi);
-                    const bool le = probe < hi && __ldg(&a.imgs[probe].unit_begin) <= u0;
-                    const int k = __popc(__ballot_sync(0xffffffffu, le));       // probes are monotone
-                    const int nlo = lo + k * step;
-                    hi = min(lo + (k + 1) * step, hi);
-                    lo = nlo;
-                }
-                img = lo;
-            }
+            bool first_copy = true;
+            int img = first_image(a, u0, lane);
             View v = get_view(a, img);
             int local = (u0 - v.unit_begin + v.tile_units - 1) / v.tile_units;   // first tile starting at >= u0
             for (;;) {
@@ -462,10 +488,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 const int max_slots = min((a.stage_bytes - 64) / slot_pitch, 2 * R);
                 const uint8_t* scol = simg + (int64_t)c_lo * kC;
                 const bool fixed = (slot_pitch & 3) == 0;
-                // word stores need every tile row 4-byte aligned: tile rows keep the 16-byte phase of their
-                // destination, which must then be a multiple of 4 for every row of the strip
-                const bool words = (((dimg + (uintptr_t)x_first * kC) | (uintptr_t)(Wo * kC)) & 3) == 0;
-                uint32_t seg_flags = kFlagNewStrip | (fixed ? kFlagFixedShift : 0u) | (words ? kFlagWordStores : 0u);
+                uint32_t seg_flags = kFlagNewStrip | (fixed ? kFlagFixedShift : 0u);
                 int carry_row = kNoCarry;    // the consumers hold the blends of rows carry_row - 1 and carry_row
                 int y_cur = rt;
                 // map_y is read through a register window of 2 x 32 rows (lane i holds rows y_win + i
@@ -524,7 +547,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                         const bool up_even = (ra & 1) == 0;
                         st128(tab + kTabRows + 16 * lane,
                               make_uint4(up_even ? wu : wl_, up_even ? wl_ : wu,
-                                         (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 15),
+                                         (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 12),
                                          (uint32_t)(ra + 1 - r_lo)));
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, 0u, kRowSentinel));
@@ -554,6 +577,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     } else if (lane < n_slots) {
                         bulk_g2s(stage_s + (uint32_t)((phase0 + lane * slot_pitch) & ~15), p - off, bytes, full_s + 8u * st);
                     }
+                    if (first_copy && lane == 0) trace_stamp(a, 1);    // first chunk planned, its copy issued
+                    first_copy = false;
                     carry_row = n_rows > 0 ? ra_last + 1 : kNoCarry;
                     y_cur += max(n_rows, 1);
                     if (++st == kStages) { st = 0; ph ^= 1u; }
@@ -576,40 +601,85 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 const int n_rows = (int)hd.x;
                 if (n_rows < 0) break;
                 if (n_rows > 0 && !(a.dbg & 2)) {
+                    // Tile row i sits at  i * out_pitch + (address of its first destination byte & 12).
+                    //   rows whose destination is 4-byte aligned: bulk store of the 16-byte aligned interior (shared
+                    //     and global addresses have the same 16-byte phase), <= 15 head and tail bytes by byte stores;
+                    //   other rows (odd widths): the interior is shifted by 1..3 bytes on its way out -- per 16-byte
+                    //     destination chunk one aligned 128-bit load + the word before it, four funnel shifts, one
+                    //     aligned 128-bit store (lanes take consecutive chunks: full-sector writes).
                     const uint4 hs = ld128(ohdr_off0 + 32 * ot + 16);  // {dst lo, dst hi, row bytes, dst pitch}
                     const int len = (int)hs.z;
                     const int64_t dpitch = (int64_t)hs.w;
                     const int obuf = out_off0 + ot * out_bytes;
                     uint8_t* g0 = reinterpret_cast<uint8_t*>(((uint64_t)hs.y << 32) | hs.x);
-                    const bool ragged = ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len | (uintptr_t)dpitch) & 15) != 0;
+                    const bool plain = ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len | (uintptr_t)dpitch) & 15) == 0;
                     if (lane < n_rows) {
                         uint8_t* g = g0 + (int64_t)lane * dpitch;
                         const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                         const int head = (16 - off) & 15;
                         const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
-                        if (body > 0)
+                        if ((off & 3) == 0 && body > 0)
                             bulk_s2g(g + head, smem_s + (uint32_t)(obuf + lane * a.out_pitch + off + head), (uint32_t)body);
                     }
                     bulk_commit();
-                    if (ragged) {
-                        // <= 15 head bytes and <= 15 tail bytes per row, one lane per byte
+                    if (!plain) {
                         for (int i = 0; i < n_rows; ++i) {
                             uint8_t* g = g0 + (int64_t)i * dpitch;
                             const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                             const int head = min((16 - off) & 15, len);
                             const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
-                            const int s = obuf + i * a.out_pitch + off;
+                            const int s = obuf + i * a.out_pitch + (off & 12);       // the row's first byte
+                            // <= 15 head bytes and <= 15 tail bytes, one lane per byte
                             if (lane < 16) {
                                 if (lane < head) g[lane] = smem[s + lane];
                             } else {
                                 const int qq = head + body + (lane - 16);
                                 if (qq < len) g[qq] = smem[s + qq];
                             }
+                            const int r = off & 3;
+                            if (r != 0) {
+                                // destination chunk c = bytes [head + 16 c, + 16) of the row = shared bytes
+                                // [A - r, A - r + 16) with A = s + head + 16 c + r a multiple of 16.  Four chunks per
+                                // lane and pass, loads first; the word before a chunk is the last word of the chunk
+                                // of the lane below (lane 0 reads its own).
+                                const uint32_t shift = 8u * (uint32_t)(4 - r);
+                                const int nch = body >> 4;
+                                const int A0 = s + head + r;
+                                uint8_t* gp = g + head;
+                                for (int c0 = 0; c0 < nch; c0 += 128) {
+                                    uint4 w[4];
+                                    uint32_t wm[4];
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int c = c0 + 32 * k + lane;
+                                        w[k] = c < nch ? ld128(A0 + 16 * c) : make_uint4(0u, 0u, 0u, 0u);
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        wm[k] = __shfl_up_sync(0xffffffffu, w[k].w, 1);
+                                        if (lane == 0) wm[k] = ld32(A0 + 16 * (c0 + 32 * k) - 4);
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int c = c0 + 32 * k + lane;
+                                        uint4 o;
+                                        o.x = __funnelshift_r(wm[k], w[k].x, shift);
+                                        o.y = __funnelshift_r(w[k].x, w[k].y, shift);
+                                        o.z = __funnelshift_r(w[k].y, w[k].z, shift);
+                                        o.w = __funnelshift_r(w[k].z, w[k].w, shift);
+                                        if (c < nch) *reinterpret_cast<uint4*>(gp + 16 * c) = o;
+                                    }
+                                }
+                            }
                         }
                     }
                     bulk_wait_read0();                                 // the tile has left shared memory
                 }
                 __syncwarp();
+                if (lane == 0 && a.trace != nullptr) {
+                    if (a.trace[(size_t)blockIdx.x * 8 + 4] == 0ull) trace_stamp(a, 4);   // first tile shipped
+                    trace_stamp(a, 5);                                                     // latest tile shipped
+                }
                 if (lane == 0) mbar_arrive(ofree_s + 8u * ot);        // tile free for the consumers
                 if (++ot == kTiles) { ot = 0; ph ^= 1u; }
             }
@@ -634,6 +704,62 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const int out_col = x0 * kC;
     const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
     const uint32_t sq_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 16);    //          my four adjacent pixels out
+    int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
+
+    // per-strip setup: taps and weights of this thread's columns, choice of the mapping
+    auto setup_strip = [&](const float* mx, int W, int ncols) {
+        store_ok = x0 < ncols ? 1u : 0u;
+        warp_live = __any_sync(0xffffffffu, store_ok != 0u);
+        int xb = -1, xb_first = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // a column past the strip's end keeps the previous column's window and gets zero weights
+            int w0 = 0, w1 = 0;
+            if (x0 + j < ncols) column_taps(__ldg(mx + x0 + j), W, xb, w0, w1);
+            if (j == 0) xb_first = xb;
+            xba[j] = xb;
+            wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
+            wh[j] = wl[j] << 16;
+        }
+        // QUAD loads are conflict-free only while the lanes' windows stay 3 words apart: when the source column
+        // of some lane's first pixel has drifted two or more pixels from "4 per lane", switch the warp to the
+        // LANE mapping
+        lane_map = false;
+        if (warp_live && a.map_policy != 1) {
+            const int xb_lane0 = __shfl_sync(0xffffffffu, xb_first, 0);
+            const int dev = store_ok ? abs(xb_first - xb_lane0 - 4 * lane) : 0;
+            lane_map = a.map_policy == 2 || __any_sync(0xffffffffu, dev >= 2);
+        }
+        if (lane_map) {
+            xb = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = xw + 32 * j + lane;
+                int w0 = 0, w1 = 0;
+                if (x < ncols) column_taps(__ldg(mx + x), W, xb, w0, w1);
+                xba[j] = xb;
+                wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
+                wh[j] = wl[j] << 16;
+            }
+        }
+    };
+    // The first strip of this CTA is known before the producer says so (same arithmetic on u0): set it up while
+    // the first rows are still in flight -- the map_x loads and the tap arithmetic leave the CTA's start-up path.
+    int pre_img = -1, pre_x_first = -1;
+    {
+        const int img = first_image(a, u0, lane);
+        if (img < a.n_img) {
+            const View v = get_view(a, img);
+            int local = (u0 - v.unit_begin + v.tile_units - 1) / v.tile_units;
+            if (local < v.n_strips * v.n_rowtiles && v.unit_begin + local * v.tile_units < u1) {
+                const int strip = local / v.n_rowtiles;
+                const int x_first = strip * v.strip_cols;
+                setup_strip(v.mx + x_first, v.W, min(v.strip_cols, v.Wo - x_first));
+                pre_img = img;
+                pre_x_first = x_first;
+            }
+        }
+    }
 
     int st = 0, ot = 0;               // source stage / output tile of the current chunk
     uint32_t sph = 0u, oph = 1u;      // parities to wait for: stage filled / tile shipped and free
@@ -641,6 +767,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             ot = ot + 1 == kTiles ? 0 : ot + 1, oph ^= ot == 0 ? 1u : 0u) {
         const int tab = tab_off0 + st * kTabBytes;
         mbar_wait(full_s + 8u * st, sph);
+        if (tid == 0 && a.trace != nullptr && a.trace[(size_t)blockIdx.x * 8 + 2] == 0ull) trace_stamp(a, 2);   // first rows landed
         const uint4 h0 = ld128(tab);
         const int n_rows = (int)h0.x;
         mbar_wait(ofree_s + 8u * ot, oph);                                       // tile shipped and free
@@ -653,44 +780,14 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         const uint32_t flags = h0.y >> 16;
         if (flags & kFlagNewStrip) {                         // new strip: per-column taps and weights
             const uint4 h1 = ld128(tab + 16);
-            const uint4 hx = ld128(tab + kTabStrip);
-            const float* mx = reinterpret_cast<const float*>(((uint64_t)hx.y << 32) | hx.x);
-            const int W = (int)hx.z, ncols = (int)hx.w;
-            store_ok = x0 < ncols ? 1u : 0u;
-            warp_live = __any_sync(0xffffffffu, store_ok != 0u);
-            int xb = (int)h1.w;
-            int xb_first = xb;
+            if ((int)h1.x != pre_img || (int)h1.y != pre_x_first) {
+                const uint4 hx = ld128(tab + kTabStrip);
+                const float* mx = reinterpret_cast<const float*>(((uint64_t)hx.y << 32) | hx.x);
+                setup_strip(mx, (int)hx.z, (int)hx.w);
+            }
+            pre_img = -1;                                    // the early setup serves the first segment only
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // a column past the strip's end keeps the previous column's window and gets zero weights
-                int w0 = 0, w1 = 0;
-                if (x0 + j < ncols) column_taps(__ldg(mx + x0 + j), W, xb, w0, w1);
-                if (j == 0) xb_first = xb;
-                wo[j] = (xb - (int)h1.w) * kC;
-                wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
-                wh[j] = wl[j] << 16;
-            }
-            // QUAD loads are conflict-free only while the lanes' windows stay 3 words apart: when the source column
-            // of some lane's first pixel has drifted two or more pixels from "4 per lane", switch the warp to the
-            // LANE mapping (needs word stores: the scratch round trip ends in the QUAD mapping's aligned stores)
-            lane_map = false;
-            if (warp_live && (flags & kFlagWordStores) && a.map_policy != 1) {
-                const int xb_lane0 = __shfl_sync(0xffffffffu, xb_first, 0);
-                const int dev = store_ok ? abs(xb_first - xb_lane0 - 4 * lane) : 0;
-                lane_map = a.map_policy == 2 || __any_sync(0xffffffffu, dev >= 2);
-            }
-            if (lane_map) {
-                xb = (int)h1.w;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int x = xw + 32 * j + lane;
-                    int w0 = 0, w1 = 0;
-                    if (x < ncols) column_taps(__ldg(mx + x), W, xb, w0, w1);
-                    wo[j] = (xb - (int)h1.w) * kC;
-                    wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
-                    wh[j] = wl[j] << 16;
-                }
-            }
+            for (int j = 0; j < 4; ++j) wo[j] = xba[j] < 0 ? 0 : (xba[j] - (int)h1.w) * kC;
         }
         if (tid == 0) {                                      // what the store warp needs to ship the tile
             st128(ohdr_off0 + 32 * ot, make_uint4(h0.x, 0u, 0u, 0u));
@@ -727,7 +824,6 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             const uint32_t base = smem_s + (uint32_t)(st * a.stage_bytes) + h0.w;    // first byte of slot 0
             const uint32_t odd = (flags & kFlagOddFirst) ? 1u : 0u;
             uint32_t win[4], sh[4];
-            const int emit = lane_map ? 2 : ((flags & kFlagWordStores) ? 0 : 1);
             if (flags & kFlagFixedShift) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -735,20 +831,22 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (emit == 0) sweep_quad<true, 0>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else if (emit == 1) sweep_quad<true, 1>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else sweep_quad<true, 2>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                if (!lane_map) sweep_quad<true, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else sweep_quad<true, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (emit == 0) sweep_quad<false, 0>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else if (emit == 1) sweep_quad<false, 1>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else sweep_quad<false, 2>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                if (!lane_map) sweep_quad<false, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                else sweep_quad<false, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
             }
         }
         // publish this warp's part of the tile to the async proxy, then count the warp in
         fence_proxy_async();
         __syncwarp();
+        if (tid == 0 && a.trace != nullptr) {
+            if (a.trace[(size_t)blockIdx.x * 8 + 3] == 0ull) trace_stamp(a, 3);   // first chunk swept (warp 0)
+            trace_stamp(a, 6);                                                     // latest chunk swept
+        }
         if (lane == 0) {
             mbar_arrive(sfree_s + 8u * st);
             mbar_arrive(odone_s + 8u * ot);
@@ -833,7 +931,38 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
     if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
     const int64_t cap = (int64_t)sm_count() * c.occ;
     const int grid = (int)(a.total_units < cap ? a.total_units : cap);
+    a.wave = sm_count();
+    a.skew_ppm = env_int("ATTWARP_QUAD_SKEW_PPM", 60000);   // measured on B200 at 4 CTAs per SM (profiles/README.md)
+    // ATTWARP_REMAP_TRACE=<file>: per-CTA global-timer stamps of every launch, appended to the file (debugging
+    // only: synchronises the stream)
+    const char* trace_path = getenv("ATTWARP_REMAP_TRACE");
+    a.trace = nullptr;
+    if (trace_path != nullptr && trace_path[0] != 0) {
+        static unsigned long long* dbuf = nullptr;
+        static int dcap = 0;
+        if (grid > dcap) {
+            if (dbuf != nullptr) cudaFree(dbuf);
+            AW_CUDA(cudaMalloc(&dbuf, sizeof(unsigned long long) * 8 * (size_t)grid));
+            dcap = grid;
+        }
+        AW_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(unsigned long long) * 8 * (size_t)grid, st));
+        a.trace = dbuf;
+    }
     kern<<<grid, kThreads, smem_bytes, st>>>(a);
+    if (a.trace != nullptr) {
+        std::vector<unsigned long long> h((size_t)grid * 8);
+        AW_CUDA(cudaStreamSynchronize(st));
+        AW_CUDA(cudaMemcpy(h.data(), a.trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(trace_path, "a")) {
+            fprintf(f, "launch grid=%d threads=%d rows=%d smem=%zu\n", grid, kThreads, a.rows, smem_bytes);
+            for (int i = 0; i < grid; ++i) {
+                fprintf(f, "%d", i);
+                for (int k = 0; k < 8; ++k) fprintf(f, " %llu", h[(size_t)i * 8 + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return check_launch("remap_u8_quad_kernel");
 }
 

@@ -20,7 +20,8 @@ __device__ __forceinline__ float nan_inf_to_zero(float v) { return (isnan(v) || 
 // One CTA per row.  safe_softmax: nan_to_num(0,0,0) -> subtract max -> softmax -> nan_to_num ->
 // / max(sum, eps).
 __global__ void __launch_bounds__(kRowThreads)
-safe_softmax_kernel(const float* __restrict__ logits, int N, float eps, float* __restrict__ out) {
+safe_softmax_kernel(const float* __restrict__ logits, int N, float eps, int mix, float c1, float c2,
+                    float* __restrict__ out) {
     __shared__ float red[32];
     const float* row = logits + (int64_t)blockIdx.x * N;
     float* o = out + (int64_t)blockIdx.x * N;
@@ -38,7 +39,11 @@ safe_softmax_kernel(const float* __restrict__ logits, int N, float eps, float* _
     }
     s2 = block_sum(s2, red);
     const float denom = fmaxf(s2, eps);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = o[i] / denom;
+    // mix != 0: mix_with_uniform fused behind it (model.py:98-101), the same two roundings as the stand-alone kernel
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float q = o[i] / denom;
+        o[i] = mix ? fadd_nofma(fmul_nofma(c1, q), c2) : q;
+    }
 }
 
 __global__ void mix_with_uniform_kernel(const float* __restrict__ p, int64_t total, float c1,
@@ -243,7 +248,7 @@ adaptive_avg_pool2d_kernel(const float* __restrict__ A, const uint8_t* __restric
 // dz = 0 where z is not finite (nan_to_num has zero slope there).
 __global__ void __launch_bounds__(kRowThreads)
 safe_softmax_backward_kernel(const float* __restrict__ logits, const float* __restrict__ grad_out, int N, float eps,
-                             float* __restrict__ grad_logits) {
+                             float gscale, float* __restrict__ grad_logits) {
     __shared__ float red[32];
     const float* row = logits + (int64_t)blockIdx.x * N;
     const float* g = grad_out + (int64_t)blockIdx.x * N;
@@ -258,7 +263,7 @@ safe_softmax_backward_kernel(const float* __restrict__ logits, const float* __re
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const float p = nan_inf_to_zero(expf(nan_inf_to_zero(row[i]) - m) / e);
         s += p;
-        gp += g[i] * p;
+        gp += g[i] * gscale * p;
     }
     s = block_sum(s, red);
     gp = block_sum(gp, red);
@@ -269,13 +274,13 @@ safe_softmax_backward_kernel(const float* __restrict__ logits, const float* __re
     float gpp = 0.f;                                    // sum g' p
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const float p = nan_inf_to_zero(expf(nan_inf_to_zero(row[i]) - m) / e);
-        gpp += (g[i] - shift) / denom * p;
+        gpp += (g[i] * gscale - shift) / denom * p;
     }
     gpp = block_sum(gpp, red);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const float z = row[i];
         const float p = nan_inf_to_zero(expf(nan_inf_to_zero(z) - m) / e);
-        const float gi = (g[i] - shift) / denom;
+        const float gi = (g[i] * gscale - shift) / denom;
         o[i] = (isnan(z) || isinf(z)) ? 0.f : p * (gi - gpp);
     }
 }
@@ -301,7 +306,14 @@ upsample_right_inverse_backward_kernel(const float* __restrict__ gx, const float
 }  // namespace
 
 int launch_safe_softmax(const float* logits, int B, int N, float eps, float* out, cudaStream_t st) {
-    safe_softmax_kernel<<<B, kRowThreads, 0, st>>>(logits, N, eps, out);
+    safe_softmax_kernel<<<B, kRowThreads, 0, st>>>(logits, N, eps, 0, 1.f, 0.f, out);
+    return check_launch("safe_softmax_kernel");
+}
+
+// safe_softmax followed by mix_with_uniform in one launch (MarginalNet.forward's last op + trainer.py:212-214)
+int launch_safe_softmax_mix(const float* logits, int B, int N, float eps, float alpha, float* out, cudaStream_t st) {
+    const float c1 = (float)(1.0 - (double)alpha), c2 = (float)((double)alpha / (double)N);
+    safe_softmax_kernel<<<B, kRowThreads, 0, st>>>(logits, N, eps, alpha > 0.f, c1, c2, out);
     return check_launch("safe_softmax_kernel");
 }
 
@@ -371,7 +383,15 @@ int launch_upsample_right_inverse(const float* y, const float* M, int B, int L_o
 
 int launch_safe_softmax_backward(const float* logits, const float* grad_out, int B, int N, float eps,
                                  float* grad_logits, cudaStream_t st) {
-    safe_softmax_backward_kernel<<<B, kRowThreads, 0, st>>>(logits, grad_out, N, eps, grad_logits);
+    safe_softmax_backward_kernel<<<B, kRowThreads, 0, st>>>(logits, grad_out, N, eps, 1.f, grad_logits);
+    return check_launch("safe_softmax_backward_kernel");
+}
+
+// backward of the fused pair: d mix / d q = (1 - alpha) (alpha <= 0: identity), then the softmax backward
+int launch_safe_softmax_mix_backward(const float* logits, const float* grad_out, int B, int N, float eps, float alpha,
+                                     float* grad_logits, cudaStream_t st) {
+    const float c1 = alpha > 0.f ? (float)(1.0 - (double)alpha) : 1.f;
+    safe_softmax_backward_kernel<<<B, kRowThreads, 0, st>>>(logits, grad_out, N, eps, c1, grad_logits);
     return check_launch("safe_softmax_backward_kernel");
 }
 

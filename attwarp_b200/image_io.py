@@ -6,10 +6,13 @@ batches the rest:
 
 * ``decode_jpeg_batch(sources)``     JPEG bytes / paths -> uint8 HWC **BGR** device tensors, the layout stage 5
   reads (nvJPEG through ``torchvision.io.decode_jpeg(device=...)`` -- library code, like calling cuBLAS).
-  NOT bit-identical to libjpeg: IDCT and chroma up-sampling differ between decoders.  Measured against Pillow on
-  the GPU box (tests/test_image_io.py states the bound it holds): 4:4:4 files differ by at most 1-2 LSB on a few
-  pixels, 4:2:0 files (chroma up-sampling: libjpeg's "fancy" triangle filter vs nvJPEG's) by a few LSB along
-  colour edges.  Anything that is not a JPEG (PNG, ...) is decoded on the host by OpenCV, exactly.
+  NOT bit-identical to libjpeg: IDCT and chroma up-sampling differ between decoders.  Measured against Pillow (the
+  reader the reference drivers use) on the B200 box, synthetic photo-like images with a saturated colour block,
+  quality 90 (tests/test_image_io.py holds these bounds): 4:4:4 files: max 4 LSB, mean 0.5 LSB; 4:2:0 files: mean
+  1.9 LSB, 99 % of the bytes within ~10 LSB, but up to ~100 LSB on the one-pixel rim of a saturated colour edge
+  (nvJPEG replicates chroma samples where libjpeg's "fancy" up-sampling interpolates them).  ``exact=True`` decodes
+  on the host with Pillow instead -- bit-identical to ``Image.open(path).convert('RGB')`` -- for runs that must
+  reproduce the reference's pixels.  Anything that is not a JPEG (PNG, ...) is decoded on the host, exactly.
 * ``encode_png_batch(images, paths)`` device tensors -> PNG files: device -> pinned host copy, then
   ``cv2.imwrite`` in a thread pool -- the reference's own encoder, so the files decode to the same bytes.
   (A GPU PNG/deflate encoder is out of scope until its output is pinned; PNG is lossless, so only speed is at stake.)
@@ -40,14 +43,23 @@ def _is_jpeg(buf: bytes) -> bool:
     return len(buf) > 3 and buf[0] == 0xFF and buf[1] == 0xD8
 
 
-def decode_jpeg_batch(sources: Sequence, device=None) -> List[torch.Tensor]:
+def decode_jpeg_batch(sources: Sequence, device=None, exact: bool = False) -> List[torch.Tensor]:
     """Paths or encoded bytes -> list of uint8 [H, W, 3] BGR tensors on ``device`` (cv2.imread's channel order, the
     one ``save_warped_image`` warps in).  JPEG files are decoded on the GPU in one batched nvJPEG call; grey JPEGs
-    come out as three equal channels (like ``Image.convert('RGB')``)."""
-    from torchvision.io import ImageReadMode, decode_jpeg
+    come out as three equal channels (like ``Image.convert('RGB')``).  ``exact=True``: host decode with Pillow,
+    bit-identical to the reference's reader, then one copy to the device."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     bufs = [_read_bytes(s) for s in sources]
     out: List[Optional[torch.Tensor]] = [None] * len(bufs)
+    if exact:
+        import io
+
+        from PIL import Image
+        for i, b in enumerate(bufs):
+            rgb = np.array(Image.open(io.BytesIO(b)).convert("RGB"))
+            out[i] = torch.from_numpy(np.ascontiguousarray(rgb[..., ::-1])).to(dev, non_blocking=True)
+        return out  # type: ignore[return-value]
+    from torchvision.io import ImageReadMode, decode_jpeg
     jpeg_idx = [i for i, b in enumerate(bufs) if _is_jpeg(b)]
     if jpeg_idx:
         datas = [torch.frombuffer(bytearray(bufs[i]), dtype=torch.uint8) for i in jpeg_idx]

@@ -2,6 +2,8 @@
 
 * ``safe_softmax(logits, dim=1, eps=1e-6)``   (model.py:8-14)
 * ``mix_with_uniform(p, alpha)``              (model.py:98-101)
+* ``safe_softmax_mix(logits, alpha)``         the two back to back in one launch (MarginalNet.forward's last op,
+  model.py:93-94, followed by trainer.py:212-214); bit-identical to calling them in turn
 
 CUDA tensors only; computed by libattwarp_sm100.so (no CPU fallback).  The MarginalNet network
 itself (dense convolutions, model.py:17-95) is out of scope.
@@ -17,6 +19,8 @@ from ._lib import check, current_stream, load, ptr, require_cuda
 def _rows(t: torch.Tensor, dim: int):
     """View ``t`` as [B, N] float32 rows along ``dim``; returns (rows, restore_fn)."""
     dim = dim % t.dim()
+    if t.dim() == 2 and dim == 1 and t.dtype == torch.float32 and t.is_contiguous():
+        return t, lambda r: r                       # the trainer's case: no views, no copies
     moved = t.movedim(dim, -1)
     shape = moved.shape
     rows = moved.reshape(-1, shape[-1]).contiguous().float()
@@ -89,3 +93,34 @@ def mix_with_uniform(p: torch.Tensor, alpha: float) -> torch.Tensor:
     require_cuda(p)
     assert p.dim() == 2, "mix_with_uniform expects (B, N)"
     return _MixWithUniform.apply(p.contiguous().float(), alpha).to(p.dtype)
+
+
+class _SafeSoftmaxMixRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, eps, alpha):
+        lib = load()
+        out = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_safe_softmax_mix(ptr(rows), rows.shape[0], rows.shape[1], float(eps), float(alpha),
+                                               ptr(out), current_stream(rows.device)))
+        ctx.save_for_backward(rows)
+        ctx.eps, ctx.alpha = float(eps), float(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rows,) = ctx.saved_tensors
+        lib = load()
+        g = grad.contiguous().float()
+        gz = torch.empty_like(rows)
+        with torch.cuda.device(rows.device):
+            check(lib.attwarp_safe_softmax_mix_backward(ptr(rows), ptr(g), rows.shape[0], rows.shape[1], ctx.eps,
+                                                        ctx.alpha, ptr(gz), current_stream(rows.device)))
+        return gz, None, None
+
+
+def safe_softmax_mix(logits: torch.Tensor, alpha: float, dim: int = 1, eps: float = 1e-6) -> torch.Tensor:
+    """``mix_with_uniform(safe_softmax(logits, dim, eps), alpha)`` in one launch (and one backward launch)."""
+    require_cuda(logits)
+    rows, restore = _rows(logits, dim)
+    return restore(_SafeSoftmaxMixRows.apply(rows, eps, alpha))

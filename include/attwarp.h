@@ -241,6 +241,12 @@ int attwarp_warp_image_host(const void* image_host, int img_dtype, int C, int H,
  */
 /* safe_softmax, dim=1 (mnfd/model.py:8-14). */
 int attwarp_safe_softmax(const float* logits, int B, int N, float eps, float* out, void* stream);
+/* safe_softmax (mnfd/model.py:8-14) followed by mix_with_uniform (model.py:98-101) in ONE launch -- what
+ * MarginalNet.forward + trainer.py:212-214 compute back to back; alpha <= 0 is plain safe_softmax.  Bit-identical to
+ * the two stand-alone entry points run in turn.  backward: grad_out [B][N] -> grad_logits [B][N]. */
+int attwarp_safe_softmax_mix(const float* logits, int B, int N, float eps, float alpha, float* out, void* stream);
+int attwarp_safe_softmax_mix_backward(const float* logits, const float* grad_out, int B, int N, float eps, float alpha,
+                                      float* grad_logits, void* stream);
 /* mix_with_uniform (mnfd/model.py:98-101): alpha<=0 copies. */
 int attwarp_mix_with_uniform(const float* p, int B, int N, float alpha, float* out,
                              void* stream);

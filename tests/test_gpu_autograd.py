@@ -166,3 +166,24 @@ def test_library_gradients_match_the_reference_golden():
     (Fp * torch.from_numpy(g["cdf/w"]).cuda()).sum().backward()
     assert _close(Fp, torch.from_numpy(g["cdf/F"]), 1e-5)
     assert _close(p.grad, torch.from_numpy(g["cdf/grad_p"]), 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alpha", [0.0, 0.1, 0.3])
+def test_fused_softmax_mix_equals_the_two_calls(alpha):
+    """model.safe_softmax_mix == mix_with_uniform(safe_softmax(.)) bit for bit (forward) and to float32 rounding
+    (backward), incl. rows with NaN / +-inf logits."""
+    need_gpu()
+    from attwarp_b200 import model as M
+    g = torch.Generator().manual_seed(17)
+    z = torch.randn(128, 24, generator=g) * 3
+    z[3, 5], z[4, 2], z[5, 1] = float("nan"), float("inf"), float("-inf")
+    w = torch.randn(128, 24, generator=g).cuda()
+    z1 = z.clone().cuda().requires_grad_(True)
+    z2 = z.clone().cuda().requires_grad_(True)
+    a = M.mix_with_uniform(M.safe_softmax(z1, dim=1, eps=1e-6), alpha)
+    b = M.safe_softmax_mix(z2, alpha)
+    assert torch.equal(a, b)
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    assert _close(z2.grad, z1.grad, 1e-6)

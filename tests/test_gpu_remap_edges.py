@@ -10,6 +10,7 @@ every row start at a different 16-byte phase."""
 
 import numpy as np
 import pytest
+import torch
 
 from gpu_util import dev, hwc, need_gpu
 from oracle import numpy_path as ON
