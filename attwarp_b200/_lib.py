@@ -55,6 +55,7 @@ SIGNATURES = {
     "attwarp_abi_version": (_i, []),
     "attwarp_last_error": (C.c_char_p, []),
     "attwarp_device_info": (_i, [C.POINTER(_i)] * 3),
+    "attwarp_set_sm_share": (_i, [_i]),
     "attwarp_aggregate_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "attwarp_aggregate_attention": (_i, [_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _f, _vp,
                                          _sz, _vp, _i, _f, _vp]),

@@ -33,15 +33,24 @@ class StreamRing:
         ring.join()                      # caller's stream waits for every ring stream
     """
 
-    def __init__(self, n: int = 4, device=None):
+    def __init__(self, n: int = 4, device=None, sm_share: int = 1):
+        """``sm_share=2``: between ``fork()`` and ``join()`` every launch of the two streaming kernels fills only
+        half of each SM (``attwarp_set_sm_share``), so that stage 1 of one batch and stage 5 of another are
+        co-resident on every SM instead of overlapping only at their ramps (83 vs 90 us per batch at
+        configs[1]; a single batch alone is slower that way, which is why it is not the default)."""
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, int(n)))]
         self.k = 0
+        self.sm_share = int(sm_share)
+        self._prev_share = None
 
     def fork(self):
         caller = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(caller)
+        if self.sm_share > 1:
+            from ._lib import load
+            self._prev_share = load().attwarp_set_sm_share(self.sm_share)
 
     def submit(self, fn):
         st = self.streams[self.k % len(self.streams)]
@@ -53,6 +62,10 @@ class StreamRing:
         caller = torch.cuda.current_stream(self.device)
         for s in self.streams:
             caller.wait_stream(s)
+        if self._prev_share is not None:
+            from ._lib import load
+            load().attwarp_set_sm_share(self._prev_share)
+            self._prev_share = None
 
 
 class HostBatchPipeline:

@@ -261,7 +261,7 @@ int aggregate_nsplit(int B, int L, int Hh) {
     }();
     const int n_rows = L * Hh;
     const int max_split = (n_rows + 2 * kAggWarps - 1) / (2 * kAggWarps);
-    int nsplit = forced > 0 ? forced : (4 * sm_count()) / (B > 0 ? B : 1);
+    int nsplit = forced > 0 ? forced : (4 * sm_count() / sm_share()) / (B > 0 ? B : 1);
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;
     return nsplit;

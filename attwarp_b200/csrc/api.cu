@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -56,6 +57,12 @@ int check_launch(const char* what) {
     if (e != cudaSuccess) return fail(ATTWARP_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
     return ATTWARP_OK;
 }
+
+// How much of an SM one launch of the two streaming kernels (stage 1, stage 5) may fill: 1 = all of it (lowest
+// latency for a single stream), 2 = half, so that kernels of two independent batches on different streams are
+// co-resident on every SM (stage 1 is HBM-bound, stage 5 issue-bound: together they use both).
+static std::atomic<int> g_sm_share{1};
+int sm_share() { return g_sm_share.load(std::memory_order_relaxed); }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -148,6 +155,12 @@ extern "C" {
 int attwarp_abi_version(void) { return ATTWARP_ABI_VERSION; }
 
 const char* attwarp_last_error(void) { return g_err; }
+
+int attwarp_set_sm_share(int share) {
+    if (share < 1) share = 1;
+    if (share > 4) share = 4;
+    return g_sm_share.exchange(share, std::memory_order_relaxed);
+}
 
 int attwarp_device_info(int* sm, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -31,6 +31,7 @@ int check_launch(const char* what);  // cudaGetLastError -> ATTWARP_ERR_CUDA
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int sm_count();
+int sm_share();          // attwarp_set_sm_share: 1 = a launch may fill the SMs, 2 = half of each SM, ...
 
 // ---- one image of a ragged batch (device table built by the launchers in remap_stream.cu / api.cu) ----
 struct RaggedImage {

@@ -45,7 +45,8 @@ using namespace ptx;
 
 constexpr int kMaxRing = 4;            // source-row stages / output tiles per CTA are launch parameters (2 .. 4)
 constexpr int kMaxRows = 16;          // capacity of a chunk table; the rows per chunk are a launch parameter
-constexpr int kRoleThreads = 64;      // producer warp + store warp
+// role warps: one producer warp + `store_warps` store warps (a launch parameter: wide strips with odd row pitches keep
+// several warps busy shifting rows on their way out)
 constexpr int kC = 3;
 
 extern __shared__ __align__(128) uint8_t smem[];
@@ -292,7 +293,7 @@ struct QuadArgs {
     int out_pitch;           // bytes per row of an output tile
     int rows;                // output rows per chunk (<= kMaxRows)
     int stages, tiles;       // ring depths: source-row stages (chunks whose loads are in flight), output tiles
-    int wave, skew_ppm;      // CTAs per wave (= SMs) and the share skew between the first and the last wave, 1e-6 units
+    int store_warps;         // store warps per CTA (rows of a tile are dealt round-robin to them)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
                              // 1: always QUAD, 2: LANE wherever word stores apply
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
@@ -357,7 +358,8 @@ __device__ __forceinline__ int first_image(const QuadArgs& a, int u0, int lane) 
 }
 
 // Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
-// blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads + 32 store threads.
+// blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads + 32 x store_warps
+// store threads.
 // Shared memory: [stages source arenas][tiles output tiles][stages chunk tables][tiles tile headers][mbarriers].
 // Chunk c lives in source stage c % stages and output tile c % tiles.  mbarriers:
 //   full[s]  producer -> consumers   table written, source rows landed (transaction bytes)
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const uint32_t sfree_s = full_s + 8u * kStages;
     const uint32_t odone_s = sfree_s + 8u * kStages;
     const uint32_t ofree_s = odone_s + 8u * kTiles;
-    const int n_cons_warps = ((int)blockDim.x - kRoleThreads) >> 5;
+    const int n_store_warps = a.store_warps;
+    const int n_cons_warps = ((int)blockDim.x >> 5) - 1 - n_store_warps;
     // LANE-mapping scratch: 1 KB per consumer warp at a 1 KB aligned shared address (the two 512-byte halves are
     // toggled with xor)
     const uint32_t scratch_s = (ofree_s + 8u * kTiles + 1023u) & ~1023u;
@@ -391,36 +394,18 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         }
         for (int s = 0; s < kTiles; ++s) {
             mbar_init(odone_s + 8u * s, n_cons_warps);
-            mbar_init(ofree_s + 8u * s, 1);
+            mbar_init(ofree_s + 8u * s, n_store_warps);
         }
         mbar_init_fence();
         trace_stamp(a, 0);                                   // CTA started
     }
     __syncthreads();
 
-    // Contiguous range of the cost axis for this CTA: it owns the tiles that START inside it.  The ranges are equal
-    // up to a measured skew: with several CTAs per SM the hardware favours the warps of the CTA that arrived first
-    // (CTAs 0 .. SMs-1 finish ~15 % ahead of CTAs 3 SMs .. 4 SMs-1 when all get the same rows, and the SM idles
-    // behind its last CTA), so CTA b of wave q = b / wave gets a share proportional to 1 + skew (1 - 2 q / (waves-1)).
-    int u0, u1;
-    if (a.skew_ppm == 0 || a.wave <= 0 || (int)gridDim.x <= a.wave) {
-        u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
-        u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
-    } else {
-        const int waves = ((int)gridDim.x + a.wave - 1) / a.wave;
-        auto cum = [&](int b) -> double {           // cumulative share of CTAs [0, b)
-            double c = 0.0;
-            for (int q = 0; q < waves; ++q) {
-                const int lo = q * a.wave, hi = min((q + 1) * a.wave, (int)gridDim.x);
-                const int n = max(0, min(b, hi) - lo);
-                c += n * (1.0 + a.skew_ppm * 1e-6 * (1.0 - 2.0 * q / (waves - 1)));
-            }
-            return c;
-        };
-        const double tot = cum((int)gridDim.x);
-        u0 = (int)((double)a.total_units * cum((int)blockIdx.x) / tot);
-        u1 = blockIdx.x + 1 == gridDim.x ? a.total_units : (int)((double)a.total_units * cum((int)blockIdx.x + 1) / tot);
-    }
+    // contiguous, balanced range of the cost axis for this CTA: it owns the tiles that START inside it
+    // (a share skewed towards the CTAs that reach an SM first -- they finish ~15 % ahead of the last ones, see
+    // profiles/r02g_cta_timeline_c2.txt -- was measured and is slower: 47.4 -> 49 us at configs[1])
+    const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
+    const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
 
     const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
@@ -592,7 +577,9 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 mbar_arrive(full_s + 8u * st);
             }
         } else {
-            // =============================== store warp ======================================
+            // =============================== store warps =====================================
+            // store warp k ships rows k, k + n_store_warps, ... of every tile
+            const int sw = warp_idx - n_cons_warps - 1;
             int ot = 0;
             uint32_t ph = 0;
             for (;;) {
@@ -613,17 +600,18 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     const int obuf = out_off0 + ot * out_bytes;
                     uint8_t* g0 = reinterpret_cast<uint8_t*>(((uint64_t)hs.y << 32) | hs.x);
                     const bool plain = ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len | (uintptr_t)dpitch) & 15) == 0;
-                    if (lane < n_rows) {
-                        uint8_t* g = g0 + (int64_t)lane * dpitch;
+                    const int my_row = sw + lane * n_store_warps;
+                    if (my_row < n_rows) {
+                        uint8_t* g = g0 + (int64_t)my_row * dpitch;
                         const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                         const int head = (16 - off) & 15;
                         const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
                         if ((off & 3) == 0 && body > 0)
-                            bulk_s2g(g + head, smem_s + (uint32_t)(obuf + lane * a.out_pitch + off + head), (uint32_t)body);
+                            bulk_s2g(g + head, smem_s + (uint32_t)(obuf + my_row * a.out_pitch + off + head), (uint32_t)body);
                     }
                     bulk_commit();
                     if (!plain) {
-                        for (int i = 0; i < n_rows; ++i) {
+                        for (int i = sw; i < n_rows; i += n_store_warps) {
                             uint8_t* g = g0 + (int64_t)i * dpitch;
                             const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
                             const int head = min((16 - off) & 15, len);
@@ -676,7 +664,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     bulk_wait_read0();                                 // the tile has left shared memory
                 }
                 __syncwarp();
-                if (lane == 0 && a.trace != nullptr) {
+                if (lane == 0 && sw == 0 && a.trace != nullptr) {
                     if (a.trace[(size_t)blockIdx.x * 8 + 4] == 0ull) trace_stamp(a, 4);   // first tile shipped
                     trace_stamp(a, 5);                                                     // latest tile shipped
                 }
@@ -861,8 +849,9 @@ struct Geometry {
     int warps;          // consumer warps per CTA
     int ctas;           // CTAs per SM the kernel is built for
     int max_cols;       // widest strip (multiple of 16)
+    int store_warps;    // store warps per CTA
 };
-constexpr Geometry kGeo[6] = {{3, 4, 352}, {6, 2, 704}, {11, 1, 1408}, {11, 2, 1408}, {3, 5, 352}, {6, 3, 704}};
+constexpr Geometry kGeo[3] = {{3, 4, 352, 1}, {6, 2, 704, 2}, {11, 1, 1408, 4}};
 
 struct StripPlan { int n_strips, strip_cols; };
 inline StripPlan plan_strips(int Wo, int max_cols_) {
@@ -879,10 +868,10 @@ int env_int(const char* name, int dflt) {
 }
 
 // geometry index for strips of `Wo`-wide outputs: the narrowest configuration that takes the image in one strip,
-// else the widest (ATTWARP_QUAD_GEO = 0 .. 5 forces one: tuning experiments)
+// else the widest (ATTWARP_QUAD_GEO = 0 .. 2 forces one: tuning experiments)
 int pick_geometry(int Wo) {
     const int forced = env_int("ATTWARP_QUAD_GEO", -1);
-    if (forced >= 0 && forced <= 5) return forced;
+    if (forced >= 0 && forced <= 2) return forced;
     for (int g = 0; g < 3; ++g)
         if (Wo <= kGeo[g].max_cols) return g;
     return 2;
@@ -890,7 +879,8 @@ int pick_geometry(int Wo) {
 
 template <int G>
 int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
-    constexpr int kThreads = kGeo[G].warps * 32 + kRoleThreads;
+    constexpr int kThreads = (kGeo[G].warps + 1 + kGeo[G].store_warps) * 32;
+    a.store_warps = kGeo[G].store_warps;
     auto kern = remap_u8_quad_kernel<kThreads, kGeo[G].ctas>;
     a.dbg = env_int("ATTWARP_REMAP_DBG", 0);
     a.out_pitch = (cols * kC + 15 + 15) & ~15;              // + the 16-byte phase of the destination
@@ -929,10 +919,11 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
         c = Cfg{smem_bytes, dev, o};
     }
     if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
-    const int64_t cap = (int64_t)sm_count() * c.occ;
+    // attwarp_set_sm_share(2): leave half of every SM to the kernels of another stream
+    const int share = sm_share();
+    const int occ = c.occ >= 2 * share ? c.occ / share : (c.occ >= 2 && share > 1 ? c.occ / 2 : c.occ);
+    const int64_t cap = (int64_t)sm_count() * occ;
     const int grid = (int)(a.total_units < cap ? a.total_units : cap);
-    a.wave = sm_count();
-    a.skew_ppm = env_int("ATTWARP_QUAD_SKEW_PPM", 60000);   // measured on B200 at 4 CTAs per SM (profiles/README.md)
     // ATTWARP_REMAP_TRACE=<file>: per-CTA global-timer stamps of every launch, appended to the file (debugging
     // only: synchronises the stream)
     const char* trace_path = getenv("ATTWARP_REMAP_TRACE");
@@ -970,9 +961,6 @@ int launch_by_geometry(int g, QuadArgs& a, int cols, cudaStream_t st) {
     switch (g) {
         case 0: return launch_geo<0>(a, cols, st);
         case 1: return launch_geo<1>(a, cols, st);
-        case 3: return launch_geo<3>(a, cols, st);
-        case 4: return launch_geo<4>(a, cols, st);
-        case 5: return launch_geo<5>(a, cols, st);
         default: return launch_geo<2>(a, cols, st);
     }
 }
@@ -1029,7 +1017,7 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     int pos = 0;
     for (int c = 0; c < kRaggedClasses; ++c) {
         plan->offset[c] = pos;
-        plan->geo[c] = forced >= 0 && forced <= 5 ? forced : kClassGeo[c];
+        plan->geo[c] = forced >= 0 && forced <= 2 ? forced : kClassGeo[c];
         pos += plan->count[c] + 1;
     }
     int fill[kRaggedClasses] = {0, 0, 0};

@@ -435,7 +435,7 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
     """configs[1] / configs[2]: uniform batches, every rank its own batch (weak scaling)."""
     import torch
 
-    from attwarp_b200 import ops, sharding
+    from attwarp_b200 import _lib, ops, sharding
     from attwarp_b200.batched import HostBatchPipeline, HostCopyProbe, HostTokenPipeline, StreamRing
 
     args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
@@ -476,21 +476,35 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
         ops.remap_bilinear(s["img"], mx, my, "hwc", out=s["out"])
         return 2
 
-    # one CUDA graph per resident buffer set: a step is ONE driver launch of its 2-3 kernels
-    launches_per_step = 3 if wl["has_attention"] else 2
-    graphs = None
-    if not args.no_graph:
-        graphs = [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
-
     # Consecutive steps are independent batches: they go round-robin over a few streams so that the
     # HBM-bound stage 1 of one step shares the GPU with the issue-bound stage 5 of the previous one.
     n_streams = args.streams if args.streams > 0 else (4 if wl["has_attention"] else 3)
     n_streams = max(1, min(n_streams, R))        # concurrent steps need distinct buffer sets
     ring = StreamRing(n_streams, dev) if n_streams > 1 else None
+    # ... and for them to be CO-RESIDENT on an SM each launch may fill only half of it (attwarp_set_sm_share; the
+    # grid size is part of a captured graph, so the graphs of the overlapped steps are captured in that mode)
+    lib = _lib.load()
+    sm_share = args.sm_share if args.sm_share > 0 else (2 if (wl["has_attention"] and ring is not None) else 1)
+
+    # one CUDA graph per resident buffer set: a step is ONE driver launch of its 2-3 kernels
+    launches_per_step = 3 if wl["has_attention"] else 2
+    graphs = graphs_single = None
+    if not args.no_graph:
+        prev_share = lib.attwarp_set_sm_share(sm_share)
+        graphs = [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets]
+        lib.attwarp_set_sm_share(prev_share)
+        # the single-stream figure runs graphs captured with whole-SM launches
+        graphs_single = graphs if sm_share == 1 else [ops.GraphedCall(lambda s=s: enqueue(s), device=dev) for s in sets[:3]]
 
     def run_step(i):
         if graphs is not None:
             graphs[i % R].replay()
+        else:
+            enqueue(sets[i % R])
+
+    def run_step_single(i):
+        if graphs_single is not None:
+            graphs_single[i % len(graphs_single)].replay()
         else:
             enqueue(sets[i % R])
 
@@ -503,6 +517,8 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
 
     fork = ring.fork if ring is not None else None
     join = ring.join if ring is not None else None
+    if args.no_graph and sm_share > 1:
+        lib.attwarp_set_sm_share(sm_share)             # eager launches read the mode at every launch
     if fork:
         fork()
     for i in range(args.warmup):
@@ -520,6 +536,7 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
     sus_steps = int(min(max(args.steps, 0.12e3 / max(elapsed_ms / args.steps, 1e-3)), 4000))
     sus_ms, _ = timed_steps(ctx, step, sus_steps, args.warmup + args.steps, fork, join)
     clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+    lib.attwarp_set_sm_share(1)
 
     n_done = args.warmup + args.steps + sus_steps
     chk = sharding.checksum64(sets[(n_done - 1) % R]["out"][:8])
@@ -529,7 +546,7 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
     worst_ms = max(s[0] for s in stats)
 
     # single-stream figure (one batch at a time: nothing of another step to overlap with)
-    one_ms, _ = timed_steps(ctx, lambda i: (run_step(i), launches_per_step)[1], max(args.steps, 20), 0)
+    one_ms, _ = timed_steps(ctx, lambda i: (run_step_single(i), launches_per_step)[1], max(args.steps, 20), 0)
     one_stats = sharding.gather_stats(one_ms, B * max(args.steps, 20), 0, dev)
 
     # ---- per-kernel durations, outside the timed region ---------------------------------------------
@@ -657,11 +674,14 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
            "single_stream": {"ms_per_step": max(s[0] for s in one_stats) / max(args.steps, 20),
                              "value": sharding.aggregate_throughput(one_stats),
                              "note": "one batch at a time on one stream (no overlap between steps)"},
-           "run": {"rotate": R, "streams": n_streams,
+           "run": {"rotate": R, "streams": n_streams, "sm_share": sm_share,
                    "launch": ("one CUDA graph replay per step" if graphs is not None else "eager launches") +
                              (f"; consecutive steps round-robin over {n_streams} CUDA streams (independent batches: "
-                              "the early stages of one step overlap stage 5 of the previous one)" if ring is not None else "")}}
-    del sets, graphs
+                              "the early stages of one step overlap stage 5 of the previous one)" if ring is not None else "") +
+                             ("; every launch of stage 1 / stage 5 fills half of each SM so that two steps are co-resident "
+                              "(attwarp_set_sm_share(2)); the single-stream figure and the per-kernel timings use whole-SM "
+                              "launches" if sm_share > 1 else "")}}
+    del sets, graphs, graphs_single
     torch.cuda.empty_cache()
     return res
 
@@ -926,6 +946,7 @@ def main():
                          "`workloads`; or one workload alone")
     ap.add_argument("--rotate", type=int, default=0, help="resident input buffer sets to rotate over (default 8 with attention, else 4)")
     ap.add_argument("--streams", type=int, default=0, help="CUDA streams consecutive steps alternate over (default 4 with attention, else 3)")
+    ap.add_argument("--sm-share", type=int, default=0, help="attwarp_set_sm_share for the overlapped steps (default 2 with attention and several streams, else 1)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="images per host-pipeline chunk (default 64 at 336^2, 16 at 1344^2)")
     ap.add_argument("--c4-steps", type=int, default=0, help="steps of the c4 workload (default: min(--steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -75,6 +75,13 @@ int attwarp_abi_version(void);
 const char* attwarp_last_error(void);
 /* Number of SMs of the current device and whether it is compute capability 10.x. */
 int attwarp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* How much of each SM one launch of the two streaming kernels (stage 1 aggregation, stage 5 resample) may occupy.
+ * 1 (default): the whole SM -- the lowest latency for one batch at a time.  2: half, so that the kernels of two
+ * independent batches enqueued on different streams are co-resident on every SM (stage 1 is HBM-bound and leaves
+ * issue slots idle, stage 5 the opposite): +9 % images/s at BASELINE configs[1] over four streams, at the price of a
+ * slower single batch.  Process-wide, read at every launch; returns the previous value.  (No reference counterpart:
+ * the reference warps one image at a time on the host.) */
+int attwarp_set_sm_share(int share);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- attention aggregation.

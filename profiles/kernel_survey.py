@@ -69,7 +69,23 @@ A = torch.rand(128, 1, 512, 512, device=dev, generator=g)
 report("gt_marginals 128 x 512^2 f32", lambda: CU.gt_marginals(A), A.numel() * 4)
 report("adaptive_avg_pool2d 128 x 512^2 -> 24^2", lambda: CU.adaptive_avg_pool2d_24(A), A.numel() * 4)
 px = torch.softmax(torch.randn(128, 24, device=dev, generator=g), -1)
-report("safe_softmax + mix_with_uniform [128,24]", lambda: M.mix_with_uniform(M.safe_softmax(px), 0.1))
+report("safe_softmax + mix_with_uniform [128,24] (two calls)", lambda: M.mix_with_uniform(M.safe_softmax(px), 0.1))
+report("safe_softmax_mix [128,24] (one launch)", lambda: M.safe_softmax_mix(px, 0.1))
+from attwarp_b200 import trainer as TR  # noqa: E402
+py_ = torch.softmax(torch.randn(128, 24, device=dev, generator=g), -1)
+gx_ = torch.softmax(torch.randn(128, 24, device=dev, generator=g), -1)
+gy_ = torch.softmax(torch.randn(128, 24, device=dev, generator=g), -1)
+report("pdf_l1_loss forward [128,24]x2 -> 512^2 (one launch)", lambda: TR.pdf_l1_loss(px, py_, gx_, gy_, (512, 512)))
+pxg = px.clone().requires_grad_(True)
+def _fb():
+    pxg.grad = None
+    TR.pdf_l1_loss(pxg, py_, gx_, gy_, (512, 512)).backward()
+report("pdf_l1_loss forward + backward", _fb)
+# live hook logger step (cached offsets tensor)
+from attwarp_b200 import attention_extraction as AE  # noqa: E402
+lg = AE.BatchMaskHookLogger(None, dev)
+lg.set_batch_image_token_ranges([int(x) for x in starts.tolist()], [int(x) + 576 for x in starts.tolist()])
+report("BatchMaskHookLogger._process_attention [16,32,64,700] fp16", lambda: lg._process_attention(att))
 up = CU.upsample_pdf_right_inverse(px, 512)
 report("upsample_pdf_right_inverse [128,24] -> 512", lambda: CU.upsample_pdf_right_inverse(px, 512))
 F = CU.cdf_from_density(up.clamp_min(0))
