@@ -235,27 +235,34 @@ def test_fused_path_on_second_device():
 
 def test_sm_share_changes_grids_not_results():
     """attwarp_set_sm_share(2) (half an SM per launch of stage 1 / stage 5, for co-resident batches on several
-    streams) only changes launch geometry: same bytes; StreamRing(sm_share=2) restores the previous mode."""
+    streams) only changes launch geometry: stage 5 gives the same bytes for the same maps, stage 1 the same token
+    maps up to the float32 order of its split sums; StreamRing(sm_share=2) restores the previous mode."""
     need_gpu()
     from attwarp_b200 import _lib, ops
     from attwarp_b200.batched import StreamRing
     B, L, Hh, g, H = 40, 32, 32, 24, 336
     attn = _attention(B, L, Hh, g * g, torch.bfloat16, seed=5).cuda()
     imgs = torch.from_numpy(np.random.default_rng(5).integers(0, 256, (B, H, H, 3), dtype=np.uint8)).cuda()
-    ref, tok_ref, _, _ = ops.warp_from_attention_tokens(attn, imgs, (g, g), return_aux=True)
+    tok_ref = ops.aggregate_attention(attn)
+    mx, my = ops.maps_from_tokens(tok_ref.view(B, g, g), (H, H))
+    ref = ops.remap_bilinear(imgs, mx, my, "hwc")
     lib = _lib.load()
     prev = lib.attwarp_set_sm_share(2)
     try:
-        out, tok, _, _ = ops.warp_from_attention_tokens(attn, imgs, (g, g), return_aux=True)
+        tok = ops.aggregate_attention(attn)
+        out = ops.remap_bilinear(imgs, mx, my, "hwc")
     finally:
         assert lib.attwarp_set_sm_share(prev) == 2
     assert torch.equal(out, ref)
-    assert rel_err(tok.cpu().numpy(), tok_ref.cpu().numpy(), floor=1e-12) <= 1e-6      # split count differs: fp32 sum order
+    assert rel_err(tok.cpu().numpy(), tok_ref.cpu().numpy(), floor=1e-12) <= 1e-6
     ring = StreamRing(3, sm_share=2)
     ring.fork()
-    outs = [ring.submit(lambda: ops.warp_from_attention_tokens(attn, imgs, (g, g))) for _ in range(3)]
+    outs = [ring.submit(lambda: ops.remap_bilinear(imgs, mx, my, "hwc")) for _ in range(3)]
+    fused = ring.submit(lambda: ops.warp_from_attention_tokens(attn, imgs, (g, g)))
     ring.join()
     torch.cuda.synchronize()
     assert lib.attwarp_set_sm_share(1) == 1
     for o in outs:
         assert torch.equal(o, ref)
+    d = (fused.to(torch.int16) - ref.to(torch.int16)).abs()
+    assert int(d.max()) <= 8 and float((d != 0).float().mean()) <= 5e-3     # a few rint(32 x) flips from the split order
