@@ -92,6 +92,10 @@ int launch_pdf_l1_loss_backward(const float* px, const float* py, const float* g
 bool remap_quad_enabled();
 int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, int Ho, int Wo, const float* map_x,
                          const float* map_y, cudaStream_t st);
+// float32 images through remap_f32_stream.cu (ATTWARP_ERR_UNSUPPORTED: shape not taken, use the rows kernel)
+bool remap_f32_stream_enabled();
+int launch_remap_f32_stream(const float* src, float* dst, int n_planes, int E, int H, int W, int Ho, int Wo,
+                            const float* map_x, const float* map_y, int map_div, cudaStream_t st);
 // ragged: images grouped into width classes (one launch each); dev_main holds n + 1 entries in batch order,
 // dev_sorted n + kRaggedClasses entries grouped by class
 constexpr int kRaggedClasses = 3;

@@ -248,6 +248,12 @@ int launch_remap(const void* src, void* dst, int dtype, int layout, int B, int C
         return launch_direct<uint8_t>(src, dst, layout, B, C, H, W, Ho, Wo, map_x, map_y, st);
     if (dtype == ATTWARP_F32) {
         const int64_t planes = layout == ATTWARP_LAYOUT_HWC ? B : (int64_t)B * C;
+        if (!force_direct() && remap_f32_stream_enabled() && planes <= 0x7fffffff) {
+            const bool hwc = layout == ATTWARP_LAYOUT_HWC;
+            const int rc = launch_remap_f32_stream(static_cast<const float*>(src), static_cast<float*>(dst), (int)planes,
+                                                   hwc ? C : 1, H, W, Ho, Wo, map_x, map_y, hwc ? 1 : C, st);
+            if (rc != ATTWARP_ERR_UNSUPPORTED) return rc;
+        }
         if (!force_direct() && planes <= 65535 && (int64_t)Wo * C < 0x7fffffff && (int64_t)H * W * C < 0x7fffffff)
             return launch_f32_rows(static_cast<const float*>(src), static_cast<float*>(dst), layout, B, C, H, W,
                                    Ho, Wo, map_x, map_y, st);

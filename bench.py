@@ -862,9 +862,9 @@ def bench_pdf(ctx):
     tokr = torch.rand(B, N, N, device=dev, generator=gen) ** 3
     hx, hy = ops.maps_from_tokens((tokr / tokr.sum(dim=(1, 2), keepdim=True)).contiguous(), (side, side))
     kms, hms = kernel_ms(mx, my), kernel_ms(hx, hy)
-    kernels = {"remap_f32_rows_kernel": {"ms": kms, "algorithmic_bytes": by, "achieved_gbs": by / kms / 1e6,
+    kernels = {"remap_f32_stream_kernel": {"ms": kms, "algorithmic_bytes": by, "achieved_gbs": by / kms / 1e6,
                                          "frac": by / kms / 1e6 / ctx.peak, "maps": "PDF maps of the step (alpha = 0.1)"},
-               "remap_f32_rows_kernel@rand3_token_maps": {"ms": hms, "algorithmic_bytes": by,
+               "remap_f32_stream_kernel@rand3_token_maps": {"ms": hms, "algorithmic_bytes": by,
                                                           "achieved_gbs": by / hms / 1e6, "frac": by / hms / 1e6 / ctx.peak,
                                                           "maps": "maps of rand^3 24x24 token grids"}}
     hard = max(kernels, key=lambda k: kernels[k]["ms"])
@@ -872,9 +872,9 @@ def bench_pdf(ctx):
            "launches": launches * world, "kernels": kernels, "clocks": clocks, "e2e": None,
            "sustained": {"steps": sus_steps, "ms_per_step": max(s[0] for s in sus_stats) / sus_steps,
                          "value": sharding.aggregate_throughput(sus_stats)},
-           "roofline": {"bound": "hbm", "kernel": "remap_f32_rows_kernel", "achieved": kernels[hard]["achieved_gbs"],
+           "roofline": {"bound": "hbm", "kernel": "remap_f32_stream_kernel", "achieved": kernels[hard]["achieved_gbs"],
                         "peak": ctx.peak, "unit": "GB/s", "frac": kernels[hard]["frac"],
-                        "traffic": ncu_traffic("remap_f32_rows_kernel", "c5"), "peak_source": ctx.peak_src,
+                        "traffic": ncu_traffic("remap_f32_stream_kernel", "c5"), "peak_source": ctx.peak_src,
                         "algorithmic_bytes_per_launch": by, "kernel_ms": kernels[hard]["ms"],
                         "selection": "the slower of the two map families (" + kernels[hard]["maps"] + ")"},
            "run": {"rotate": R, "streams": n_streams,
