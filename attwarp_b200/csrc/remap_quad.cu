@@ -59,7 +59,8 @@ __device__ __forceinline__ void st128(int off, uint4 v) { *reinterpret_cast<uint
 //   +0   uint4 {n_rows, n_slots | flags << 16, slot_pitch, byte offset of slot 0's first byte in the arena}
 //              n_rows 0: output row y0 takes the direct path; -1: stop
 //   +16  uint4 {img, x_first, y0, c_lo}
-//   +32  uint4 {address of the chunk's first output byte (lo, hi), bytes per tile row, Wo * 3}
+//   +32  uint4 {address of the chunk's first output byte -- DIRECT: of the image's -- (lo, hi), bytes per strip row,
+//               Wo * 3}
 //   +48  uint4 {address of map_x[x_first] (lo, hi), W, columns in the strip}      (new strip only)
 //   +64  uint4 row[kMaxRows + 1]:  x = wE << 14, y = wO << 14  (weights of the even / odd source row)
 //                                  z = byte offset of the row inside the output tile: row * pitch + (address of the
@@ -165,6 +166,56 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "@pv st.shared.b32 [o], q4;\n"                              \
     "@pv st.shared.b32 [o+4], q5;\n"                            \
     "@pv st.shared.b32 [o+8], q1;\n"
+// DIRECT stores (every destination row 4-byte aligned, no output tile, no store warp): the warp's 384 output bytes of
+// a row change hands through the scratch so that lane t ends up with WORDS t, t + 32, t + 64 of them -- three
+// fully coalesced 128-byte global stores per row.  %49 = address of the warp's first destination byte at row offset
+// 0 (64-bit), %50 = 4 * lane, bits 0..2 of %53 = word k lies inside the strip.
+//   QUAD mapping: packed words to P + 12 * lane (%51), back from P + 4 * lane (%52)
+#define AWQ_DIRECT_ADDR                                         \
+    "cvt.u64.u32 ro64, ez;\n"                                   \
+    "add.u64 oa, %49, ro64;\n"                                  \
+    "cvt.u64.u32 ro64, %50;\n"                                  \
+    "add.u64 oa, oa, ro64;\n"
+#define AWQ_EMIT_WD                                             \
+    AWQ_VBLEND                                                  \
+    "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
+    "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
+    "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
+    "prmt.b32 q3, vc0, vc1, 0x0073;\n"                          \
+    "prmt.b32 q4, vc2, vd0, 0x0073;\n"                          \
+    "prmt.b32 q5, vd1, vd2, 0x0073;\n"                          \
+    "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
+    "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
+    "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
+    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
+    AWQ_DIRECT_ADDR                                             \
+    "xor.b32 pw, pw, 512;\n xor.b32 pr, pr, 512;\n"             \
+    "@pw0 st.global.b32 [oa], q0;\n"                            \
+    "@pw1 st.global.b32 [oa+128], q1;\n"                        \
+    "@pw2 st.global.b32 [oa+256], q2;\n"
+//   LANE mapping: RGBX pixels to X + 4 * lane (+ 128 j), word k of the lane = bytes of two adjacent RGBX pixels
+//   (addresses xa0..2, byte selectors xs0..2: per-lane constants)
+#define AWQ_EMIT_LD                                             \
+    AWQ_VBLEND                                                  \
+    "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
+    "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
+    "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
+    "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
+    "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
+    "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
+    "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
+    AWQ_DIRECT_ADDR                                             \
+    "xor.b32 sx, sx, 512;\n xor.b32 xa0, xa0, 512;\n xor.b32 xa1, xa1, 512;\n xor.b32 xa2, xa2, 512;\n" \
+    "prmt.b32 q0, q0, q1, xs0;\n"                               \
+    "prmt.b32 q2, q2, q3, xs1;\n"                               \
+    "prmt.b32 q4, q4, q5, xs2;\n"                               \
+    "@pw0 st.global.b32 [oa], q0;\n"                            \
+    "@pw1 st.global.b32 [oa+128], q2;\n"                        \
+    "@pw2 st.global.b32 [oa+256], q4;\n"
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  The entry of the row AFTER the
 // one being emitted is requested before the emit, so the loop-carried compare never waits for a shared-memory load
 // (the entry after the sentinel is read too: still inside the CTA's shared memory, never used)
@@ -183,7 +234,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
     ".reg .pred p, q, pv, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq;\n"                 \
+    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq, pw, pr, xa0, xa1, xa2, xs0, xs1, xs2, tm;\n" \
+    ".reg .pred pw0, pw1, pw2;\n"                               \
+    ".reg .b64 ro64, oa;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
     ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
     ".reg .b32 ka, kb, kc, kd, ua, ub, uc, ud, sa, sb, sc, sd, ma, mb, mc, md, na, nb, nc, nd;\n" \
@@ -203,6 +256,12 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
     "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
+    "mov.b32 pw, %51;\n mov.b32 pr, %52;\n"                     \
+    "mov.b32 xa0, %54;\n mov.b32 xa1, %55;\n mov.b32 xa2, %56;\n"      \
+    "mov.b32 xs0, %57;\n mov.b32 xs1, %58;\n mov.b32 xs2, %59;\n"      \
+    "and.b32 tm, %53, 1;\n setp.ne.u32 pw0, tm, 0;\n"           \
+    "and.b32 tm, %53, 2;\n setp.ne.u32 pw1, tm, 0;\n"           \
+    "and.b32 tm, %53, 4;\n setp.ne.u32 pw2, tm, 0;\n"           \
     "setp.ne.u32 pv, %40, 0;\n"                                 \
     "setp.ne.u32 podd, %39, 0;\n"                               \
     "mov.b32 rp, %37;\n"                                        \
@@ -257,23 +316,34 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
       "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "+r"(O[9]), "+r"(O[10]), "+r"(O[11])      \
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
       "r"(n_slots), "r"(sx), "r"(sq), "r"(0), "r"(pitch), "r"(rp), "r"(ocol), "r"(odd_first), "r"(store_ok),  \
-      "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3])        \
+      "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3]),       \
+      "l"(d.obase), "r"(d.lane4), "r"(d.pw), "r"(d.pr), "r"(d.wmask), "r"(d.xa[0]), "r"(d.xa[1]), "r"(d.xa[2]),    \
+      "r"(d.xs[0]), "r"(d.xs[1]), "r"(d.xs[2])                                                              \
     : "memory"
 
+// what the DIRECT emit variants need besides the tile variants' operands (see AWQ_EMIT_WD / AWQ_EMIT_LD)
+struct DirectOps {
+    uint64_t obase;
+    uint32_t lane4, pw, pr, wmask, xa[3], xs[3];
+};
+
 // FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
-// LANE: false = QUAD mapping, true = LANE mapping (both end in three aligned word stores per thread and row).
-template <bool FIXED, bool LANE>
+// LANE: false = QUAD mapping, true = LANE mapping.  DIRECT: rows go straight to global memory (three coalesced word
+// stores per lane), else into the output tile (three aligned word stores at the QUAD position).
+template <bool FIXED, bool LANE, bool DIRECT>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
                                            const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
                                            uint32_t rp, uint32_t ocol, uint32_t odd_first, uint32_t store_ok,
-                                           uint32_t sx, uint32_t sq) {
+                                           uint32_t sx, uint32_t sq, const DirectOps& d) {
+#define AWQ_RUN(BODY, EMIT) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE BODY(EMIT) AWQ_EPILOGUE "}\n" AWQ_OPERANDS)
     if (FIXED) {
-        if (!LANE) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_F(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (!DIRECT) { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_W); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_L); }
+        else { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_LD); }
     } else {
-        if (!LANE) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_W) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
-        else asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE AWQ_BODY_V(AWQ_EMIT_L) AWQ_EPILOGUE "}\n" AWQ_OPERANDS);
+        if (!DIRECT) { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_W); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_L); }
+        else { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_LD); }
     }
+#undef AWQ_RUN
 }
 
 struct QuadArgs {
@@ -369,10 +439,12 @@ __device__ __forceinline__ int first_image(const QuadArgs& a, int u0, int lane) 
 //   sfree[s] consumers -> producer   every consumer warp is done with the stage's rows and table
 //   odone[o] consumers -> store warp every consumer warp has written its columns of the tile
 //   ofree[o] store warp -> consumers the tile has been read out of shared memory
-template <int MAXT, int MINB>
+// DIRECT (every destination row of the launch is 4-byte aligned): no output tiles, no store warps -- the consumers
+// write their rows to global memory themselves (AWQ_EMIT_WD / AWQ_EMIT_LD).
+template <int MAXT, int MINB, bool DIRECT>
 __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArgs a) {
     const int R = a.rows;
-    const int kStages = a.stages, kTiles = a.tiles;
+    const int kStages = a.stages, kTiles = DIRECT ? 0 : a.tiles;
     const int out_bytes = R * a.out_pitch;
     const int out_off0 = kStages * a.stage_bytes;
     const int tab_off0 = out_off0 + kTiles * out_bytes;
@@ -383,10 +455,10 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const uint32_t sfree_s = full_s + 8u * kStages;
     const uint32_t odone_s = sfree_s + 8u * kStages;
     const uint32_t ofree_s = odone_s + 8u * kTiles;
-    const int n_store_warps = a.store_warps;
+    const int n_store_warps = DIRECT ? 0 : a.store_warps;
     const int n_cons_warps = ((int)blockDim.x >> 5) - 1 - n_store_warps;
-    // LANE-mapping scratch: 1 KB per consumer warp at a 1 KB aligned shared address (the two 512-byte halves are
-    // toggled with xor)
+    // per consumer warp 2 KB of scratch at a 1 KB aligned shared address: two 512-byte RGBX buffers (LANE mapping)
+    // and two 512-byte packed-row buffers (DIRECT stores), each pair toggled with xor 512
     const uint32_t scratch_s = (ofree_s + 8u * kTiles + 1023u) & ~1023u;
 
     if (threadIdx.x == 0) {
@@ -541,9 +613,12 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     if (lane < n_rows) {
                         const uint32_t wu = (uint32_t)wa << 14, wl_ = (uint32_t)(32 - wa) << 14;   // upper / lower tap
                         const bool up_even = (ra & 1) == 0;
+                        // z: tile mode -> offset of the row in the output tile; DIRECT -> offset of the row's first
+                        // byte (of this strip) from the image's first destination byte
                         st128(tab + kTabRows + 16 * lane,
                               make_uint4(up_even ? wu : wl_, up_even ? wl_ : wu,
-                                         (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 12),
+                                         DIRECT ? (uint32_t)(gd - dimg)
+                                                : (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 12),
                                          (uint32_t)(ra + 1 - r_lo)));
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, 0u, kRowSentinel));
@@ -553,7 +628,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                         st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (fl << 16),
                                               (uint32_t)slot_pitch, (uint32_t)phase0));
                         st128(tab + 16, make_uint4((uint32_t)img, (uint32_t)x_first, (uint32_t)y_cur, (uint32_t)c_lo));
-                        st128(tab + kTabStore, make_uint4((uint32_t)gd, (uint32_t)((uint64_t)gd >> 32),
+                        const uintptr_t gbase = DIRECT ? dimg : gd;         // DIRECT: the image, else the chunk's first row
+                        st128(tab + kTabStore, make_uint4((uint32_t)gbase, (uint32_t)((uint64_t)gbase >> 32),
                                                           (uint32_t)(ncols * kC), (uint32_t)(Wo * kC)));
                         if (seg_flags & kFlagNewStrip) {
                             const uintptr_t mxa = reinterpret_cast<uintptr_t>(mx);
@@ -701,8 +777,22 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     bool lane_map = false;            // this warp runs the LANE mapping in the current strip
     uint32_t store_ok = 0u;           // this thread stores at least one column (QUAD position)
     const int out_col = x0 * kC;
-    const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
-    const uint32_t sq_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 16);    //          my four adjacent pixels out
+    const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 2048 + lane * 4);     // scratch: my RGBX pixels in
+    const uint32_t sq_s = scratch_s + (uint32_t)(warp_idx * 2048 + lane * 16);    //          my four adjacent pixels out
+    DirectOps dops{};
+    if (DIRECT) {
+        dops.lane4 = 4u * (uint32_t)lane;
+        dops.pw = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + lane * 12);     // packed row: my 12 bytes in
+        dops.pr = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + lane * 4);      //             my three words out
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // output word w = lane + 32 k of the warp's row = bytes 4 w .. 4 w + 3 of the RGB stream: pixel
+            // p0 = floor(4 w / 3) (and the next one), starting at channel 4 w - 3 p0
+            const int w = lane + 32 * k, p0 = (4 * w) / 3, c0 = 4 * w - 3 * p0;
+            dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 2048 + 4 * p0);
+            dops.xs[k] = c0 == 0 ? 0x4210u : (c0 == 1 ? 0x5421u : 0x6542u);
+        }
+    }
     int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
 
     // per-strip setup: taps and weights of this thread's columns, choice of the mapping
@@ -769,11 +859,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         if (tid == 0 && a.trace != nullptr && a.trace[(size_t)blockIdx.x * 8 + 2] == 0ull) trace_stamp(a, 2);   // first rows landed
         const uint4 h0 = ld128(tab);
         const int n_rows = (int)h0.x;
-        wait(ofree_s + 8u * ot, oph);                                       // tile shipped and free
+        if (!DIRECT) wait(ofree_s + 8u * ot, oph);                          // tile shipped and free
         if (n_rows < 0) {                                                        // pass the stop on
-            if (tid == 0) st128(ohdr_off0 + 32 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(odone_s + 8u * ot);
+            if (!DIRECT) {
+                if (tid == 0) st128(ohdr_off0 + 32 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(odone_s + 8u * ot);
+            }
             break;
         }
         const uint32_t flags = h0.y >> 16;
@@ -788,7 +880,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
 #pragma unroll
             for (int j = 0; j < 4; ++j) wo[j] = xba[j] < 0 ? 0 : (xba[j] - (int)h1.w) * kC;
         }
-        if (tid == 0) {                                      // what the store warp needs to ship the tile
+        if (!DIRECT && tid == 0) {                           // what the store warp needs to ship the tile
             st128(ohdr_off0 + 32 * ot, make_uint4(h0.x, 0u, 0u, 0u));
             st128(ohdr_off0 + 32 * ot + 16, ld128(tab + kTabStore));
         }
@@ -823,6 +915,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             const uint32_t base = smem_s + (uint32_t)(st * a.stage_bytes) + h0.w;    // first byte of slot 0
             const uint32_t odd = (flags & kFlagOddFirst) ? 1u : 0u;
             uint32_t win[4], sh[4];
+            if (DIRECT) {
+                // the warp's 384 bytes of a row start 384 * warp bytes after the strip's first byte
+                const uint4 hs = ld128(tab + kTabStore);                         // {image lo, hi, strip row bytes, -}
+                dops.obase = (((uint64_t)hs.y << 32) | hs.x) + (uint64_t)(warp_idx * 384);
+                const int nb = (int)hs.z - warp_idx * 384;                       // bytes of the warp's block in the strip
+                dops.wmask = (4 * lane + 4 <= nb ? 1u : 0u) | (4 * lane + 132 <= nb ? 2u : 0u) | (4 * lane + 260 <= nb ? 4u : 0u);
+            }
             if (flags & kFlagFixedShift) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -830,17 +929,17 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (!lane_map) sweep_quad<true, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else sweep_quad<true, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                if (!lane_map) sweep_quad<true, false, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
+                else sweep_quad<true, true, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (!lane_map) sweep_quad<false, false>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
-                else sweep_quad<false, true>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s);
+                if (!lane_map) sweep_quad<false, false, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
+                else sweep_quad<false, true, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
             }
         }
         // publish this warp's part of the tile to the async proxy, then count the warp in
-        fence_proxy_async();
+        if (!DIRECT) fence_proxy_async();
         __syncwarp();
         if (tid == 0 && a.trace != nullptr) {
             if (a.trace[(size_t)blockIdx.x * 8 + 3] == 0ull) trace_stamp(a, 3);   // first chunk swept (warp 0)
@@ -848,7 +947,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         }
         if (lane == 0) {
             mbar_arrive(sfree_s + 8u * st);
-            mbar_arrive(odone_s + 8u * ot);
+            if (!DIRECT) mbar_arrive(odone_s + 8u * ot);
         }
     }
 }
@@ -862,7 +961,8 @@ struct Geometry {
     int max_cols;       // widest strip (multiple of 16)
     int store_warps;    // store warps per CTA
 };
-constexpr Geometry kGeo[3] = {{3, 4, 352, 1}, {6, 2, 704, 2}, {11, 1, 1408, 4}};
+constexpr Geometry kGeo[3] = {{3, 4, 352, 1}, {6, 2, 704, 2}, {11, 1, 1408, 4}};      // with output tiles
+constexpr Geometry kGeoD[3] = {{3, 5, 352, 0}, {6, 2, 704, 0}, {11, 1, 1408, 0}};     // DIRECT stores
 
 struct StripPlan { int n_strips, strip_cols; };
 inline StripPlan plan_strips(int Wo, int max_cols_) {
@@ -888,25 +988,26 @@ int pick_geometry(int Wo) {
     return 2;
 }
 
-template <int G>
+template <int G, bool DIRECT>
 int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
-    constexpr int kThreads = (kGeo[G].warps + 1 + kGeo[G].store_warps) * 32;
-    a.store_warps = kGeo[G].store_warps;
-    auto kern = remap_u8_quad_kernel<kThreads, kGeo[G].ctas>;
+    constexpr Geometry geo = DIRECT ? kGeoD[G] : kGeo[G];
+    constexpr int kThreads = (geo.warps + 1 + geo.store_warps) * 32;
+    a.store_warps = geo.store_warps;
+    auto kern = remap_u8_quad_kernel<kThreads, geo.ctas, DIRECT>;
     a.dbg = env_int("ATTWARP_REMAP_DBG", 0);
     a.out_pitch = (cols * kC + 15 + 15) & ~15;              // + the 16-byte phase of the destination
     const int unit_pitch = (((cols + 1) * kC + 45 + 15) & ~15) + 16;      // a slot at unit scale
     // ring depths (ATTWARP_QUAD_RING = stages * 10 + tiles, tuning experiments) and rows per chunk: as many as the
     // shared memory of 1 / ctas of an SM holds (stages of R + 2 slots, tiles of R rows), at most kMaxRows
-    int stages = 2, tiles = 2;
+    int stages = 2, tiles = DIRECT ? 0 : 2;
     {
         const int ring = env_int("ATTWARP_QUAD_RING", 0);
-        if (ring / 10 >= 2 && ring / 10 <= kMaxRing && ring % 10 >= 2 && ring % 10 <= kMaxRing) { stages = ring / 10; tiles = ring % 10; }
+        if (ring / 10 >= 2 && ring / 10 <= kMaxRing && ring % 10 >= 2 && ring % 10 <= kMaxRing) { stages = ring / 10; tiles = DIRECT ? 0 : ring % 10; }
     }
     a.stages = stages;
     a.tiles = tiles;
-    const int budget = (227 * 1024) / kGeo[G].ctas - 1024 - stages * kTabBytes - tiles * 32 - 16 * kMaxRing - 256 -
-                       1024 * (kGeo[G].warps + 1);
+    const int scratch = 2048 * geo.warps + 1024;
+    const int budget = (227 * 1024) / geo.ctas - 1024 - stages * kTabBytes - tiles * 32 - 16 * kMaxRing - 256 - scratch;
     int R = (budget - stages * (2 * unit_pitch + 64 + 128)) / (stages * unit_pitch + tiles * a.out_pitch);
     R = R > kMaxRows ? kMaxRows : R;
     const int forced = env_int("ATTWARP_QUAD_ROWS", 0);
@@ -915,7 +1016,7 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
     a.rows = R;
     a.stage_bytes = ((R + 2) * unit_pitch + 64 + 127) & ~127;
     const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + (size_t)tiles * ((size_t)R * a.out_pitch + 32) +
-                              2 * (size_t)(stages + tiles) * sizeof(uint64_t) + 16 + 1024 * (size_t)(kGeo[G].warps + 1);
+                              2 * (size_t)(stages + tiles) * sizeof(uint64_t) + 16 + (size_t)scratch;
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     a.wait_hint_ns = env_int("ATTWARP_QUAD_WAIT_HINT", 0);
     a.roles_first = env_int("ATTWARP_QUAD_ROLES_FIRST", 0);
@@ -970,12 +1071,26 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
     return check_launch("remap_u8_quad_kernel");
 }
 
-int launch_by_geometry(int g, QuadArgs& a, int cols, cudaStream_t st) {
-    switch (g) {
-        case 0: return launch_geo<0>(a, cols, st);
-        case 1: return launch_geo<1>(a, cols, st);
-        default: return launch_geo<2>(a, cols, st);
+// direct: every destination row of the launch is 4-byte aligned (no output tile, consumers store to global memory)
+int launch_by_geometry(int g, bool direct, QuadArgs& a, int cols, cudaStream_t st) {
+    if (direct) {
+        switch (g) {
+            case 0: return launch_geo<0, true>(a, cols, st);
+            case 1: return launch_geo<1, true>(a, cols, st);
+            default: return launch_geo<2, true>(a, cols, st);
+        }
     }
+    switch (g) {
+        case 0: return launch_geo<0, false>(a, cols, st);
+        case 1: return launch_geo<1, false>(a, cols, st);
+        default: return launch_geo<2, false>(a, cols, st);
+    }
+}
+
+// ATTWARP_QUAD_DIRECT=0 keeps the output tiles + store warps for aligned images too (A/B comparisons)
+bool direct_allowed() { return env_int("ATTWARP_QUAD_DIRECT", 1) != 0; }
+inline bool rows_word_aligned(const void* dst, int Wo) {
+    return ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)(Wo * kC)) & 3) == 0;
 }
 
 }  // namespace
@@ -1008,16 +1123,18 @@ int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, in
     const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
     if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
     a.total_units = (int)total;
-    return launch_by_geometry(g, a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
+    return launch_by_geometry(g, direct_allowed() && rows_word_aligned(dst, Wo), a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
 }
 
 // Ragged batch.  Images are grouped into width classes, one launch per class with the geometry that fits it
 // (a 300-wide image in a CTA built for 1408 columns would leave eight of its eleven consumer warps idle):
-//   class 0: Wo <= 352 (3 consumer warps per CTA), class 1: Wo <= 704 (6), class 2: wider (11; strips of <= 1408).
+//   class 0: Wo <= 352 (3 consumer warps per CTA), class 1: Wo <= 704 (6), class 2: wider (11; strips of <= 1408);
+//   classes 3..5: the same widths for images whose destination rows are not 4-byte aligned (output tiles + store
+//   warps instead of direct stores).
 // Step 1: `host` (n + 1 entries, batch order) gets each image's strip plan and is uploaded to dev_main (the maps
 // kernel reads shapes and map pointers from it); a copy grouped by class, every group followed by an entry that
 // carries its unit total, is uploaded to dev_sorted (n + 3 entries).
-constexpr int kClassGeo[kRaggedClasses] = {0, 1, 2};
+constexpr int kClassGeo[3] = {0, 1, 2};
 inline int width_class(int Wo) { return Wo <= kGeo[kClassGeo[0]].max_cols ? 0 : (Wo <= kGeo[kClassGeo[1]].max_cols ? 1 : 2); }
 
 int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
@@ -1026,17 +1143,23 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     sorted.assign((size_t)n + kRaggedClasses, RaggedImage{});
     *plan = RaggedQuadPlan{};
     const int forced = env_int("ATTWARP_QUAD_GEO", -1);
-    for (int i = 0; i < n; ++i) plan->count[forced >= 0 ? 2 : width_class(host[i].Wo)]++;
+    const bool direct_ok = direct_allowed();
+    auto cls = [&](const RaggedImage& im) {
+        const int wc = forced >= 0 ? 2 : width_class(im.Wo);
+        return wc + ((direct_ok && rows_word_aligned(im.dst, im.Wo)) ? 0 : 3);
+    };
+    for (int i = 0; i < n; ++i) plan->count[cls(host[i])]++;
     int pos = 0;
     for (int c = 0; c < kRaggedClasses; ++c) {
         plan->offset[c] = pos;
-        plan->geo[c] = forced >= 0 && forced <= 2 ? forced : kClassGeo[c];
+        plan->geo[c] = forced >= 0 && forced <= 2 ? forced : kClassGeo[c % 3];
+        plan->direct[c] = c < 3 ? 1 : 0;
         pos += plan->count[c] + 1;
     }
-    int fill[kRaggedClasses] = {0, 0, 0};
-    int64_t total[kRaggedClasses] = {0, 0, 0};
+    int fill[kRaggedClasses] = {};
+    int64_t total[kRaggedClasses] = {};
     for (int i = 0; i < n; ++i) {
-        const int c = forced >= 0 ? 2 : width_class(host[i].Wo);
+        const int c = cls(host[i]);
         const StripPlan sp = plan_strips(host[i].Wo, kGeo[plan->geo[c]].max_cols);
         const int cols = host[i].Wo < sp.strip_cols ? host[i].Wo : sp.strip_cols;
         const int units = (cols + 127) / 128;
@@ -1067,7 +1190,7 @@ int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImag
         a.imgs = dev_sorted + plan.offset[c];
         a.n_img = plan.count[c];
         a.total_units = plan.total_units[c];
-        const int rc = launch_by_geometry(plan.geo[c], a, plan.max_strip[c], st);
+        const int rc = launch_by_geometry(plan.geo[c], plan.direct[c] != 0, a, plan.max_strip[c], st);
         if (rc != ATTWARP_OK) return rc;
     }
     return ATTWARP_OK;
