@@ -69,6 +69,8 @@ SIGNATURES = {
                                                 _sz, _vp, _vp, _vp, C.POINTER(_vp), _vp]),
     "attwarp_revise_mask": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "attwarp_resize_lanczos_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "attwarp_maps_from_mask_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "attwarp_maps_from_mask": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _tp, _vp, _sz, _vp, _vp, _vp]),
     "attwarp_warp_from_pdfs": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp]),
     "attwarp_ragged_workspace_bytes": (_sz, [_vp, _i]),

@@ -32,6 +32,10 @@ int launch_adaptive_avg_pool2d(const float* A, const uint8_t* sqrt_mask, int B, 
 int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float coe, float* revised,
                        uint8_t* mask_u8, cudaStream_t st);
 int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, int Wo, uint8_t* dst, cudaStream_t st);
+size_t maps_from_mask_workspace_bytes_impl(int B, int h, int w, int H, int W);
+int launch_maps_from_mask(const uint8_t* mask, int B, int h, int w, int H, int W, int Wo, int Ho,
+                          const attwarp_transform_params& tp, void* ws, size_t ws_bytes, float* map_x, float* map_y,
+                          cudaStream_t st);
 int launch_strictly_increasing(const float* F, int B, int N, float eps, float* out, cudaStream_t st);
 int launch_interp_linear_rows(const float* F, int B, int N, int L, float* out, cudaStream_t st);
 
@@ -217,6 +221,23 @@ int attwarp_maps_from_attention(const void* att, int att_dtype, int B, int H, in
     if (rc != ATTWARP_OK) return rc;
     return launch_maps_from_attention(att, att_dtype, B, H, W, Wo, Ho, *tp, workspace, workspace_bytes,
                                       map_x, map_y, nullptr, as_stream(stream));
+}
+
+size_t attwarp_maps_from_mask_workspace_bytes(int B, int h, int w, int H, int W) {
+    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+    return maps_from_mask_workspace_bytes_impl(B, h, w, H, W);
+}
+
+int attwarp_maps_from_mask(const void* mask_u8, int B, int h, int w, int H, int W, int Wo, int Ho,
+                           const attwarp_transform_params* tp, void* workspace, size_t workspace_bytes,
+                           float* map_x, float* map_y, void* stream) {
+    AW_REQUIRE(mask_u8 && map_x && map_y, "maps_from_mask: NULL pointer");
+    AW_REQUIRE(B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && Wo > 0 && Ho > 0, "maps_from_mask: sizes must be positive");
+    AW_REQUIRE(B <= 65535, "maps_from_mask: B=%d exceeds 65535", B);
+    int rc = check_transform(tp);
+    if (rc != ATTWARP_OK) return rc;
+    return launch_maps_from_mask(static_cast<const uint8_t*>(mask_u8), B, h, w, H, W, Wo, Ho, *tp, workspace,
+                                 workspace_bytes, map_x, map_y, as_stream(stream));
 }
 
 int attwarp_maps_from_tokens(const float* tok, int B, int gh, int gw, int H, int W, int Wo, int Ho,

@@ -98,10 +98,10 @@ int launch_remap_f32_stream(const float* src, float* dst, int n_planes, int E, i
                             const float* map_x, const float* map_y, int map_div, cudaStream_t st);
 // ragged: images grouped into width classes (one launch each); dev_main holds n + 1 entries in batch order,
 // dev_sorted n + kRaggedClasses entries grouped by class
-constexpr int kRaggedClasses = 6;      // 3 width classes x {rows 4-byte aligned (direct stores), not aligned (tiles)}
+constexpr int kRaggedClasses = 28;     // 14 width classes x {rows 4-byte aligned, any alignment}
 struct RaggedQuadPlan {
     int count[kRaggedClasses], offset[kRaggedClasses], total_units[kRaggedClasses], max_strip[kRaggedClasses],
-        geo[kRaggedClasses], direct[kRaggedClasses];
+        mode[kRaggedClasses];
 };
 int launch_remap_u8_quad_ragged_prepare(RaggedImage* host_table, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
                                         RaggedQuadPlan* plan, cudaStream_t st);

@@ -141,13 +141,20 @@ __device__ __forceinline__ void unpack4(uint32_t w, int* v) {
 }
 __device__ __forceinline__ uint32_t clip8(int acc) { return (uint32_t)clampi(acc >> kPrecisionBits, 0, 255); }
 
+//
+// MARG (the fusion of llava.py:243-255 with new_method.py:215-216): the mask is not written at all;
+// the kernel leaves the marginal sums of its bytes instead, in the partial layout of profiles.cu (P2b) -- column
+// sums per (tile, row group) chunk in colpart[b][chunk][Wo], whole row sums in rowpart[b][0][Ho], each with the
+// + 1e-9 per element of new_method.py:212 added as count x 1e-9 -- for maps_from_partials_kernel to finish.  All
+// sums are exact integers (<= 255 x 65535), whatever the order the threads add them in.
 constexpr int kUpMaxThreads = 512;
-template <int TAPS>     // taps per axis actually used (7 for pure up-scaling)
+template <int TAPS, bool MARG>     // taps per axis actually used (7 for pure up-scaling)
 __global__ void __launch_bounds__(kUpMaxThreads)
 resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, int Wo,
                          const int2* __restrict__ bx, const int* __restrict__ kx, int ksx,
                          const int2* __restrict__ by, const int* __restrict__ ky, int ksy,
-                         int rows_per_tile, int n_rowgroups, uint8_t* __restrict__ dst) {
+                         int rows_per_tile, int n_rowgroups, uint8_t* __restrict__ dst,
+                         double* __restrict__ colpart, double* __restrict__ rowpart) {
     extern __shared__ __align__(16) uint8_t sm_b[];
     const int Wp = (Wo + 3) & ~3;                        // pitch of the horizontal pass
     const int b = blockIdx.y;
@@ -160,6 +167,10 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
     uint8_t* tmp = in + (((size_t)h * w + 15) & ~(size_t)15);                   // [nr][Wp]
     const uint8_t* img = src + ((int64_t)b * h + r0) * w;
     for (int i = threadIdx.x; i < nr * w; i += blockDim.x) in[i] = img[i];
+    // MARG: the row sums of the tile are added up in shared memory
+    int* rsum = reinterpret_cast<int*>(tmp + (((size_t)h * Wp + 15) & ~(size_t)15));   // [rows_per_tile], MARG only
+    if (MARG)
+        for (int i = threadIdx.x; i < y1 - y0; i += blockDim.x) rsum[i] = 0;
     for (int i = threadIdx.x; i < (y1 - y0) * kUpTaps; i += blockDim.x) {
         const int yy = i >> 3, t = i & 7;
         reinterpret_cast<int*>(coef)[i] = t < ksy ? __ldg(ky + (int64_t)(y0 + yy) * ksy + t) : 0;
@@ -182,12 +193,17 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
     // vertical pass: thread = (row group, column group of 4)
     const int n_cg = Wp >> 2;
     const int rg = threadIdx.x / n_cg;
-    if (rg >= n_rowgroups) return;
+    // MARG: the lanes of this warp that work on the same row group (they add their row sums up with one REDUX)
+    const unsigned peers = MARG ? __match_any_sync(0xffffffffu, rg) : 0u;
+    if (!MARG && rg >= n_rowgroups) return;
     const int cg = threadIdx.x - rg * n_cg;
     const int rows = y1 - y0;
-    const int ya = (int)(((int64_t)rows * rg) / n_rowgroups), yb = (int)(((int64_t)rows * (rg + 1)) / n_rowgroups);
+    const bool live = rg < n_rowgroups;
+    const int ya = live ? (int)(((int64_t)rows * rg) / n_rowgroups) : 0;
+    const int yb = live ? (int)(((int64_t)rows * (rg + 1)) / n_rowgroups) : 0;
     const bool vec = (Wo & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
     uint8_t* out = dst + ((int64_t)b * Ho + y0) * Wo;
+    uint32_t csum[4] = {0u, 0u, 0u, 0u};
     {
         const int g = cg;               // one column group per thread (the launcher sizes the CTA so)
         int win[TAPS][4];
@@ -221,6 +237,13 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
             uint32_t hi2, o;
             asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(acc[3] >> kPrecisionBits), "r"(acc[2] >> kPrecisionBits), "r"(0));
             asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o) : "r"(acc[1] >> kPrecisionBits), "r"(acc[0] >> kPrecisionBits), "r"(hi2));
+            if (MARG) {
+                // columns >= Wo of the last group are zero (zero horizontal coefficients), so they add nothing
+                csum[0] += o & 0xffu; csum[1] += (o >> 8) & 0xffu; csum[2] += (o >> 16) & 0xffu; csum[3] += o >> 24;
+                const uint32_t part = __reduce_add_sync(peers, __dp4a(o, 0x01010101u, 0u));
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&rsum[yy], (int)part);
+                continue;
+            }
             uint8_t* p = out + (int64_t)yy * Wo + 4 * g;
             if (vec) {
                 *reinterpret_cast<uint32_t*>(p) = o;
@@ -230,6 +253,20 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
                     if (4 * g + q < Wo) p[q] = (uint8_t)(o >> (8 * q));
             }
         }
+    }
+    if (MARG) {
+        const int n_chunks = gridDim.x * n_rowgroups;
+        if (live) {
+            double* cp = colpart + ((int64_t)b * n_chunks + blockIdx.x * n_rowgroups + rg) * Wo;
+            const double base = (double)(yb - ya) * kBaseAttention;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * cg + q < Wo) cp[4 * cg + q] = (double)csum[q] + base;
+        }
+        __syncthreads();
+        const double row_base = (double)Wo * kBaseAttention;
+        for (int i = threadIdx.x; i < rows; i += blockDim.x)
+            rowpart[(int64_t)b * Ho + y0 + i] = (double)rsum[i] + row_base;
     }
 }
 
@@ -314,6 +351,58 @@ int launch_revise_mask(const float* tok, int B, int gh, int gw, int ksize, float
     return check_launch("revise_mask_kernel");
 }
 
+// Launch geometry of the up-scaling kernel: tiles of `rows` output rows (enough CTAs to fill the GPU, as tall as
+// possible: the horizontal pass is redone per tile), n_rg row groups of Wp / 4 threads each.
+struct UpGeometry { bool ok; int n_tiles, rows, n_rg, threads; size_t smem; };
+static UpGeometry up_geometry(int B, int h, int w, int Ho, int Wo) {
+    UpGeometry g{};
+    const int Wp = (Wo + 3) & ~3, n_cg = Wp / 4;
+    if (n_cg > kUpMaxThreads) return g;
+    int n_tiles = (2 * sm_count() + B - 1) / B;
+    n_tiles = n_tiles < 1 ? 1 : n_tiles;
+    if (n_tiles > (Ho + 31) / 32) n_tiles = (Ho + 31) / 32;
+    g.rows = (Ho + n_tiles - 1) / n_tiles;
+    g.n_tiles = (Ho + g.rows - 1) / g.rows;
+    g.n_rg = kUpMaxThreads / n_cg;
+    g.threads = (n_cg * g.n_rg + 31) & ~31;
+    // coefficients + first taps | source rows | horizontal pass | row sums (MARG)
+    g.smem = (size_t)g.rows * 36 + (((size_t)h * w + 15) & ~(size_t)15) + (((size_t)h * Wp + 15) & ~(size_t)15) +
+             (size_t)g.rows * 4;
+    g.ok = g.smem <= 200 * 1024;
+    return g;
+}
+
+// Partial-sum chunks per image the fused kernel writes (0: this resize is not taken by the fused kernel).
+int lanczos_marginals_chunks(int B, int h, int w, int H, int W) {
+    if (H <= h || W <= w || h > 0xffff || w > 0xffff) return 0;
+    // pure up-scaling: 3 * 2 + 1 = 7 taps per axis
+    const UpGeometry g = up_geometry(B, h, w, H, W);
+    return g.ok ? g.n_tiles * g.n_rg : 0;
+}
+
+// mask_u8 [B][h][w] (revise_mask's uint8 output) -> marginal partial sums of its LANCZOS resize to H x W, which is
+// never written: colpart [B][chunks][W], rowpart [B][1][H].
+int launch_lanczos_marginals(const uint8_t* src, int B, int h, int w, int H, int W, double* colpart, double* rowpart,
+                             int* n_chunks, cudaStream_t st) {
+    const UpGeometry ug = up_geometry(B, h, w, H, W);
+    if (H <= h || W <= w || !ug.ok)
+        return fail(ATTWARP_ERR_UNSUPPORTED, "lanczos_marginals: %dx%d -> %dx%d is not an up-scaling that fits shared memory", h, w, H, W);
+    CoeffTable tx, ty;
+    int rc = get_table(w, W, &tx);
+    if (rc != ATTWARP_OK) return rc;
+    rc = get_table(h, H, &ty);
+    if (rc != ATTWARP_OK) return rc;
+    if (tx.ksize > kUpTaps || ty.ksize > kUpTaps) return fail(ATTWARP_ERR_UNSUPPORTED, "lanczos_marginals: too many taps");
+    auto kern = (tx.ksize <= 7 && ty.ksize <= 7) ? resize_lanczos_up_kernel<7, true> : resize_lanczos_up_kernel<8, true>;
+    if (ug.smem > 48 * 1024)
+        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ug.smem));
+    kern<<<dim3(ug.n_tiles, B), ug.threads, ug.smem, st>>>(
+        src, h, w, H, W, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, ug.rows, ug.n_rg, nullptr,
+        colpart, rowpart);
+    *n_chunks = ug.n_tiles * ug.n_rg;
+    return check_launch("resize_lanczos_up_kernel<marginals>");
+}
+
 int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, int Wo, uint8_t* dst, cudaStream_t st) {
     CoeffTable tx, ty;
     if (Wo != w) {
@@ -325,25 +414,15 @@ int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, in
         if (rc != ATTWARP_OK) return rc;
     }
     // up-scaling (or any resize with <= 8 taps per axis) of both axes: the register-window kernel
-    const int Wp = (Wo + 3) & ~3, n_cg = Wp / 4;
-    if (Wo != w && Ho != h && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps && n_cg <= kUpMaxThreads) {
-        // tiles: enough CTAs to fill the GPU, as tall as possible (the horizontal pass is redone per tile)
-        int n_tiles = (2 * sm_count() + B - 1) / B;
-        n_tiles = n_tiles < 1 ? 1 : n_tiles;
-        if (n_tiles > (Ho + 31) / 32) n_tiles = (Ho + 31) / 32;
-        const int rows = (Ho + n_tiles - 1) / n_tiles;
-        n_tiles = (Ho + rows - 1) / rows;
-        const int n_rg = kUpMaxThreads / n_cg;
-        const int threads = (n_cg * n_rg + 31) & ~31;
-        const size_t smem_up = (size_t)rows * 36 + (((size_t)h * w + 15) & ~(size_t)15) + (size_t)h * Wp;
-        if (smem_up <= 200 * 1024) {
-            auto kern = (tx.ksize <= 7 && ty.ksize <= 7) ? resize_lanczos_up_kernel<7> : resize_lanczos_up_kernel<8>;
-            if (smem_up > 48 * 1024)
-                AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up));
-            kern<<<dim3(n_tiles, B), threads, smem_up, st>>>(
-                src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, rows, n_rg, dst);
-            return check_launch("resize_lanczos_up_kernel");
-        }
+    const UpGeometry ug = up_geometry(B, h, w, Ho, Wo);
+    if (Wo != w && Ho != h && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps && ug.ok) {
+        auto kern = (tx.ksize <= 7 && ty.ksize <= 7) ? resize_lanczos_up_kernel<7, false> : resize_lanczos_up_kernel<8, false>;
+        if (ug.smem > 48 * 1024)
+            AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ug.smem));
+        kern<<<dim3(ug.n_tiles, B), ug.threads, ug.smem, st>>>(
+            src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, ug.rows, ug.n_rg, dst,
+            nullptr, nullptr);
+        return check_launch("resize_lanczos_up_kernel");
     }
     // shared memory: the source rows a tile taps (at most all of them) + their horizontal pass
     const size_t smem = (((size_t)h * w + 15) & ~(size_t)15) + (size_t)h * Wo;

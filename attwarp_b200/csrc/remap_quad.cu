@@ -5,12 +5,18 @@
 // reference call sites "Attention Guided Warping/new_method.py:268-271",
 // "model/marginalnet_full_dataset/checkpoint_utils.py:195-198").  Same skeleton as remap_stream.cu (producer
 // warp plans chunks of output rows and fetches the source rows they tap with cp.async.bulk, consumer warps
-// sweep them once, store warp ships output tiles with cp.async.bulk), with the consumer side rebuilt around the
-// two resources the round-1 kernel ran out of -- shared-memory wavefronts and issue slots (profiles/README.md):
+// sweep them once), with the consumer side rebuilt around the two resources the round-1 kernel ran out of --
+// shared-memory wavefronts and issue slots (profiles/README.md) -- and WITHOUT output tiles or store warps: the
+// consumer warps write their rows to global memory themselves:
 //
-//   * a thread owns output columns 4t .. 4t+3 of its strip: 12 contiguous output bytes = three aligned 32-bit
-//     stores per output row instead of twelve byte stores, and its four source windows sit 3 words apart at
-//     unit scale (12-byte lane stride: every 32-bit load of a warp is conflict-free);
+//   * a thread owns output columns 4t .. 4t+3 of its strip (QUAD mapping: its four source windows sit 3 words
+//     apart at unit scale, 12-byte lane stride: every 32-bit load of a warp is conflict-free) or columns t, t + 32,
+//     t + 64, t + 96 of its warp's 128-column block (LANE mapping, chosen per warp and strip where the map's local
+//     scale would make the QUAD windows collide);
+//   * the 384 output bytes of a warp and row change hands through a per-warp shared-memory scratch so that lane t
+//     ends up with words t, t + 32, t + 64 of them: three fully coalesced 128-byte global stores per row.  Rows at
+//     any byte alignment are handled by a second build (MODE 2: funnel-shifted words + byte stores at the two ends
+//     of the block), so no destination needs an output tile;
 //   * the horizontal blends of the two most recent source rows are held per channel in an EVEN-row and an
 //     ODD-row register (source row r goes to E when r is even), so a new source row overwrites one of them
 //     without re-packing; the vertical blend of an output row is  t = wO*O + (wE*E + 512 * 2^14)  with the row's
@@ -24,8 +30,9 @@
 //     slots whose pitch is congruent to the row pitch modulo 16.  When the pitch is a multiple of 4 the
 //     per-pixel window addresses advance by a constant and their byte shifts never change (fixed-shift sweep);
 //     otherwise address and shift are re-derived per slot (three more ALU operations per pixel and slot);
-//   * strips are as wide as the consumer threads allow (up to 4 columns x 352 threads = 1408): a 1344-wide
-//     image is processed in whole rows, fetched and shipped as contiguous 4 KB rows.
+//   * a CTA has exactly the consumer warps its strips need (3 .. 16: strips of up to 2048 columns), so a
+//     1344-wide image is processed in whole rows fetched as contiguous 4 KB rows, and the images of a ragged batch
+//     are grouped by that number.
 //
 // Maps need not be monotone (a chunk ends before the first output row that taps an earlier source row than its
 // predecessor), a strip whose source span does not fit a stage is gathered from global memory (the kernel is
@@ -33,6 +40,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "bulk_ptx.cuh"
@@ -43,29 +54,24 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kMaxRing = 4;            // source-row stages / output tiles per CTA are launch parameters (2 .. 4)
+constexpr int kMaxRing = 4;            // source-row stages per CTA are a launch parameter (2 .. 4)
 constexpr int kMaxRows = 16;          // capacity of a chunk table; the rows per chunk are a launch parameter
-// role warps: one producer warp + `store_warps` store warps (a launch parameter: wide strips with odd row pitches keep
-// several warps busy shifting rows on their way out)
 constexpr int kC = 3;
 
 extern __shared__ __align__(128) uint8_t smem[];
-__device__ __forceinline__ uint32_t ld32(int off) { return *reinterpret_cast<const uint32_t*>(smem + off); }
 __device__ __forceinline__ uint4 ld128(int off) { return *reinterpret_cast<const uint4*>(smem + off); }
-__device__ __forceinline__ void st32(int off, uint32_t v) { *reinterpret_cast<uint32_t*>(smem + off) = v; }
 __device__ __forceinline__ void st128(int off, uint4 v) { *reinterpret_cast<uint4*>(smem + off) = v; }
 
 // ---- per-stage chunk table (byte offsets), written by the producer, read by the consumers ----------
 //   +0   uint4 {n_rows, n_slots | flags << 16, slot_pitch, byte offset of slot 0's first byte in the arena}
 //              n_rows 0: output row y0 takes the direct path; -1: stop
 //   +16  uint4 {img, x_first, y0, c_lo}
-//   +32  uint4 {address of the chunk's first output byte -- DIRECT: of the image's -- (lo, hi), bytes per strip row,
-//               Wo * 3}
+//   +32  uint4 {the 4-byte aligned address at or below the image's first destination byte (lo, hi), bytes per strip
+//               row, Wo * 3}
 //   +48  uint4 {address of map_x[x_first] (lo, hi), W, columns in the strip}      (new strip only)
 //   +64  uint4 row[kMaxRows + 1]:  x = wE << 14, y = wO << 14  (weights of the even / odd source row)
-//                                  z = byte offset of the row inside the output tile: row * pitch + (address of the
-//                                      row's first destination byte & 12) -- always 4-byte aligned for the
-//                                      consumers' word stores; the store warp bridges the remaining 0..3 bytes
+//                                  z = offset of the row's first destination byte (of this strip) from the address
+//                                      in +32: its low two bits are the row's misalignment
 //                                  w = slot after which the row is emitted (= slot of its LOWER tap);
 //                                      0xffffffff: both taps are the carried pair, emit before slot 0;
 //                                      the entry after the last row is a sentinel
@@ -91,8 +97,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
 //   w?l / w?h       : dp4a weight words  w0 | w1 << 8  and the same shifted by 16
 //   FIXED:  k? = shared address of the word holding the window's first byte in slot 0, s? = 8 * byte offset
 //   !FIXED: u? = shared BYTE address of the window in slot 0 (word address and shift derived per slot)
-// Common: n_slots, pitch (bytes between slots), rp (shared address of row[0]), ocol (shared address of this
-// thread's 12 bytes in a tile row at offset 0), first slot parity, store predicate.
+// Common: n_slots, pitch (bytes between slots), rp (shared address of row[0]), first slot parity.
 #define AWQ_LOAD1(J)                                            \
     "ld.shared.b32 lo" #J ", [k" #J "];\n"                      \
     "ld.shared.b32 mi" #J ", [k" #J "+4];\n"                    \
@@ -128,48 +133,12 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
 #define AWQ_VBLEND                                              \
     AWQ_V1(a, 0) AWQ_V1(a, 1) AWQ_V1(a, 2) AWQ_V1(b, 0) AWQ_V1(b, 1) AWQ_V1(b, 2)  \
     AWQ_V1(c, 0) AWQ_V1(c, 1) AWQ_V1(c, 2) AWQ_V1(d, 0) AWQ_V1(d, 1) AWQ_V1(d, 2)
-// 12 top bytes -> 3 words (prmt: x.b3 | y.b3 << 8, then the low halves of two pairs), three aligned stores
-#define AWQ_EMIT_W                                              \
-    AWQ_VBLEND                                                  \
-    "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
-    "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
-    "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
-    "prmt.b32 q3, vc0, vc1, 0x0073;\n"                          \
-    "prmt.b32 q4, vc2, vd0, 0x0073;\n"                          \
-    "prmt.b32 q5, vd1, vd2, 0x0073;\n"                          \
-    "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
-    "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
-    "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
-    "add.u32 o, ez, %38;\n"                                     \
-    "@pv st.shared.b32 [o], q0;\n"                              \
-    "@pv st.shared.b32 [o+4], q2;\n"                            \
-    "@pv st.shared.b32 [o+8], q4;\n"
-// LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
-// 128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict whatever the
-// local scale of the map.  The output bytes change hands through a per-warp scratch (two 512-byte buffers used
-// alternately: one bar.warp.sync per row): 4-byte RGBX per pixel in, the 16 bytes of four adjacent pixels out,
-// squeezed to 12 bytes -- the tile stores are the same three aligned words as in the QUAD mapping.
-#define AWQ_EMIT_L                                              \
-    AWQ_VBLEND                                                  \
-    "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
-    "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
-    "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
-    "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
-    "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
-    "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.v4.b32 {q0, q1, q2, q3}, [sq];\n"                \
-    "xor.b32 sx, sx, 512;\n xor.b32 sq, sq, 512;\n"             \
-    "prmt.b32 q4, q0, q1, 0x4210;\n"                            \
-    "prmt.b32 q5, q1, q2, 0x5421;\n"                            \
-    "prmt.b32 q1, q2, q3, 0x6542;\n"                            \
-    "add.u32 o, ez, %38;\n"                                     \
-    "@pv st.shared.b32 [o], q4;\n"                              \
-    "@pv st.shared.b32 [o+4], q5;\n"                            \
-    "@pv st.shared.b32 [o+8], q1;\n"
-// DIRECT stores (every destination row 4-byte aligned, no output tile, no store warp): the warp's 384 output bytes of
-// a row change hands through the scratch so that lane t ends up with WORDS t, t + 32, t + 64 of them -- three
-// fully coalesced 128-byte global stores per row.  %49 = address of the warp's first destination byte at row offset
-// 0 (64-bit), %50 = 4 * lane, bits 0..2 of %53 = word k lies inside the strip.
+// Emit of one output row, destination rows 4-byte aligned (MODE 1): the 12 top bytes of the vertical blends are
+// packed into 3 words (prmt: x.b3 | y.b3 << 8, then the low halves of two pairs); the warp's 384 output bytes change
+// hands through the scratch (two buffers used alternately: one bar.warp.sync per row) so that lane t ends up with
+// WORDS t, t + 32, t + 64 of them -- three fully coalesced 128-byte global stores per row.  %49 = address of the
+// warp's first destination byte at row offset 0 (64-bit), %50 = 4 * lane, bits 0..2 of %53 = word k lies inside the
+// strip.
 //   QUAD mapping: packed words to P + 12 * lane (%51), back from P + 4 * lane (%52)
 #define AWQ_DIRECT_ADDR                                         \
     "cvt.u64.u32 ro64, ez;\n"                                   \
@@ -195,8 +164,10 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "@pw0 st.global.b32 [oa], q0;\n"                            \
     "@pw1 st.global.b32 [oa+128], q1;\n"                        \
     "@pw2 st.global.b32 [oa+256], q2;\n"
-//   LANE mapping: RGBX pixels to X + 4 * lane (+ 128 j), word k of the lane = bytes of two adjacent RGBX pixels
-//   (addresses xa0..2, byte selectors xs0..2: per-lane constants)
+//   LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
+//   128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict whatever the
+//   local scale of the map.  RGBX pixels go to X + 4 * lane (+ 128 j); output word k of the lane = bytes of two
+//   adjacent RGBX pixels (addresses xa0..2, byte selectors xs0..2: per-lane constants)
 #define AWQ_EMIT_LD                                             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
@@ -216,6 +187,65 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "@pw0 st.global.b32 [oa], q0;\n"                            \
     "@pw1 st.global.b32 [oa+128], q2;\n"                        \
     "@pw2 st.global.b32 [oa+256], q4;\n"
+// DIRECT stores at ANY byte alignment of the destination rows (MODE 2).  The row-table offset `ez` is taken from the
+// 4-byte aligned address below the image's first byte, so k = ez & 3 is the misalignment of this row's block; the
+// block's packed bytes sit in P (one pad word in front); aligned global word j of the block is the funnel shift of
+// packed words j - 1 and j by 8 (4 - k) bits.  Lane t stores words t, t + 32, t + 64 where they lie wholly inside
+// the block (%53: validity bits [4 k + m] for the four alignments) and the <= 3 + 3 bytes of the partial first and
+// last word are stored byte by byte by lanes 4..6 and 0..2 (%60: bit k = this lane stores its edge byte at
+// alignment k, %61 = the byte's offset in the block, %62 = its address in P).
+#define AWQ_UNALIGNED_TAIL                                      \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
+    "ld.shared.b32 q3, [pr+-4];\n ld.shared.b32 q4, [pr+124];\n ld.shared.b32 q5, [pr+252];\n" \
+    "and.b32 uk, ez, 3;\n"                                      \
+    "shl.b32 tm, uk, 3;\n sub.u32 tm, 32, tm;\n"                \
+    "shf.r.clamp.b32 q0, q3, q0, tm;\n shf.r.clamp.b32 q1, q4, q1, tm;\n shf.r.clamp.b32 q2, q5, q2, tm;\n" \
+    "sub.u32 tm, ez, uk;\n"                                     \
+    "cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n"          \
+    "cvt.u64.u32 ro64, %50;\n add.u64 oa, oa, ro64;\n"          \
+    "shl.b32 tm, uk, 2;\n shr.u32 tm, %53, tm;\n"               \
+    "and.b32 o, tm, 1;\n setp.ne.u32 pw0, o, 0;\n"              \
+    "and.b32 o, tm, 2;\n setp.ne.u32 pw1, o, 0;\n"              \
+    "and.b32 o, tm, 4;\n setp.ne.u32 pw2, o, 0;\n"              \
+    "@pw0 st.global.b32 [oa], q0;\n"                            \
+    "@pw1 st.global.b32 [oa+128], q1;\n"                        \
+    "@pw2 st.global.b32 [oa+256], q2;\n"                        \
+    "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
+    "@pe ld.shared.u8 o, [pedge];\n"                            \
+    "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n" \
+    "@pe st.global.u8 [oa], o;\n"                               \
+    "xor.b32 pw, pw, 512;\n xor.b32 pr, pr, 512;\n xor.b32 pedge, pedge, 512;\n"
+#define AWQ_EMIT_WU                                             \
+    AWQ_VBLEND                                                  \
+    "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
+    "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
+    "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
+    "prmt.b32 q3, vc0, vc1, 0x0073;\n"                          \
+    "prmt.b32 q4, vc2, vd0, 0x0073;\n"                          \
+    "prmt.b32 q5, vd1, vd2, 0x0073;\n"                          \
+    "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
+    "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
+    "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
+    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
+    AWQ_UNALIGNED_TAIL
+#define AWQ_EMIT_LU                                             \
+    AWQ_VBLEND                                                  \
+    "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
+    "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
+    "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
+    "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
+    "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
+    "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
+    "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
+    "xor.b32 sx, sx, 512;\n xor.b32 xa0, xa0, 512;\n xor.b32 xa1, xa1, 512;\n xor.b32 xa2, xa2, 512;\n" \
+    "prmt.b32 q0, q0, q1, xs0;\n"                               \
+    "prmt.b32 q2, q2, q3, xs1;\n"                               \
+    "prmt.b32 q4, q4, q5, xs2;\n"                               \
+    "st.shared.b32 [pr], q0;\n st.shared.b32 [pr+128], q2;\n st.shared.b32 [pr+256], q4;\n" \
+    AWQ_UNALIGNED_TAIL
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  The entry of the row AFTER the
 // one being emitted is requested before the emit, so the loop-carried compare never waits for a shared-memory load
 // (the entry after the sentinel is read too: still inside the CTA's shared memory, never used)
@@ -233,9 +263,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     L "_NEXT:\n"                                                \
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
-    ".reg .pred p, q, pv, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq, pw, pr, xa0, xa1, xa2, xs0, xs1, xs2, tm;\n" \
-    ".reg .pred pw0, pw1, pw2;\n"                               \
+    ".reg .pred p, q, podd;\n"                              \
+    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, pw, pr, xa0, xa1, xa2, xs0, xs1, xs2, tm, uk, pedge;\n" \
+    ".reg .pred pw0, pw1, pw2, pe;\n"                               \
     ".reg .b64 ro64, oa;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
     ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
@@ -246,8 +276,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     ".reg .b32 va0, va1, va2, vb0, vb1, vb2, vc0, vc1, vc2, vd0, vd1, vd2;\n"   \
     ".reg .b32 q0, q1, q2, q3, q4, q5;\n"
 // operands: %0-%11 E, %12-%23 O (read/write) | %24-%27 window address (a..d) | %28-%31 shift (a..d) |
-//           %32 n_slots | %33, %34 LANE mapping: scratch addresses (write, read) | %35 unused | %36 pitch | %37 rp | %38 ocol | %39 first slot odd |
-//           %40 store predicate | %41-%48 weight words (la, ha, lb, hb, lc, hc, ld, hd)
+//           %32 n_slots | %33 LANE mapping: scratch address of my RGBX pixels | %34, %35 unused | %36 pitch | %37 rp |
+//           %38 unused | %39 first slot odd | %40 unused | %41-%48 weight words (la, ha, lb, hb, lc, hc, ld, hd) |
+//           %49-%62 see the emit variants
 #define AWQ_PROLOGUE                                            \
     "mov.b32 Ea0, %0;\n mov.b32 Ea1, %1;\n mov.b32 Ea2, %2;\n mov.b32 Eb0, %3;\n mov.b32 Eb1, %4;\n mov.b32 Eb2, %5;\n" \
     "mov.b32 Ec0, %6;\n mov.b32 Ec1, %7;\n mov.b32 Ec2, %8;\n mov.b32 Ed0, %9;\n mov.b32 Ed1, %10;\n mov.b32 Ed2, %11;\n" \
@@ -255,14 +286,13 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 Oc0, %18;\n mov.b32 Oc1, %19;\n mov.b32 Oc2, %20;\n mov.b32 Od0, %21;\n mov.b32 Od1, %22;\n mov.b32 Od2, %23;\n" \
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
-    "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
-    "mov.b32 pw, %51;\n mov.b32 pr, %52;\n"                     \
+    "mov.b32 sx, %33;\n"                                        \
+    "mov.b32 pw, %51;\n mov.b32 pr, %52;\n mov.b32 pedge, %62;\n"  \
     "mov.b32 xa0, %54;\n mov.b32 xa1, %55;\n mov.b32 xa2, %56;\n"      \
     "mov.b32 xs0, %57;\n mov.b32 xs1, %58;\n mov.b32 xs2, %59;\n"      \
     "and.b32 tm, %53, 1;\n setp.ne.u32 pw0, tm, 0;\n"           \
     "and.b32 tm, %53, 2;\n setp.ne.u32 pw1, tm, 0;\n"           \
     "and.b32 tm, %53, 4;\n setp.ne.u32 pw2, tm, 0;\n"           \
-    "setp.ne.u32 pv, %40, 0;\n"                                 \
     "setp.ne.u32 podd, %39, 0;\n"                               \
     "mov.b32 rp, %37;\n"                                        \
     "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp];\n"
@@ -315,33 +345,33 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
       "+r"(E[8]), "+r"(E[9]), "+r"(E[10]), "+r"(E[11]), "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]),     \
       "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "+r"(O[9]), "+r"(O[10]), "+r"(O[11])      \
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
-      "r"(n_slots), "r"(sx), "r"(sq), "r"(0), "r"(pitch), "r"(rp), "r"(ocol), "r"(odd_first), "r"(store_ok),  \
+      "r"(n_slots), "r"(sx), "r"(0), "r"(0), "r"(pitch), "r"(rp), "r"(0), "r"(odd_first), "r"(0),             \
       "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3]),       \
       "l"(d.obase), "r"(d.lane4), "r"(d.pw), "r"(d.pr), "r"(d.wmask), "r"(d.xa[0]), "r"(d.xa[1]), "r"(d.xa[2]),    \
-      "r"(d.xs[0]), "r"(d.xs[1]), "r"(d.xs[2])                                                              \
+      "r"(d.xs[0]), "r"(d.xs[1]), "r"(d.xs[2]), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                     \
     : "memory"
 
-// what the DIRECT emit variants need besides the tile variants' operands (see AWQ_EMIT_WD / AWQ_EMIT_LD)
+// what the emit variants need (see AWQ_EMIT_WD / AWQ_EMIT_LD / AWQ_UNALIGNED_TAIL)
 struct DirectOps {
     uint64_t obase;
     uint32_t lane4, pw, pr, wmask, xa[3], xs[3];
+    uint32_t emask, eoff, pedge;        // MODE 2 only
 };
 
 // FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
-// LANE: false = QUAD mapping, true = LANE mapping.  DIRECT: rows go straight to global memory (three coalesced word
-// stores per lane), else into the output tile (three aligned word stores at the QUAD position).
-template <bool FIXED, bool LANE, bool DIRECT>
+// LANE: false = QUAD mapping, true = LANE mapping.  MODE 1: destination rows 4-byte aligned (three coalesced word
+// stores per lane); 2: rows at any alignment (+ byte stores at the two ends of the warp's block).
+template <bool FIXED, bool LANE, int MODE>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
                                            const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
-                                           uint32_t rp, uint32_t ocol, uint32_t odd_first, uint32_t store_ok,
-                                           uint32_t sx, uint32_t sq, const DirectOps& d) {
+                                           uint32_t rp, uint32_t odd_first, uint32_t sx, const DirectOps& d) {
 #define AWQ_RUN(BODY, EMIT) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE BODY(EMIT) AWQ_EPILOGUE "}\n" AWQ_OPERANDS)
     if (FIXED) {
-        if (!DIRECT) { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_W); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_L); }
-        else { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_LD); }
+        if (MODE == 1) { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_LD); }
+        else { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_WU); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_LU); }
     } else {
-        if (!DIRECT) { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_W); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_L); }
-        else { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_LD); }
+        if (MODE == 1) { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_LD); }
+        else { if (!LANE) AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_WU); else AWQ_RUN(AWQ_BODY_V, AWQ_EMIT_LU); }
     }
 #undef AWQ_RUN
 }
@@ -360,16 +390,14 @@ struct QuadArgs {
     int n_img;
     int total_units;         // length of the cost axis (uniform batch: one unit per output row of a strip)
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
-    int out_pitch;           // bytes per row of an output tile
     int rows;                // output rows per chunk (<= kMaxRows)
-    int stages, tiles;       // ring depths: source-row stages (chunks whose loads are in flight), output tiles
-    int store_warps;         // store warps per CTA (rows of a tile are dealt round-robin to them)
+    int stages;              // ring depth: source-row stages (chunks whose loads are in flight)
     int wait_hint_ns;        // suspend-time hint of the mbarrier waits (0: plain try_wait polling)
-    int roles_first;         // 1: the producer / store warps are the CTA's first warps (the consumers get the higher
-                             // warp ids, which the issue arbiter favours), 0: they are its last warps
+    int roles_first;         // 1: the producer warp is the CTA's first warp (the consumers get the higher warp ids),
+                             // 0: it is its last warp (no measurable difference: profiles/r02p_*)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
                              // 1: always QUAD, 2: LANE wherever word stores apply
-    int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep, 2 skip the tile stores
+    int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep (loads and pipeline only)
     unsigned long long* trace;   // ATTWARP_REMAP_TRACE: 8 global-timer stamps per CTA (nullptr: off)
 };
 
@@ -431,44 +459,31 @@ __device__ __forceinline__ int first_image(const QuadArgs& a, int u0, int lane) 
 }
 
 // Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
-// blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads + 32 x store_warps
-// store threads.
-// Shared memory: [stages source arenas][tiles output tiles][stages chunk tables][tiles tile headers][mbarriers].
-// Chunk c lives in source stage c % stages and output tile c % tiles.  mbarriers:
+// blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads.
+// Shared memory: [stages source arenas][stages chunk tables][mbarriers][2 KB of scratch per consumer warp].
+// Chunk c lives in source stage c % stages.  mbarriers:
 //   full[s]  producer -> consumers   table written, source rows landed (transaction bytes)
 //   sfree[s] consumers -> producer   every consumer warp is done with the stage's rows and table
-//   odone[o] consumers -> store warp every consumer warp has written its columns of the tile
-//   ofree[o] store warp -> consumers the tile has been read out of shared memory
-// DIRECT (every destination row of the launch is 4-byte aligned): no output tiles, no store warps -- the consumers
-// write their rows to global memory themselves (AWQ_EMIT_WD / AWQ_EMIT_LD).
-template <int MAXT, int MINB, bool DIRECT>
+// MODE 1: every destination row of the launch is 4-byte aligned; MODE 2: any alignment (see AWQ_UNALIGNED_TAIL).
+template <int MAXT, int MINB, int MODE>
 __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArgs a) {
+    static_assert(MODE == 1 || MODE == 2, "MODE: 1 = aligned rows, 2 = any alignment");
     const int R = a.rows;
-    const int kStages = a.stages, kTiles = DIRECT ? 0 : a.tiles;
-    const int out_bytes = R * a.out_pitch;
-    const int out_off0 = kStages * a.stage_bytes;
-    const int tab_off0 = out_off0 + kTiles * out_bytes;
-    const int ohdr_off0 = tab_off0 + kStages * kTabBytes;
-    const int bar_off0 = ohdr_off0 + kTiles * 32;
+    const int kStages = a.stages;
+    const int tab_off0 = kStages * a.stage_bytes;
+    const int bar_off0 = tab_off0 + kStages * kTabBytes;
     const uint32_t smem_s = smem_u32(smem);
     const uint32_t full_s = smem_s + (uint32_t)bar_off0;
     const uint32_t sfree_s = full_s + 8u * kStages;
-    const uint32_t odone_s = sfree_s + 8u * kStages;
-    const uint32_t ofree_s = odone_s + 8u * kTiles;
-    const int n_store_warps = DIRECT ? 0 : a.store_warps;
-    const int n_cons_warps = ((int)blockDim.x >> 5) - 1 - n_store_warps;
+    const int n_cons_warps = ((int)blockDim.x >> 5) - 1;
     // per consumer warp 2 KB of scratch at a 1 KB aligned shared address: two 512-byte RGBX buffers (LANE mapping)
-    // and two 512-byte packed-row buffers (DIRECT stores), each pair toggled with xor 512
-    const uint32_t scratch_s = (ofree_s + 8u * kTiles + 1023u) & ~1023u;
+    // and two 512-byte packed-row buffers, each pair toggled with xor 512
+    const uint32_t scratch_s = (sfree_s + 8u * kStages + 1023u) & ~1023u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_s + 8u * s, 1);
             mbar_init(sfree_s + 8u * s, n_cons_warps);
-        }
-        for (int s = 0; s < kTiles; ++s) {
-            mbar_init(odone_s + 8u * s, n_cons_warps);
-            mbar_init(ofree_s + 8u * s, n_store_warps);
         }
         mbar_init_fence();
         trace_stamp(a, 0);                                   // CTA started
@@ -481,10 +496,9 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
     const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
 
-    // warp roles: consumers 0 .. n_cons_warps-1, then the producer, then the store warps (logical indices)
-    const int n_roles = 1 + n_store_warps;
+    // warp roles: consumers 0 .. n_cons_warps-1, then the producer (logical indices)
     const int hw_warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
-    const int warp_idx = a.roles_first ? (hw_warp < n_roles ? n_cons_warps + hw_warp : hw_warp - n_roles) : hw_warp;
+    const int warp_idx = a.roles_first ? (hw_warp < 1 ? n_cons_warps + hw_warp : hw_warp - 1) : hw_warp;
     const int lane = (int)threadIdx.x & 31;
     const int tid = warp_idx * 32 + lane;                  // logical thread index: consumers first
     const uint32_t hint = (uint32_t)a.wait_hint_ns;
@@ -494,7 +508,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     };
 
     if (warp_idx >= n_cons_warps) {
-        if (warp_idx == n_cons_warps) {
+        {
             // =========================== producer warp =========================================
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
@@ -613,12 +627,11 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     if (lane < n_rows) {
                         const uint32_t wu = (uint32_t)wa << 14, wl_ = (uint32_t)(32 - wa) << 14;   // upper / lower tap
                         const bool up_even = (ra & 1) == 0;
-                        // z: tile mode -> offset of the row in the output tile; DIRECT -> offset of the row's first
-                        // byte (of this strip) from the image's first destination byte
+                        // z: offset of the row's first byte (of this strip) from the 4-byte aligned address at or
+                        // below the image's first byte
                         st128(tab + kTabRows + 16 * lane,
                               make_uint4(up_even ? wu : wl_, up_even ? wl_ : wu,
-                                         DIRECT ? (uint32_t)(gd - dimg)
-                                                : (uint32_t)(lane * a.out_pitch) + (uint32_t)(gd & 12),
+                                         (uint32_t)(gd - (dimg & ~(uintptr_t)3)),
                                          (uint32_t)(ra + 1 - r_lo)));
                     } else if (lane == n_rows) {
                         st128(tab + kTabRows + 16 * lane, make_uint4(0u, 0u, 0u, kRowSentinel));
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                         st128(tab, make_uint4((uint32_t)n_rows, (uint32_t)n_slots | (fl << 16),
                                               (uint32_t)slot_pitch, (uint32_t)phase0));
                         st128(tab + 16, make_uint4((uint32_t)img, (uint32_t)x_first, (uint32_t)y_cur, (uint32_t)c_lo));
-                        const uintptr_t gbase = DIRECT ? dimg : gd;         // DIRECT: the image, else the chunk's first row
+                        const uintptr_t gbase = dimg & ~(uintptr_t)3;
                         st128(tab + kTabStore, make_uint4((uint32_t)gbase, (uint32_t)((uint64_t)gbase >> 32),
                                                           (uint32_t)(ncols * kC), (uint32_t)(Wo * kC)));
                         if (seg_flags & kFlagNewStrip) {
@@ -663,108 +676,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 st128(tab_off0 + st * kTabBytes, make_uint4(0xffffffffu, 0u, 0u, 0u));
                 mbar_arrive(full_s + 8u * st);
             }
-        } else {
-            // =============================== store warps =====================================
-            // store warp k ships rows k, k + n_store_warps, ... of every tile
-            const int sw = warp_idx - n_cons_warps - 1;
-            int ot = 0;
-            uint32_t ph = 0;
-            for (;;) {
-                wait(odone_s + 8u * ot, ph);                      // every consumer warp is through
-                const uint4 hd = ld128(ohdr_off0 + 32 * ot);           // {n_rows, -, -, -}
-                const int n_rows = (int)hd.x;
-                if (n_rows < 0) break;
-                if (n_rows > 0 && !(a.dbg & 2)) {
-                    // Tile row i sits at  i * out_pitch + (address of its first destination byte & 12).
-                    //   rows whose destination is 4-byte aligned: bulk store of the 16-byte aligned interior (shared
-                    //     and global addresses have the same 16-byte phase), <= 15 head and tail bytes by byte stores;
-                    //   other rows (odd widths): the interior is shifted by 1..3 bytes on its way out -- per 16-byte
-                    //     destination chunk one aligned 128-bit load + the word before it, four funnel shifts, one
-                    //     aligned 128-bit store (lanes take consecutive chunks: full-sector writes).
-                    const uint4 hs = ld128(ohdr_off0 + 32 * ot + 16);  // {dst lo, dst hi, row bytes, dst pitch}
-                    const int len = (int)hs.z;
-                    const int64_t dpitch = (int64_t)hs.w;
-                    const int obuf = out_off0 + ot * out_bytes;
-                    uint8_t* g0 = reinterpret_cast<uint8_t*>(((uint64_t)hs.y << 32) | hs.x);
-                    const bool plain = ((reinterpret_cast<uintptr_t>(g0) | (uintptr_t)len | (uintptr_t)dpitch) & 15) == 0;
-                    const int my_row = sw + lane * n_store_warps;
-                    if (my_row < n_rows) {
-                        uint8_t* g = g0 + (int64_t)my_row * dpitch;
-                        const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
-                        const int head = (16 - off) & 15;
-                        const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
-                        if ((off & 3) == 0 && body > 0)
-                            bulk_s2g(g + head, smem_s + (uint32_t)(obuf + my_row * a.out_pitch + off + head), (uint32_t)body);
-                    }
-                    bulk_commit();
-                    if (!plain) {
-                        for (int i = sw; i < n_rows; i += n_store_warps) {
-                            uint8_t* g = g0 + (int64_t)i * dpitch;
-                            const int off = (int)(reinterpret_cast<uintptr_t>(g) & 15);
-                            const int head = min((16 - off) & 15, len);
-                            const int body = (len - head) > 0 ? ((len - head) & ~15) : 0;
-                            const int s = obuf + i * a.out_pitch + (off & 12);       // the row's first byte
-                            // <= 15 head bytes and <= 15 tail bytes, one lane per byte
-                            if (lane < 16) {
-                                if (lane < head) g[lane] = smem[s + lane];
-                            } else {
-                                const int qq = head + body + (lane - 16);
-                                if (qq < len) g[qq] = smem[s + qq];
-                            }
-                            const int r = off & 3;
-                            if (r != 0) {
-                                // destination chunk c = bytes [head + 16 c, + 16) of the row = shared bytes
-                                // [A - r, A - r + 16) with A = s + head + 16 c + r a multiple of 16.  Four chunks per
-                                // lane and pass, loads first; the word before a chunk is the last word of the chunk
-                                // of the lane below (lane 0 reads its own).
-                                const uint32_t shift = 8u * (uint32_t)(4 - r);
-                                const int nch = body >> 4;
-                                const int A0 = s + head + r;
-                                uint8_t* gp = g + head;
-                                for (int c0 = 0; c0 < nch; c0 += 128) {
-                                    uint4 w[4];
-                                    uint32_t wm[4];
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const int c = c0 + 32 * k + lane;
-                                        w[k] = c < nch ? ld128(A0 + 16 * c) : make_uint4(0u, 0u, 0u, 0u);
-                                    }
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        wm[k] = __shfl_up_sync(0xffffffffu, w[k].w, 1);
-                                        if (lane == 0) wm[k] = ld32(A0 + 16 * (c0 + 32 * k) - 4);
-                                    }
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const int c = c0 + 32 * k + lane;
-                                        uint4 o;
-                                        o.x = __funnelshift_r(wm[k], w[k].x, shift);
-                                        o.y = __funnelshift_r(w[k].x, w[k].y, shift);
-                                        o.z = __funnelshift_r(w[k].y, w[k].z, shift);
-                                        o.w = __funnelshift_r(w[k].z, w[k].w, shift);
-                                        if (c < nch) *reinterpret_cast<uint4*>(gp + 16 * c) = o;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    bulk_wait_read0();                                 // the tile has left shared memory
-                }
-                __syncwarp();
-                if (lane == 0 && sw == 0 && a.trace != nullptr) {
-                    if (a.trace[(size_t)blockIdx.x * 8 + 4] == 0ull) trace_stamp(a, 4);   // first tile shipped
-                    trace_stamp(a, 5);                                                     // latest tile shipped
-                }
-                if (lane == 0) mbar_arrive(ofree_s + 8u * ot);        // tile free for the consumers
-                if (++ot == kTiles) { ot = 0; ph ^= 1u; }
-            }
         }
         return;
     }
 
     // =============================== consumer warps ==============================================
     // this thread's output columns inside the strip.  QUAD mapping: 4 tid .. 4 tid + 3.  LANE mapping: columns
-    // 32 j + lane of the warp's 128-column block (the STORES are those of the QUAD mapping in both cases).
+    // 32 j + lane of the warp's 128-column block.
     const int x0 = tid * 4;
     const int xw = (tid & ~31) * 4;   // first column of the warp's block
     int wo[4];                        // byte offset of each column's window inside a staged row span
@@ -775,23 +693,20 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     for (int j = 0; j < 4; ++j) { wo[j] = 0; wl[j] = wh[j] = 0u; }
     bool warp_live = false;           // some lane of this warp owns a column of the strip
     bool lane_map = false;            // this warp runs the LANE mapping in the current strip
-    uint32_t store_ok = 0u;           // this thread stores at least one column (QUAD position)
-    const int out_col = x0 * kC;
+    uint32_t store_ok = 0u;           // this thread owns at least one column of the strip (QUAD position)
     const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 2048 + lane * 4);     // scratch: my RGBX pixels in
-    const uint32_t sq_s = scratch_s + (uint32_t)(warp_idx * 2048 + lane * 16);    //          my four adjacent pixels out
     DirectOps dops{};
-    if (DIRECT) {
-        dops.lane4 = 4u * (uint32_t)lane;
-        dops.pw = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + lane * 12);     // packed row: my 12 bytes in
-        dops.pr = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + lane * 4);      //             my three words out
+    dops.lane4 = 4u * (uint32_t)lane;
+    // packed row P (one pad word in front of it for MODE 2's funnel shifts): my 12 bytes in, my three words out
+    dops.pw = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + lane * 12);
+    dops.pr = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + lane * 4);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            // output word w = lane + 32 k of the warp's row = bytes 4 w .. 4 w + 3 of the RGB stream: pixel
-            // p0 = floor(4 w / 3) (and the next one), starting at channel 4 w - 3 p0
-            const int w = lane + 32 * k, p0 = (4 * w) / 3, c0 = 4 * w - 3 * p0;
-            dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 2048 + 4 * p0);
-            dops.xs[k] = c0 == 0 ? 0x4210u : (c0 == 1 ? 0x5421u : 0x6542u);
-        }
+    for (int k = 0; k < 3; ++k) {
+        // output word w = lane + 32 k of the warp's row = bytes 4 w .. 4 w + 3 of the RGB stream: pixel
+        // p0 = floor(4 w / 3) (and the next one), starting at channel 4 w - 3 p0
+        const int w = lane + 32 * k, p0 = (4 * w) / 3, c0 = 4 * w - 3 * p0;
+        dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 2048 + 4 * p0);
+        dops.xs[k] = c0 == 0 ? 0x4210u : (c0 == 1 ? 0x5421u : 0x6542u);
     }
     int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
 
@@ -850,24 +765,15 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         }
     }
 
-    int st = 0, ot = 0;               // source stage / output tile of the current chunk
-    uint32_t sph = 0u, oph = 1u;      // parities to wait for: stage filled / tile shipped and free
-    for (;; st = st + 1 == kStages ? 0 : st + 1, sph ^= st == 0 ? 1u : 0u,
-            ot = ot + 1 == kTiles ? 0 : ot + 1, oph ^= ot == 0 ? 1u : 0u) {
+    int st = 0;                       // source stage of the current chunk
+    uint32_t sph = 0u;                // parity to wait for: stage filled
+    for (;; st = st + 1 == kStages ? 0 : st + 1, sph ^= st == 0 ? 1u : 0u) {
         const int tab = tab_off0 + st * kTabBytes;
         wait(full_s + 8u * st, sph);
         if (tid == 0 && a.trace != nullptr && a.trace[(size_t)blockIdx.x * 8 + 2] == 0ull) trace_stamp(a, 2);   // first rows landed
         const uint4 h0 = ld128(tab);
         const int n_rows = (int)h0.x;
-        if (!DIRECT) wait(ofree_s + 8u * ot, oph);                          // tile shipped and free
-        if (n_rows < 0) {                                                        // pass the stop on
-            if (!DIRECT) {
-                if (tid == 0) st128(ohdr_off0 + 32 * ot, make_uint4(0xffffffffu, 0u, 0u, 0u));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(odone_s + 8u * ot);
-            }
-            break;
-        }
+        if (n_rows < 0) break;                               // the producer's stop
         const uint32_t flags = h0.y >> 16;
         if (flags & kFlagNewStrip) {                         // new strip: per-column taps and weights
             const uint4 h1 = ld128(tab + 16);
@@ -879,10 +785,6 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             pre_img = -1;                                    // the early setup serves the first segment only
 #pragma unroll
             for (int j = 0; j < 4; ++j) wo[j] = xba[j] < 0 ? 0 : (xba[j] - (int)h1.w) * kC;
-        }
-        if (!DIRECT && tid == 0) {                           // what the store warp needs to ship the tile
-            st128(ohdr_off0 + 32 * ot, make_uint4(h0.x, 0u, 0u, 0u));
-            st128(ohdr_off0 + 32 * ot + 16, ld128(tab + kTabStore));
         }
         if (n_rows == 0) {
             // ---- direct path for one output row whose source span does not fit a stage ----------
@@ -911,16 +813,38 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         } else if (warp_live && !(a.dbg & 1)) {
             const int n_slots = (int)(h0.y & 0xffffu);
             const uint32_t rp_s = smem_s + (uint32_t)(tab + kTabRows);
-            const uint32_t ocol_s = smem_s + (uint32_t)(out_off0 + ot * out_bytes + out_col);
             const uint32_t base = smem_s + (uint32_t)(st * a.stage_bytes) + h0.w;    // first byte of slot 0
             const uint32_t odd = (flags & kFlagOddFirst) ? 1u : 0u;
             uint32_t win[4], sh[4];
-            if (DIRECT) {
+            {
                 // the warp's 384 bytes of a row start 384 * warp bytes after the strip's first byte
                 const uint4 hs = ld128(tab + kTabStore);                         // {image lo, hi, strip row bytes, -}
                 dops.obase = (((uint64_t)hs.y << 32) | hs.x) + (uint64_t)(warp_idx * 384);
                 const int nb = (int)hs.z - warp_idx * 384;                       // bytes of the warp's block in the strip
-                dops.wmask = (4 * lane + 4 <= nb ? 1u : 0u) | (4 * lane + 132 <= nb ? 2u : 0u) | (4 * lane + 260 <= nb ? 4u : 0u);
+                if (MODE == 1) {
+                    dops.wmask = (4 * lane + 4 <= nb ? 1u : 0u) | (4 * lane + 132 <= nb ? 2u : 0u) | (4 * lane + 260 <= nb ? 4u : 0u);
+                } else {
+                    // the block's bytes sit at [k, k + nb) of the aligned word stream, nb = min(bytes left, 384)
+                    const int nbb = nb < 384 ? nb : 384;
+                    uint32_t vm = 0u, em = 0u;
+                    const int edge = lane < 3 ? lane : lane - 4;                   // tail byte nbb - 3 + i | head byte i
+                    const int boff = lane < 3 ? nbb - 3 + lane : lane - 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) {
+                            const int j = lane + 32 * m;
+                            if ((j > 0 || k == 0) && 4 * j + 4 <= k + nbb) vm |= 1u << (4 * k + m);
+                        }
+                        const bool tail = lane < 3 && k + nbb - 3 + edge >= ((k + nbb) & ~3);
+                        const bool head = lane >= 4 && lane < 7 && k > 0 && k + edge < 4;
+                        if (tail || head) em |= 1u << k;
+                    }
+                    dops.wmask = vm;
+                    dops.emask = nbb >= 3 ? em : 0u;
+                    dops.eoff = (uint32_t)boff;
+                    dops.pedge = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + (boff > 0 ? boff : 0));
+                }
             }
             if (flags & kFlagFixedShift) {
 #pragma unroll
@@ -929,41 +853,25 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (!lane_map) sweep_quad<true, false, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
-                else sweep_quad<true, true, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
+                if (!lane_map) sweep_quad<true, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
+                else sweep_quad<true, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (!lane_map) sweep_quad<false, false, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
-                else sweep_quad<false, true, DIRECT>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, ocol_s, odd, store_ok, sx_s, sq_s, dops);
+                if (!lane_map) sweep_quad<false, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
+                else sweep_quad<false, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
             }
         }
-        // publish this warp's part of the tile to the async proxy, then count the warp in
-        if (!DIRECT) fence_proxy_async();
         __syncwarp();
         if (tid == 0 && a.trace != nullptr) {
             if (a.trace[(size_t)blockIdx.x * 8 + 3] == 0ull) trace_stamp(a, 3);   // first chunk swept (warp 0)
             trace_stamp(a, 6);                                                     // latest chunk swept
         }
-        if (lane == 0) {
-            mbar_arrive(sfree_s + 8u * st);
-            if (!DIRECT) mbar_arrive(odone_s + 8u * ot);
-        }
+        if (lane == 0) mbar_arrive(sfree_s + 8u * st);       // this warp is done with the stage
     }
 }
 
 // ---- launch geometry ------------------------------------------------------------------------------
-// A configuration = consumer warps per CTA (each covers 128 output columns) and CTAs per SM; the rows per chunk
-// follow from the shared memory that leaves.  Registers: the quad sweep needs ~120, so about 16 warps fit an SM.
-struct Geometry {
-    int warps;          // consumer warps per CTA
-    int ctas;           // CTAs per SM the kernel is built for
-    int max_cols;       // widest strip (multiple of 16)
-    int store_warps;    // store warps per CTA
-};
-constexpr Geometry kGeo[3] = {{3, 4, 352, 1}, {6, 2, 704, 2}, {11, 1, 1408, 4}};      // with output tiles
-constexpr Geometry kGeoD[3] = {{3, 5, 352, 0}, {6, 2, 704, 0}, {11, 1, 1408, 0}};     // DIRECT stores
-
 struct StripPlan { int n_strips, strip_cols; };
 inline StripPlan plan_strips(int Wo, int max_cols_) {
     StripPlan p;
@@ -978,64 +886,69 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// geometry index for strips of `Wo`-wide outputs: the narrowest configuration that takes the image in one strip,
-// else the widest (ATTWARP_QUAD_GEO = 0 .. 2 forces one: tuning experiments)
-int pick_geometry(int Wo) {
-    const int forced = env_int("ATTWARP_QUAD_GEO", -1);
-    if (forced >= 0 && forced <= 2) return forced;
-    for (int g = 0; g < 3; ++g)
-        if (Wo <= kGeo[g].max_cols) return g;
-    return 2;
-}
-
-template <int G, bool DIRECT>
-int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
-    constexpr Geometry geo = DIRECT ? kGeoD[G] : kGeo[G];
-    constexpr int kThreads = (geo.warps + 1 + geo.store_warps) * 32;
-    a.store_warps = geo.store_warps;
-    auto kern = remap_u8_quad_kernel<kThreads, geo.ctas, DIRECT>;
+// One launch: `kern` (a build of the kernel whose launch bounds admit it) run with `warps` consumer warps + the
+// producer warp per CTA, `ctas` CTAs per SM wanted.
+using QuadKernel = void (*)(const QuadArgs);
+int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cudaStream_t st) {
+    const int threads = (warps + 1) * 32;
     a.dbg = env_int("ATTWARP_REMAP_DBG", 0);
-    a.out_pitch = (cols * kC + 15 + 15) & ~15;              // + the 16-byte phase of the destination
     const int unit_pitch = (((cols + 1) * kC + 45 + 15) & ~15) + 16;      // a slot at unit scale
-    // ring depths (ATTWARP_QUAD_RING = stages * 10 + tiles, tuning experiments) and rows per chunk: as many as the
-    // shared memory of 1 / ctas of an SM holds (stages of R + 2 slots, tiles of R rows), at most kMaxRows
-    int stages = 2, tiles = DIRECT ? 0 : 2;
+    // ring depth (ATTWARP_QUAD_RING = 2 .. 4 stages, tuning experiments) and rows per chunk: as many as the shared
+    // memory of 1 / ctas of an SM holds (stages of R + 2 slots), at most kMaxRows
+    int stages = 2;
     {
         const int ring = env_int("ATTWARP_QUAD_RING", 0);
-        if (ring / 10 >= 2 && ring / 10 <= kMaxRing && ring % 10 >= 2 && ring % 10 <= kMaxRing) { stages = ring / 10; tiles = DIRECT ? 0 : ring % 10; }
+        if (ring >= 2 && ring <= kMaxRing) stages = ring;
     }
     a.stages = stages;
-    a.tiles = tiles;
-    const int scratch = 2048 * geo.warps + 1024;
-    const int budget = (227 * 1024) / geo.ctas - 1024 - stages * kTabBytes - tiles * 32 - 16 * kMaxRing - 256 - scratch;
-    int R = (budget - stages * (2 * unit_pitch + 64 + 128)) / (stages * unit_pitch + tiles * a.out_pitch);
+    const int scratch = 2048 * warps + 1024;
+    const int budget = (227 * 1024) / ctas - 1024 - stages * kTabBytes - 16 * kMaxRing - 256 - scratch;
+    int R = (budget - stages * (2 * unit_pitch + 64 + 128)) / (stages * unit_pitch);
     R = R > kMaxRows ? kMaxRows : R;
     const int forced = env_int("ATTWARP_QUAD_ROWS", 0);
     if (forced >= 2 && forced <= R) R = forced;
     if (R < 2) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: strips of %d columns do not fit shared memory", cols);
     a.rows = R;
     a.stage_bytes = ((R + 2) * unit_pitch + 64 + 127) & ~127;
-    const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + (size_t)tiles * ((size_t)R * a.out_pitch + 32) +
-                              2 * (size_t)(stages + tiles) * sizeof(uint64_t) + 16 + (size_t)scratch;
+    const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + 2 * (size_t)stages * sizeof(uint64_t) + 16 +
+                              (size_t)scratch;
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     a.wait_hint_ns = env_int("ATTWARP_QUAD_WAIT_HINT", 0);
     a.roles_first = env_int("ATTWARP_QUAD_ROLES_FIRST", 0);
-    struct Cfg { size_t smem; int dev, occ; };
-    static thread_local Cfg c = {0, -1, 0};
-    int dev = 0;
+    // per (kernel, device): the largest shared-memory size configured so far; per (kernel, device, threads, smem): occupancy
+    struct Key {
+        QuadKernel k; int dev, threads; size_t smem;
+        bool operator<(const Key& o) const { return std::tie(k, dev, threads, smem) < std::tie(o.k, o.dev, o.threads, o.smem); }
+    };
+    static std::mutex mu;
+    static std::map<std::pair<QuadKernel, int>, size_t> configured;
+    static std::map<Key, int> occupancy;
+    int dev = 0, occ_q = 0;
     AW_CUDA(cudaGetDevice(&dev));
-    if (c.smem != smem_bytes || c.dev != dev) {
-        AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        int o = 0;
-        AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem_bytes));
-        const int cap = env_int("ATTWARP_REMAP_CTAS_PER_SM", 0);
-        if (cap >= 1 && cap < o) o = cap;
-        c = Cfg{smem_bytes, dev, o};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& conf = configured[{kern, dev}];
+        if (smem_bytes > conf) {
+            AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            conf = smem_bytes;
+        }
+        const Key key{kern, dev, threads, smem_bytes};
+        auto it = occupancy.find(key);
+        if (it == occupancy.end()) {
+            int o = 0;
+            AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem_bytes));
+            it = occupancy.emplace(key, o).first;
+        }
+        occ_q = it->second;
     }
-    if (c.occ < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
+    {
+        const int cap = env_int("ATTWARP_REMAP_CTAS_PER_SM", 0);
+        if (cap >= 1 && cap < occ_q) occ_q = cap;
+    }
+    if (occ_q < 1) return fail(ATTWARP_ERR_CUDA, "remap: kernel does not fit an SM (%zu B shared)", smem_bytes);
     // attwarp_set_sm_share(2): leave half of every SM to the kernels of another stream
     const int share = sm_share();
-    const int occ = c.occ >= 2 * share ? c.occ / share : (c.occ >= 2 && share > 1 ? c.occ / 2 : c.occ);
+    const int occ = occ_q >= 2 * share ? occ_q / share : (occ_q >= 2 && share > 1 ? occ_q / 2 : occ_q);
     const int64_t cap = (int64_t)sm_count() * occ;
     const int grid = (int)(a.total_units < cap ? a.total_units : cap);
     // ATTWARP_REMAP_TRACE=<file>: per-CTA global-timer stamps of every launch, appended to the file (debugging
@@ -1053,13 +966,13 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
         AW_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(unsigned long long) * 8 * (size_t)grid, st));
         a.trace = dbuf;
     }
-    kern<<<grid, kThreads, smem_bytes, st>>>(a);
+    kern<<<grid, threads, smem_bytes, st>>>(a);
     if (a.trace != nullptr) {
         std::vector<unsigned long long> h((size_t)grid * 8);
         AW_CUDA(cudaStreamSynchronize(st));
         AW_CUDA(cudaMemcpy(h.data(), a.trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(trace_path, "a")) {
-            fprintf(f, "launch grid=%d threads=%d rows=%d smem=%zu\n", grid, kThreads, a.rows, smem_bytes);
+            fprintf(f, "launch grid=%d threads=%d rows=%d smem=%zu\n", grid, threads, a.rows, smem_bytes);
             for (int i = 0; i < grid; ++i) {
                 fprintf(f, "%d", i);
                 for (int k = 0; k < 8; ++k) fprintf(f, " %llu", h[(size_t)i * 8 + k]);
@@ -1071,24 +984,35 @@ int launch_geo(QuadArgs& a, int cols, cudaStream_t st) {
     return check_launch("remap_u8_quad_kernel");
 }
 
-// direct: every destination row of the launch is 4-byte aligned (no output tile, consumers store to global memory)
-int launch_by_geometry(int g, bool direct, QuadArgs& a, int cols, cudaStream_t st) {
-    if (direct) {
-        switch (g) {
-            case 0: return launch_geo<0, true>(a, cols, st);
-            case 1: return launch_geo<1, true>(a, cols, st);
-            default: return launch_geo<2, true>(a, cols, st);
-        }
-    }
-    switch (g) {
-        case 0: return launch_geo<0, false>(a, cols, st);
-        case 1: return launch_geo<1, false>(a, cols, st);
-        default: return launch_geo<2, false>(a, cols, st);
-    }
+// The CTA gets exactly the consumer warps the strips need -- ceil(columns / 128), at least 3 -- and the SM as many
+// CTAs as its registers hold.  Builds of the kernel by register budget (launch bounds): <= 3 consumer warps (5 CTAs
+// per SM), <= 6 (2-3 CTAs), <= 11 and 12 (one CTA, ~120 registers) and a 96-register build that runs 7..9 warps with
+// two CTAs per SM and 13..16 (strips of <= 2048 columns) with one.
+constexpr int kDirectMaxWarps = 16;
+inline int direct_warps(int cols) {
+    const int w = (cols + 127) / 128;
+    return w < 3 ? 3 : w;
+}
+// ATTWARP_QUAD_MAXW = 3 .. 16 narrows the widest strip to that many warps (tuning experiments)
+inline int direct_max_cols() {
+    const int w = env_int("ATTWARP_QUAD_MAXW", kDirectMaxWarps);
+    return (w >= 3 && w <= kDirectMaxWarps ? w : kDirectMaxWarps) * 128;
+}
+template <int MODE>
+int launch_direct_mode(QuadArgs& a, int cols, cudaStream_t st) {
+    const int w = direct_warps(cols);
+    if (w <= 3) return launch_core(remap_u8_quad_kernel<128, 5, MODE>, w, 5, a, cols, st);
+    if (w <= 6) return launch_core(remap_u8_quad_kernel<224, 2, MODE>, w, w == 4 ? 3 : 2, a, cols, st);
+    if (w <= 9) return launch_core(remap_u8_quad_kernel<(kDirectMaxWarps + 1) * 32, 1, MODE>, w, 2, a, cols, st);
+    if (w <= 11) return launch_core(remap_u8_quad_kernel<384, 1, MODE>, w, 1, a, cols, st);
+    if (w <= 12) return launch_core(remap_u8_quad_kernel<416, 1, MODE>, w, 1, a, cols, st);
+    return launch_core(remap_u8_quad_kernel<(kDirectMaxWarps + 1) * 32, 1, MODE>, w, 1, a, cols, st);
+}
+// aligned: every destination row of the launch starts at a multiple of 4 bytes
+int launch_direct(QuadArgs& a, int cols, bool aligned, cudaStream_t st) {
+    return aligned ? launch_direct_mode<1>(a, cols, st) : launch_direct_mode<2>(a, cols, st);
 }
 
-// ATTWARP_QUAD_DIRECT=0 keeps the output tiles + store warps for aligned images too (A/B comparisons)
-bool direct_allowed() { return env_int("ATTWARP_QUAD_DIRECT", 1) != 0; }
 inline bool rows_word_aligned(const void* dst, int Wo) {
     return ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)(Wo * kC)) & 3) == 0;
 }
@@ -1108,8 +1032,7 @@ bool remap_quad_enabled() {
 int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, int Ho, int Wo, const float* map_x,
                          const float* map_y, cudaStream_t st) {
     QuadArgs a{};
-    const int g = pick_geometry(Wo);
-    const StripPlan sp = plan_strips(Wo, kGeo[g].max_cols);
+    const StripPlan sp = plan_strips(Wo, direct_max_cols());
     a.n_strips = sp.n_strips;
     a.strip_cols = sp.strip_cols;
     a.src = static_cast<const uint8_t*>(src);
@@ -1123,44 +1046,82 @@ int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, in
     const int64_t total = (int64_t)n_img * a.n_strips * a.n_rowtiles;
     if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
     a.total_units = (int)total;
-    return launch_by_geometry(g, direct_allowed() && rows_word_aligned(dst, Wo), a, Wo < a.strip_cols ? Wo : a.strip_cols, st);
+    const int cols = Wo < a.strip_cols ? Wo : a.strip_cols;
+    return launch_direct(a, cols, rows_word_aligned(dst, Wo), st);
 }
 
-// Ragged batch.  Images are grouped into width classes, one launch per class with the geometry that fits it
-// (a 300-wide image in a CTA built for 1408 columns would leave eight of its eleven consumer warps idle):
-//   class 0: Wo <= 352 (3 consumer warps per CTA), class 1: Wo <= 704 (6), class 2: wider (11; strips of <= 1408);
-//   classes 3..5: the same widths for images whose destination rows are not 4-byte aligned (output tiles + store
-//   warps instead of direct stores).
+// Ragged batch.  Images are grouped into width classes, one launch per class with the geometry that fits it (a
+// 300-wide image in a CTA built for 1408 columns would leave eight of its eleven consumer warps idle):
+//   classes 0 .. 13   destination rows 4-byte aligned (MODE 1): strips of <= 384 columns (3 consumer warps), then one
+//                     class per extra 128 columns up to 2048 (16 warps); wider images are cut into strips.  A class
+//                     with less than ~2 M output pixels (less work than a launch's ramp) joins the next wider
+//                     non-empty one.
+//   classes 14 .. 27  the same widths for rows at any alignment (MODE 2)
 // Step 1: `host` (n + 1 entries, batch order) gets each image's strip plan and is uploaded to dev_main (the maps
 // kernel reads shapes and map pointers from it); a copy grouped by class, every group followed by an entry that
-// carries its unit total, is uploaded to dev_sorted (n + 3 entries).
-constexpr int kClassGeo[3] = {0, 1, 2};
-inline int width_class(int Wo) { return Wo <= kGeo[kClassGeo[0]].max_cols ? 0 : (Wo <= kGeo[kClassGeo[1]].max_cols ? 1 : 2); }
+// carries its unit total, is uploaded to dev_sorted (n + kRaggedClasses entries).
+constexpr int kDirectClasses = kDirectMaxWarps - 2;
+static_assert(2 * kDirectClasses == kRaggedClasses, "class table");
 
 int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
                                         RaggedQuadPlan* plan, cudaStream_t st) {
     static thread_local std::vector<RaggedImage> sorted;
+    static thread_local std::vector<int> cls;
     sorted.assign((size_t)n + kRaggedClasses, RaggedImage{});
+    cls.assign((size_t)n, 0);
     *plan = RaggedQuadPlan{};
-    const int forced = env_int("ATTWARP_QUAD_GEO", -1);
-    const bool direct_ok = direct_allowed();
-    auto cls = [&](const RaggedImage& im) {
-        const int wc = forced >= 0 ? 2 : width_class(im.Wo);
-        return wc + ((direct_ok && rows_word_aligned(im.dst, im.Wo)) ? 0 : 3);
-    };
-    for (int i = 0; i < n; ++i) plan->count[cls(host[i])]++;
+    const int dmax = direct_max_cols();
+    int64_t px[kRaggedClasses] = {};
+    for (int i = 0; i < n; ++i) {
+        const RaggedImage& im = host[i];
+        const StripPlan sp = plan_strips(im.Wo, dmax);
+        const int c = direct_warps(im.Wo < sp.strip_cols ? im.Wo : sp.strip_cols) - 3 +
+                      (rows_word_aligned(im.dst, im.Wo) ? 0 : kDirectClasses);
+        cls[(size_t)i] = c;
+        px[c] += (int64_t)im.Wo * im.Ho;
+    }
+    // An aligned class next to a non-empty any-alignment class of the same width joins it unless it is big enough
+    // to pay for a launch of its own (MODE 2 handles aligned rows too, ~20 % slower; a launch's ramp and tail cost
+    // ~10 us).  Then small classes join the next wider non-empty one.
+    int join[kRaggedClasses];
+    for (int c = 0; c < kRaggedClasses; ++c) join[c] = c;
+    const int64_t min_px = (int64_t)env_int("ATTWARP_QUAD_CLASS_MIN_PX", 2000000);
+    const int64_t min_aligned_px = (int64_t)env_int("ATTWARP_QUAD_ALIGNED_MIN_PX", 32000000);
+    for (int c = 0; c < kDirectClasses; ++c) {
+        if (px[c] == 0 || px[c] >= min_aligned_px || px[c + kDirectClasses] == 0) continue;
+        px[c + kDirectClasses] += px[c];
+        px[c] = 0;
+        join[c] = c + kDirectClasses;
+    }
+    for (int half = 0; half < 2; ++half) {
+        const int c0 = half * kDirectClasses, c1 = c0 + kDirectClasses;
+        for (int c = c0; c + 1 < c1; ++c) {
+            if (px[c] == 0 || px[c] >= min_px) continue;
+            int up = c + 1;
+            while (up < c1 && px[up] == 0) ++up;
+            if (up == c1) continue;
+            px[up] += px[c];
+            px[c] = 0;
+            join[c] = up;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        int c = cls[(size_t)i];
+        while (join[c] != c) c = join[c];
+        cls[(size_t)i] = c;
+        plan->count[c]++;
+    }
     int pos = 0;
     for (int c = 0; c < kRaggedClasses; ++c) {
         plan->offset[c] = pos;
-        plan->geo[c] = forced >= 0 && forced <= 2 ? forced : kClassGeo[c % 3];
-        plan->direct[c] = c < 3 ? 1 : 0;
+        plan->mode[c] = c < kDirectClasses ? 1 : 2;          // the kernel's MODE
         pos += plan->count[c] + 1;
     }
     int fill[kRaggedClasses] = {};
     int64_t total[kRaggedClasses] = {};
     for (int i = 0; i < n; ++i) {
-        const int c = cls(host[i]);
-        const StripPlan sp = plan_strips(host[i].Wo, kGeo[plan->geo[c]].max_cols);
+        const int c = cls[(size_t)i];
+        const StripPlan sp = plan_strips(host[i].Wo, dmax);
         const int cols = host[i].Wo < sp.strip_cols ? host[i].Wo : sp.strip_cols;
         const int units = (cols + 127) / 128;
         if (sp.n_strips > 0xffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: image %d is too wide", i);
@@ -1190,7 +1151,7 @@ int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImag
         a.imgs = dev_sorted + plan.offset[c];
         a.n_img = plan.count[c];
         a.total_units = plan.total_units[c];
-        const int rc = launch_by_geometry(plan.geo[c], plan.direct[c] != 0, a, plan.max_strip[c], st);
+        const int rc = launch_direct(a, plan.max_strip[c], plan.mode[c] == 1, st);
         if (rc != ATTWARP_OK) return rc;
     }
     return ATTWARP_OK;

@@ -158,6 +158,30 @@ def mota_mask(tok: torch.Tensor, image_hw, kernel_size: int = 3, enhance_coe: fl
     return resize_lanczos_u8(u8, image_hw)
 
 
+def maps_from_mota_tokens(tok: torch.Tensor, image_hw, out_size=None, kernel_size: int = 3, enhance_coe: float = 10.0,
+                          apply_inverse: bool = False):
+    """tok [B,gh,gw] -> (map_x, map_y) of the driver flow ``blend_mask`` -> ``save_warped_image(..., "identity")``
+    (llava.py:240-256 then new_method.py:207-261) for callers that only warp: the image-size uint8 mask is never
+    written, its marginals are summed where the LANCZOS resize computes it.  Same maps as
+    ``maps_from_attention(mota_mask(tok, image_hw), out_size)``."""
+    lib = load()
+    _, u8 = revise_mask(tok, kernel_size, enhance_coe, return_u8=True)
+    B, gh, gw = u8.shape
+    H, W = int(image_hw[0]), int(image_hw[1])
+    Ho, Wo = (H, W) if out_size is None else (int(out_size[0]), int(out_size[1]))
+    wsb = lib.attwarp_maps_from_mask_workspace_bytes(B, gh, gw, H, W)
+    if wsb == 0:        # not an up-scaling the fused kernel takes: the two device steps
+        return maps_from_attention(resize_lanczos_u8(u8, (H, W)), (Ho, Wo), apply_inverse=apply_inverse)
+    tp = _tp("identity", 1.0, 1.0, apply_inverse)
+    map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)
+    map_y = torch.empty(B, Ho, dtype=torch.float32, device=tok.device)
+    ws = _workspace(wsb, tok.device)
+    with torch.cuda.device(tok.device):
+        check(lib.attwarp_maps_from_mask(ptr(u8), B, gh, gw, H, W, Wo, Ho, C.byref(tp), ptr(ws), ws.numel(),
+                                         ptr(map_x), ptr(map_y), current_stream(tok.device)))
+    return map_x, map_y
+
+
 # --------------------------------------------------------------------------------------------
 # stages 2b-4
 # --------------------------------------------------------------------------------------------

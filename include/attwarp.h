@@ -192,6 +192,18 @@ int attwarp_revise_mask(const float* tok, int B, int gh, int gw, int kernel_size
                         float* revised, void* mask_u8, void* stream);
 int attwarp_resize_lanczos_u8(const void* src, int B, int h, int w, int Ho, int Wo, void* dst, void* stream);
 
+/* attwarp_maps_from_mask: the two steps above fused with stage 2b for the flow that only warps (the mask itself
+ * is not kept): mask_u8 [B][h][w] (attwarp_revise_mask's uint8 output) -> separable maps of the image whose
+ * attention is that mask resized to H x W with LANCZOS -- llava.py:253 followed by new_method.py:207-261 -- with
+ * the H x W mask never written to memory (its marginal sums are taken where it is computed; exact integers).
+ * Identity transform and up-scaling (H > h, W > w) only: ATTWARP_ERR_UNSUPPORTED otherwise (resize, then
+ * attwarp_maps_from_attention).  Workspace: attwarp_maps_from_mask_workspace_bytes (0 = shape not supported).
+ */
+size_t attwarp_maps_from_mask_workspace_bytes(int B, int h, int w, int H, int W);
+int attwarp_maps_from_mask(const void* mask_u8, int B, int h, int w, int H, int W, int Wo, int Ho,
+                           const attwarp_transform_params* tp, void* workspace, size_t workspace_bytes,
+                           float* map_x, float* map_y, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * attwarp_warp_from_pdfs: predicted marginal PDFs -> warped images in three launches (BASELINE
  * configs[4]).  Replaces the chain of model/marginalnet_full_dataset/trainer.py:212-218, 285-289:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Stage-5 (uint8 resample) timing probe: the kernel alone at the bench shapes, back-to-back launches over rotating
-buffers, optionally with the kernel's debug switches (ATTWARP_REMAP_DBG: 1 = skip the sweep, 2 = skip the tile
-stores, 3 = both -> what the load pipeline + launch ramp cost without the arithmetic).  Never a bench number.
+buffers, optionally with the kernel's debug switch (ATTWARP_REMAP_DBG=1: skip the sweep -> what the load pipeline +
+launch ramp cost without the arithmetic and the stores).  Never a bench number.
 
     python profiles/s5_probe.py [--dbg]
 """
@@ -33,15 +33,20 @@ def maps(B, side, grid, kind):
     return ops.maps_from_tokens(tok, (side, side))
 
 
-def run(name, B, side, grid, kind, layout="hwc", C=3, R=4):
+def run(name, B, side, grid, kind, layout="hwc", C=3, R=4, wside=None):
     if args.only and not name.strip().startswith(args.only):
         return
-    shape = (B, side, side, C) if layout == "hwc" else (B, C, side, side)
+    wside = side if wside is None else wside
+    shape = (B, side, wside, C) if layout == "hwc" else (B, C, side, wside)
     imgs = [torch.randint(0, 256, shape, device=dev, dtype=torch.uint8, generator=gen) for _ in range(R)]
     outs = [torch.empty_like(i) for i in imgs]
-    mx, my = maps(B, side, grid, kind)
+    if wside != side:
+        tok = torch.rand(B, grid, grid, device=dev, generator=gen) ** 3
+        mx, my = ops.maps_from_tokens((tok / tok.sum(dim=(1, 2), keepdim=True)).contiguous(), (side, wside))
+    else:
+        mx, my = maps(B, side, grid, kind)
     by = 2 * imgs[0].numel()
-    for dbg in (["0", "1", "2", "3"] if args.dbg else ["0"]):
+    for dbg in (["0", "1"] if args.dbg else ["0"]):
         os.environ["ATTWARP_REMAP_DBG"] = dbg
         for i in range(3):
             ops.remap_bilinear(imgs[i % R], mx, my, layout, out=outs[i % R])
@@ -61,6 +66,8 @@ def run(name, B, side, grid, kind, layout="hwc", C=3, R=4):
 
 run("c2  256x336^2 hwc near-uniform", 256, 336, 24, "c2", R=8)
 run("c2  256x336^2 hwc rand^3", 256, 336, 24, "c3", R=8)
+run("c2u 256x336x335 rows unaligned", 256, 336, 24, "c3", R=8, wside=335)
+run("c3u 64x1344x1343 rows unaligned", 64, 1344, 48, "c3", wside=1343)
 run("    1024x336^2 hwc near-uniform", 1024, 336, 24, "c2", R=3)
 run("c3  64x1344^2 hwc rand^3 48x48", 64, 1344, 48, "c3")
 run("    256x1344^2 hwc rand^3 48x48", 256, 1344, 48, "c3", R=2)

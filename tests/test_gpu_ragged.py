@@ -42,6 +42,27 @@ def test_ragged_vs_oracle(C, transform):
     _check(imgs, toks, out_sizes, outs, transform)
 
 
+@pytest.mark.parametrize("min_px", ["0", "2000000"])
+def test_ragged_every_width_class(min_px, monkeypatch):
+    """Stage 5 groups the images of a ragged batch by the consumer warps their strips need (one class per 128 output
+    columns from 384 to 2048, wider images cut into strips) and by whether their rows are 4-byte aligned (direct
+    stores) or not (output tiles): one image per class, both alignments, with and without the merging of small
+    classes into wider ones."""
+    need_gpu()
+    from attwarp_b200 import ops
+    monkeypatch.setenv("ATTWARP_QUAD_CLASS_MIN_PX", min_px)
+    rng = np.random.default_rng(23)
+    widths = [100, 384, 388, 512, 516, 640, 700, 768, 900, 1024, 1152, 1280, 1283, 1408, 1536, 1664, 1792, 1920, 2048,
+              2052, 2600, 4100, 1345, 350]
+    sizes = [(20 + (k * 7) % 23, max(16, w - (k % 3) * 9)) for k, w in enumerate(widths)]
+    out_sizes = [(24 + (k * 5) % 19, w) for k, w in enumerate(widths)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    toks = _tokens(len(sizes), 8, seed=6)
+    outs = ops.warp_ragged_from_tokens(dev(toks), [dev(i) for i in imgs], out_sizes)
+    torch.cuda.synchronize()
+    _check(imgs, toks, out_sizes, outs, "identity", max_off=5e-3)
+
+
 def test_ragged_matches_uniform_batch():
     """The same images through the ragged table and through the uniform-batch entry: bit-equal."""
     need_gpu()

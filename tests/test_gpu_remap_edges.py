@@ -115,6 +115,34 @@ def test_odd_pitches(W, Wo):
     assert np.array_equal(out, ON.remap(img[0], mx[0], my[0]))
 
 
+@pytest.mark.parametrize("Wo", [1, 2, 5, 127, 128, 129, 335, 336, 385, 500, 1000, 1347, 2047, 2050])
+@pytest.mark.parametrize("policy", ["0", "2"])
+def test_destination_at_every_alignment(Wo, policy, monkeypatch):
+    """3-channel rows written straight from the consumer warps: a destination whose first byte sits 0..3 bytes past
+    a 4-byte boundary and whose row pitch 3 * Wo walks through every alignment.  Guard bytes around the destination
+    must stay untouched (the partial first / last words of a warp's block are stored byte by byte)."""
+    need_gpu()
+    from attwarp_b200 import ops
+    monkeypatch.setenv("ATTWARP_QUAD_MAP", policy)
+    rng = np.random.default_rng(Wo)
+    B, H, W, Ho = 2, 37, max(2, Wo - 3), 41
+    img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    mx = np.sort(rng.random((B, Wo)) * W, axis=1).astype(np.float32)
+    my = np.sort(rng.random((B, Ho)) * H, axis=1).astype(np.float32)
+    refs = [ON.remap(img[b], mx[b], my[b]) for b in range(B)]
+    n = B * Ho * Wo * 3
+    for off in range(4):
+        flat = torch.full((n + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        out = flat[16 + off:16 + off + n].view(B, Ho, Wo, 3)
+        ops.remap_bilinear(dev(img), dev(mx), dev(my), "hwc", out=out)
+        torch.cuda.synchronize()
+        got = flat.cpu().numpy()
+        assert (got[:16 + off] == 0xA5).all() and (got[16 + off + n:] == 0xA5).all(), f"offset {off}: guard bytes overwritten"
+        o = got[16 + off:16 + off + n].reshape(B, Ho, Wo, 3)
+        for b in range(B):
+            assert np.array_equal(o[b], hwc(refs[b])), f"offset {off}, image {b}"
+
+
 @pytest.mark.parametrize("H,W,Ho,Wo", [(336, 336, 336, 336), (336, 336, 500, 500), (1344, 1344, 1344, 1344),
                                        (301, 224, 500, 500), (500, 333, 400, 700), (97, 53, 64, 200)])
 def test_quad_kernel_mappings_agree(H, W, Ho, Wo, monkeypatch):

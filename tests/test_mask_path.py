@@ -138,3 +138,30 @@ def test_gpu_c1_driver_chain(gm, name, out_hw, record_property):
         assert np.array_equal(np.array(pil_mask), mask_h)
         rev = AE.revise_mask(torch.from_numpy(tok), 3, 10)
         assert rev.shape == (24, 24) and rev.device.type == "cpu"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw,out_hw", [((336, 336), (500, 500)), ((500, 333), (500, 500)), ((1344, 1344), (1344, 1344)),
+                                       ((337, 339), (336, 336)), ((224, 2048), (300, 700))])
+def test_gpu_maps_from_mota_tokens_fused(hw, out_hw):
+    """token map -> revise_mask -> (LANCZOS resize to image size + marginal sums in one kernel, the
+    H x W mask never written) -> maps.  The sums are exact integers either way, so the maps must equal those of the
+    two-step device path (mota_mask + maps_from_attention) to float32 rounding of the last double ulp: compared
+    bit-wise, with at most a few entries allowed to differ by one float32 ulp."""
+    _need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(hw[0] + hw[1])
+    tok = torch.from_numpy(rng.random((5, 24, 24)).astype(np.float32) ** 2).cuda()
+    mask = ops.mota_mask(tok, hw)
+    ref_x, ref_y = ops.maps_from_attention(mask, out_hw, "identity")
+    got_x, got_y = ops.maps_from_mota_tokens(tok, hw, out_hw)
+    torch.cuda.synchronize()
+    for got, ref in ((got_x, ref_x), (got_y, ref_y)):
+        g, r = got.cpu().numpy(), ref.cpu().numpy()
+        assert g.shape == r.shape
+        ulp = np.abs(g.view(np.int32).astype(np.int64) - r.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1 and (ulp != 0).mean() <= 1e-3, (int(ulp.max()), float((ulp != 0).mean()))
+    # and against the oracle's marginals of the GPU's own mask (float64, term by term)
+    m = mask[0].cpu().numpy()
+    ox, oy, _, _ = ON.inverse_maps(m, out_hw[1], out_hw[0], "identity")
+    assert np.abs(got_x[0].cpu().numpy() - ox).max() <= 1e-3 and np.abs(got_y[0].cpu().numpy() - oy).max() <= 1e-3
