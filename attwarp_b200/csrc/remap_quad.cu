@@ -135,7 +135,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     AWQ_V1(c, 0) AWQ_V1(c, 1) AWQ_V1(c, 2) AWQ_V1(d, 0) AWQ_V1(d, 1) AWQ_V1(d, 2)
 // Emit of one output row, destination rows 4-byte aligned (MODE 1): the 12 top bytes of the vertical blends are
 // packed into 3 words (prmt: x.b3 | y.b3 << 8, then the low halves of two pairs); the warp's 384 output bytes change
-// hands through the scratch (two buffers used alternately: one bar.warp.sync per row) so that lane t ends up with
+// hands through the scratch (a bar.warp.sync before it is written and one before it is read) so that lane t ends up with
 // WORDS t, t + 32, t + 64 of them -- three fully coalesced 128-byte global stores per row.  %49 = address of the
 // warp's first destination byte at row offset 0 (64-bit), %50 = 4 * lane, bits 0..2 of %53 = word k lies inside the
 // strip.
@@ -156,11 +156,11 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
     "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
     "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
+    "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     "bar.warp.sync 0xffffffff;\n"                               \
     "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
     AWQ_DIRECT_ADDR                                             \
-    "xor.b32 pw, pw, 512;\n xor.b32 pr, pr, 512;\n"             \
     "@pw0 st.global.b32 [oa], q0;\n"                            \
     "@pw1 st.global.b32 [oa+128], q1;\n"                        \
     "@pw2 st.global.b32 [oa+256], q2;\n"
@@ -174,13 +174,13 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
     "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
     "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
+    "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
     "bar.warp.sync 0xffffffff;\n"                               \
     "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
     "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
     "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
     AWQ_DIRECT_ADDR                                             \
-    "xor.b32 sx, sx, 512;\n xor.b32 xa0, xa0, 512;\n xor.b32 xa1, xa1, 512;\n xor.b32 xa2, xa2, 512;\n" \
     "prmt.b32 q0, q0, q1, xs0;\n"                               \
     "prmt.b32 q2, q2, q3, xs1;\n"                               \
     "prmt.b32 q4, q4, q5, xs2;\n"                               \
@@ -214,8 +214,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
     "@pe ld.shared.u8 o, [pedge];\n"                            \
     "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n" \
-    "@pe st.global.u8 [oa], o;\n"                               \
-    "xor.b32 pw, pw, 512;\n xor.b32 pr, pr, 512;\n xor.b32 pedge, pedge, 512;\n"
+    "@pe st.global.u8 [oa], o;\n"
 #define AWQ_EMIT_WU                                             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
@@ -227,6 +226,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
     "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
     "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
+    "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
 #define AWQ_EMIT_LU                                             \
@@ -235,12 +235,12 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
     "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
     "prmt.b32 q3, vd0, vd1, 0x0073;\n prmt.b32 q3, q3, vd2, 0x0710;\n"  \
+    "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
     "bar.warp.sync 0xffffffff;\n"                               \
     "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
     "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
     "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
-    "xor.b32 sx, sx, 512;\n xor.b32 xa0, xa0, 512;\n xor.b32 xa1, xa1, 512;\n xor.b32 xa2, xa2, 512;\n" \
     "prmt.b32 q0, q0, q1, xs0;\n"                               \
     "prmt.b32 q2, q2, q3, xs1;\n"                               \
     "prmt.b32 q4, q4, q5, xs2;\n"                               \
@@ -397,6 +397,7 @@ struct QuadArgs {
                              // 0: it is its last warp (no measurable difference: profiles/r02p_*)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
                              // 1: always QUAD, 2: LANE wherever word stores apply
+    int drift;               // map_policy 0: pixels of drift from "4 source columns per lane" that switch a warp to LANE
     int dbg;                 // ATTWARP_REMAP_DBG experiments: 1 skip the sweep (loads and pipeline only)
     unsigned long long* trace;   // ATTWARP_REMAP_TRACE: 8 global-timer stamps per CTA (nullptr: off)
 };
@@ -460,7 +461,7 @@ __device__ __forceinline__ int first_image(const QuadArgs& a, int u0, int lane) 
 
 // Requires H >= 2 and W >= 2 for every image (the launchers route degenerate images to the direct kernel).
 // blockDim.x = consumer threads (a multiple of 32; 4 output columns each) + 32 producer threads.
-// Shared memory: [stages source arenas][stages chunk tables][mbarriers][2 KB of scratch per consumer warp].
+// Shared memory: [stages source arenas][stages chunk tables][mbarriers][1 KB of scratch per consumer warp].
 // Chunk c lives in source stage c % stages.  mbarriers:
 //   full[s]  producer -> consumers   table written, source rows landed (transaction bytes)
 //   sfree[s] consumers -> producer   every consumer warp is done with the stage's rows and table
@@ -476,9 +477,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const uint32_t full_s = smem_s + (uint32_t)bar_off0;
     const uint32_t sfree_s = full_s + 8u * kStages;
     const int n_cons_warps = ((int)blockDim.x >> 5) - 1;
-    // per consumer warp 2 KB of scratch at a 1 KB aligned shared address: two 512-byte RGBX buffers (LANE mapping)
-    // and two 512-byte packed-row buffers, each pair toggled with xor 512
-    const uint32_t scratch_s = (sfree_s + 8u * kStages + 1023u) & ~1023u;
+    // per consumer warp 1 KB of scratch: 512 bytes of RGBX pixels (LANE mapping) and 512 bytes for the packed row
+    const uint32_t scratch_s = (sfree_s + 8u * kStages + 15u) & ~15u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -694,18 +694,18 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     bool warp_live = false;           // some lane of this warp owns a column of the strip
     bool lane_map = false;            // this warp runs the LANE mapping in the current strip
     uint32_t store_ok = 0u;           // this thread owns at least one column of the strip (QUAD position)
-    const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 2048 + lane * 4);     // scratch: my RGBX pixels in
+    const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
     DirectOps dops{};
     dops.lane4 = 4u * (uint32_t)lane;
     // packed row P (one pad word in front of it for MODE 2's funnel shifts): my 12 bytes in, my three words out
-    dops.pw = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + lane * 12);
-    dops.pr = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + lane * 4);
+    dops.pw = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 12);
+    dops.pr = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 4);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         // output word w = lane + 32 k of the warp's row = bytes 4 w .. 4 w + 3 of the RGB stream: pixel
         // p0 = floor(4 w / 3) (and the next one), starting at channel 4 w - 3 p0
         const int w = lane + 32 * k, p0 = (4 * w) / 3, c0 = 4 * w - 3 * p0;
-        dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 2048 + 4 * p0);
+        dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 1024 + 4 * p0);
         dops.xs[k] = c0 == 0 ? 0x4210u : (c0 == 1 ? 0x5421u : 0x6542u);
     }
     int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
         if (warp_live && a.map_policy != 1) {
             const int xb_lane0 = __shfl_sync(0xffffffffu, xb_first, 0);
             const int dev = store_ok ? abs(xb_first - xb_lane0 - 4 * lane) : 0;
-            lane_map = a.map_policy == 2 || __any_sync(0xffffffffu, dev >= 2);
+            lane_map = a.map_policy == 2 || __any_sync(0xffffffffu, dev >= a.drift);
         }
         if (lane_map) {
             xb = -1;
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     dops.wmask = vm;
                     dops.emask = nbb >= 3 ? em : 0u;
                     dops.eoff = (uint32_t)boff;
-                    dops.pedge = scratch_s + (uint32_t)(warp_idx * 2048 + 1024 + 16 + (boff > 0 ? boff : 0));
+                    dops.pedge = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + (boff > 0 ? boff : 0));
                 }
             }
             if (flags & kFlagFixedShift) {
@@ -901,7 +901,7 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
         if (ring >= 2 && ring <= kMaxRing) stages = ring;
     }
     a.stages = stages;
-    const int scratch = 2048 * warps + 1024;
+    const int scratch = 1024 * warps + 16;
     const int budget = (227 * 1024) / ctas - 1024 - stages * kTabBytes - 16 * kMaxRing - 256 - scratch;
     int R = (budget - stages * (2 * unit_pitch + 64 + 128)) / (stages * unit_pitch);
     R = R > kMaxRows ? kMaxRows : R;
@@ -913,6 +913,7 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
     const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + 2 * (size_t)stages * sizeof(uint64_t) + 16 +
                               (size_t)scratch;
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
+    a.drift = env_int("ATTWARP_QUAD_DRIFT", 2);
     a.wait_hint_ns = env_int("ATTWARP_QUAD_WAIT_HINT", 0);
     a.roles_first = env_int("ATTWARP_QUAD_ROLES_FIRST", 0);
     // per (kernel, device): the largest shared-memory size configured so far; per (kernel, device, threads, smem): occupancy
