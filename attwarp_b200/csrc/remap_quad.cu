@@ -133,18 +133,27 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
 #define AWQ_VBLEND                                              \
     AWQ_V1(a, 0) AWQ_V1(a, 1) AWQ_V1(a, 2) AWQ_V1(b, 0) AWQ_V1(b, 1) AWQ_V1(b, 2)  \
     AWQ_V1(c, 0) AWQ_V1(c, 1) AWQ_V1(c, 2) AWQ_V1(d, 0) AWQ_V1(d, 1) AWQ_V1(d, 2)
-// Emit of one output row, destination rows 4-byte aligned (MODE 1): the 12 top bytes of the vertical blends are
-// packed into 3 words (prmt: x.b3 | y.b3 << 8, then the low halves of two pairs); the warp's 384 output bytes change
-// hands through the scratch (a bar.warp.sync before it is written and one before it is read) so that lane t ends up with
-// WORDS t, t + 32, t + 64 of them -- three fully coalesced 128-byte global stores per row.  %49 = address of the
-// warp's first destination byte at row offset 0 (64-bit), %50 = 4 * lane, bits 0..2 of %53 = word k lies inside the
-// strip.
-//   QUAD mapping: packed words to P + 12 * lane (%51), back from P + 4 * lane (%52)
-#define AWQ_DIRECT_ADDR                                         \
+// Emit of one output row.  Either mapping ends with the lane holding the 12 output bytes of four ADJACENT pixels (its
+// QUAD position: bytes 12 t .. 12 t + 11 of the warp's 384-byte block) in q0, q2, q4:
+//   QUAD mapping: the 12 top bytes of the vertical blends packed into 3 words (prmt: x.b3 | y.b3 << 8, then the low
+//                 halves of two pairs);
+//   LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
+//                 128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict
+//                 whatever the local scale of the map; they change hands through the warp's scratch as RGBX pixels
+//                 (X + 4 * lane + 128 j in, 16 bytes at X + 16 * lane out, squeezed to 12 by three prmt; a
+//                 bar.warp.sync before the scratch is written and one before it is read).
+// Destination rows 4-byte aligned (MODE 1): the lane stores its three words itself (12-byte lane stride: the three
+// stores of a warp cover 384 contiguous bytes; L2 merges the partial sectors -- measured 3 % faster at configs[1] than
+// exchanging the words through shared memory for 128-byte-contiguous stores, profiles/r02w_*).  %49 = address of the
+// warp's first destination byte at row offset 0 (64-bit), %35 = 12 * lane, pv = the lane owns a column of the strip.
+#define AWQ_STORE_OWN12                                         \
     "cvt.u64.u32 ro64, ez;\n"                                   \
     "add.u64 oa, %49, ro64;\n"                                  \
-    "cvt.u64.u32 ro64, %50;\n"                                  \
-    "add.u64 oa, oa, ro64;\n"
+    "cvt.u64.u32 ro64, %35;\n"                                  \
+    "add.u64 oa, oa, ro64;\n"                                   \
+    "@pv st.global.b32 [oa], q0;\n"                             \
+    "@pv st.global.b32 [oa+4], q2;\n"                           \
+    "@pv st.global.b32 [oa+8], q4;\n"
 #define AWQ_EMIT_WD                                             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
@@ -156,18 +165,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
     "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
     "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
-    "bar.warp.sync 0xffffffff;\n"                               \
-    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
-    "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
-    AWQ_DIRECT_ADDR                                             \
-    "@pw0 st.global.b32 [oa], q0;\n"                            \
-    "@pw1 st.global.b32 [oa+128], q1;\n"                        \
-    "@pw2 st.global.b32 [oa+256], q2;\n"
-//   LANE mapping: the thread's four pixels are 32 columns apart (pixel j of lane t is column 32 j + t of the warp's
-//   128-column block), so that the window loads of a warp stay inside ~128 bytes and never conflict whatever the
-//   local scale of the map.  RGBX pixels go to X + 4 * lane (+ 128 j); output word k of the lane = bytes of two
-//   adjacent RGBX pixels (addresses xa0..2, byte selectors xs0..2: per-lane constants)
+    AWQ_STORE_OWN12
 #define AWQ_EMIT_LD                                             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
@@ -177,20 +175,15 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
     "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
-    "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
-    "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
-    AWQ_DIRECT_ADDR                                             \
-    "prmt.b32 q0, q0, q1, xs0;\n"                               \
-    "prmt.b32 q2, q2, q3, xs1;\n"                               \
-    "prmt.b32 q4, q4, q5, xs2;\n"                               \
-    "@pw0 st.global.b32 [oa], q0;\n"                            \
-    "@pw1 st.global.b32 [oa+128], q2;\n"                        \
-    "@pw2 st.global.b32 [oa+256], q4;\n"
-// DIRECT stores at ANY byte alignment of the destination rows (MODE 2).  The row-table offset `ez` is taken from the
-// 4-byte aligned address below the image's first byte, so k = ez & 3 is the misalignment of this row's block; the
-// block's packed bytes sit in P (one pad word in front); aligned global word j of the block is the funnel shift of
-// packed words j - 1 and j by 8 (4 - k) bits.  Lane t stores words t, t + 32, t + 64 where they lie wholly inside
+    "ld.shared.v4.b32 {q1, q3, q5, tm}, [sq];\n"                \
+    "prmt.b32 q0, q1, q3, 0x4210;\n"                            \
+    "prmt.b32 q2, q3, q5, 0x5421;\n"                            \
+    "prmt.b32 q4, q5, tm, 0x6542;\n"                            \
+    AWQ_STORE_OWN12
+// Destination rows at ANY byte alignment (MODE 2).  The row-table offset `ez` is taken from the 4-byte aligned address
+// below the image's first byte, so k = ez & 3 is the misalignment of this row's block.  The lanes put their 12 bytes
+// into P (P + 12 * lane = %51; one pad word in front); aligned global word j of the block is the funnel shift of
+// packed words j - 1 and j by 8 (4 - k) bits, read back from P + 4 * lane (%52), %50 = 4 * lane.  Lane t stores words t, t + 32, t + 64 where they lie wholly inside
 // the block (%53: validity bits [4 k + m] for the four alignments) and the <= 3 + 3 bytes of the partial first and
 // last word are stored byte by byte by lanes 4..6 and 0..2 (%60: bit k = this lane stores its edge byte at
 // alignment k, %61 = the byte's offset in the block, %62 = its address in P).
@@ -238,13 +231,11 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "bar.warp.sync 0xffffffff;\n"                               \
     "st.shared.b32 [sx], q0;\n st.shared.b32 [sx+128], q1;\n st.shared.b32 [sx+256], q2;\n st.shared.b32 [sx+384], q3;\n" \
     "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.b32 q0, [xa0];\n ld.shared.b32 q1, [xa0+4];\n"   \
-    "ld.shared.b32 q2, [xa1];\n ld.shared.b32 q3, [xa1+4];\n"   \
-    "ld.shared.b32 q4, [xa2];\n ld.shared.b32 q5, [xa2+4];\n"   \
-    "prmt.b32 q0, q0, q1, xs0;\n"                               \
-    "prmt.b32 q2, q2, q3, xs1;\n"                               \
-    "prmt.b32 q4, q4, q5, xs2;\n"                               \
-    "st.shared.b32 [pr], q0;\n st.shared.b32 [pr+128], q2;\n st.shared.b32 [pr+256], q4;\n" \
+    "ld.shared.v4.b32 {q1, q3, q5, tm}, [sq];\n"                \
+    "prmt.b32 q0, q1, q3, 0x4210;\n"                            \
+    "prmt.b32 q2, q3, q5, 0x5421;\n"                            \
+    "prmt.b32 q4, q5, tm, 0x6542;\n"                            \
+    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  The entry of the row AFTER the
 // one being emitted is requested before the emit, so the loop-carried compare never waits for a shared-memory load
@@ -263,8 +254,8 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     L "_NEXT:\n"                                                \
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
-    ".reg .pred p, q, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, pw, pr, xa0, xa1, xa2, xs0, xs1, xs2, tm, uk, pedge;\n" \
+    ".reg .pred p, q, pv, podd;\n"                              \
+    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq, pw, pr, tm, uk, pedge;\n" \
     ".reg .pred pw0, pw1, pw2, pe;\n"                               \
     ".reg .b64 ro64, oa;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
@@ -286,13 +277,12 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 Oc0, %18;\n mov.b32 Oc1, %19;\n mov.b32 Oc2, %20;\n mov.b32 Od0, %21;\n mov.b32 Od1, %22;\n mov.b32 Od2, %23;\n" \
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
-    "mov.b32 sx, %33;\n"                                        \
+    "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
     "mov.b32 pw, %51;\n mov.b32 pr, %52;\n mov.b32 pedge, %62;\n"  \
-    "mov.b32 xa0, %54;\n mov.b32 xa1, %55;\n mov.b32 xa2, %56;\n"      \
-    "mov.b32 xs0, %57;\n mov.b32 xs1, %58;\n mov.b32 xs2, %59;\n"      \
     "and.b32 tm, %53, 1;\n setp.ne.u32 pw0, tm, 0;\n"           \
     "and.b32 tm, %53, 2;\n setp.ne.u32 pw1, tm, 0;\n"           \
     "and.b32 tm, %53, 4;\n setp.ne.u32 pw2, tm, 0;\n"           \
+    "setp.ne.u32 pv, %40, 0;\n"                                 \
     "setp.ne.u32 podd, %39, 0;\n"                               \
     "mov.b32 rp, %37;\n"                                        \
     "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp];\n"
@@ -345,17 +335,18 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
       "+r"(E[8]), "+r"(E[9]), "+r"(E[10]), "+r"(E[11]), "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]),     \
       "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "+r"(O[9]), "+r"(O[10]), "+r"(O[11])      \
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
-      "r"(n_slots), "r"(sx), "r"(0), "r"(0), "r"(pitch), "r"(rp), "r"(0), "r"(odd_first), "r"(0),             \
+      "r"(n_slots), "r"(sx), "r"(d.sq), "r"(d.lane12), "r"(pitch), "r"(rp), "r"(0), "r"(odd_first), "r"(store_ok), \
       "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3]),       \
-      "l"(d.obase), "r"(d.lane4), "r"(d.pw), "r"(d.pr), "r"(d.wmask), "r"(d.xa[0]), "r"(d.xa[1]), "r"(d.xa[2]),    \
-      "r"(d.xs[0]), "r"(d.xs[1]), "r"(d.xs[2]), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                     \
+      "l"(d.obase), "r"(d.lane4), "r"(d.pw), "r"(d.pr), "r"(d.wmask), "r"(0), "r"(0), "r"(0),                     \
+      "r"(0), "r"(0), "r"(0), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                                       \
     : "memory"
 
 // what the emit variants need (see AWQ_EMIT_WD / AWQ_EMIT_LD / AWQ_UNALIGNED_TAIL)
 struct DirectOps {
     uint64_t obase;
-    uint32_t lane4, pw, pr, wmask, xa[3], xs[3];
+    uint32_t lane4, pw, pr, wmask;      // MODE 2 (wmask: validity bits of the lane's three words per alignment)
     uint32_t emask, eoff, pedge;        // MODE 2 only
+    uint32_t sq, lane12;                // MODE 1: scratch address of my four adjacent RGBX pixels (LANE), 12 * lane
 };
 
 // FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
@@ -364,7 +355,8 @@ struct DirectOps {
 template <bool FIXED, bool LANE, int MODE>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
                                            const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
-                                           uint32_t rp, uint32_t odd_first, uint32_t sx, const DirectOps& d) {
+                                           uint32_t rp, uint32_t odd_first, uint32_t sx, uint32_t store_ok,
+                                           const DirectOps& d) {
 #define AWQ_RUN(BODY, EMIT) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE BODY(EMIT) AWQ_EPILOGUE "}\n" AWQ_OPERANDS)
     if (FIXED) {
         if (MODE == 1) { if (!LANE) AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_WD); else AWQ_RUN(AWQ_BODY_F, AWQ_EMIT_LD); }
@@ -697,17 +689,11 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
     DirectOps dops{};
     dops.lane4 = 4u * (uint32_t)lane;
+    dops.lane12 = 12u * (uint32_t)lane;
+    dops.sq = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 16);
     // packed row P (one pad word in front of it for MODE 2's funnel shifts): my 12 bytes in, my three words out
     dops.pw = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 12);
     dops.pr = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 4);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        // output word w = lane + 32 k of the warp's row = bytes 4 w .. 4 w + 3 of the RGB stream: pixel
-        // p0 = floor(4 w / 3) (and the next one), starting at channel 4 w - 3 p0
-        const int w = lane + 32 * k, p0 = (4 * w) / 3, c0 = 4 * w - 3 * p0;
-        dops.xa[k] = scratch_s + (uint32_t)(warp_idx * 1024 + 4 * p0);
-        dops.xs[k] = c0 == 0 ? 0x4210u : (c0 == 1 ? 0x5421u : 0x6542u);
-    }
     int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
 
     // per-strip setup: taps and weights of this thread's columns, choice of the mapping
@@ -853,13 +839,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (!lane_map) sweep_quad<true, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
-                else sweep_quad<true, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
+                if (!lane_map) sweep_quad<true, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                else sweep_quad<true, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (!lane_map) sweep_quad<false, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
-                else sweep_quad<false, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, dops);
+                if (!lane_map) sweep_quad<false, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                else sweep_quad<false, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
             }
         }
         __syncwarp();
