@@ -74,6 +74,7 @@ SIGNATURES = {
     "attwarp_warp_from_pdfs": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp]),
     "attwarp_ragged_workspace_bytes": (_sz, [_vp, _i]),
+    "attwarp_ragged_last_launches": (_i, []),
     "attwarp_warp_ragged_from_tokens": (_i, [_vp, _i, _i, _i, _vp, _i, _tp, _vp, _sz, _vp]),
     "attwarp_warp_image_host": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _tp, _vp,
                                      C.POINTER(_i)]),

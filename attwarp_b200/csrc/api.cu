@@ -337,6 +337,9 @@ int attwarp_warp_from_pdfs(const float* px, const float* py, int B, int Nx, int 
 // (n + 1 entries in batch order, then n + kRaggedClasses entries grouped by width class for the stage-5 launches)
 static size_t ragged_table_bytes(int n) { return align_up(sizeof(RaggedImage) * (size_t)(2 * n + 1 + kRaggedClasses), 256); }
 
+// kernel launches of this thread's last attwarp_warp_ragged_from_tokens call (maps + one resample launch per class)
+static thread_local int g_ragged_last_launches = 0;
+
 size_t attwarp_ragged_workspace_bytes(const attwarp_ragged_image* images, int n) {
     if (images == nullptr || n <= 0) return 0;
     size_t floats = 0;
@@ -401,9 +404,12 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
     if (rc != ATTWARP_OK) return rc;
     rc = launch_maps_from_tokens_ragged(tok, n, gh, gw, dev_table, max_h, max_w, *tp, nullptr, st);
     if (rc != ATTWARP_OK) return rc;
+    g_ragged_last_launches = 1 + (quad ? ragged_quad_launches(plan) : 1);
     return quad ? launch_remap_u8_quad_ragged_run(plan, dev_sorted, st)
                 : launch_remap_u8_stream_ragged_run(host.data(), n, C, dev_table, st);
 }
+
+int attwarp_ragged_last_launches(void) { return g_ragged_last_launches; }
 
 static int warp_image_host_impl(const void* image_host, int img_dtype, int C, int H, int W,
                                 const void* att_host, int att_dtype, int Wo, int Ho,

@@ -105,6 +105,7 @@ struct RaggedQuadPlan {
 };
 int launch_remap_u8_quad_ragged_prepare(RaggedImage* host_table, int n, RaggedImage* dev_main, RaggedImage* dev_sorted,
                                         RaggedQuadPlan* plan, cudaStream_t st);
+int ragged_quad_launches(const RaggedQuadPlan& plan);      // stage-5 launches the plan needs (one per non-empty class)
 int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImage* dev_sorted, cudaStream_t st);
 
 #if defined(__CUDACC__)

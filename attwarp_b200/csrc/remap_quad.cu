@@ -146,16 +146,21 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
 // stores of a warp cover 384 contiguous bytes; L2 merges the partial sectors -- measured 3 % faster at configs[1] than
 // exchanging the words through shared memory for 128-byte-contiguous stores, profiles/r02w_*).  %49 = address of the
 // warp's first destination byte at row offset 0 (64-bit), %35 = 12 * lane, pv = the lane owns a column of the strip.
-#define AWQ_STORE_OWN12                                         \
+// The row's table entry (ex, ey: weights, ez: offset) is dead once the blends and the address are computed: the NEXT
+// row's entry is loaded straight over it, early enough for the loop-carried compare of `ew` (no register rotation).
+#define AWQ_OWN12_BEGIN                                         \
+    AWQ_VBLEND                                                  \
     "cvt.u64.u32 ro64, ez;\n"                                   \
     "add.u64 oa, %49, ro64;\n"                                  \
     "cvt.u64.u32 ro64, %35;\n"                                  \
     "add.u64 oa, oa, ro64;\n"                                   \
+    "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp+16];\n"
+#define AWQ_STORE_OWN12                                         \
     "@pv st.global.b32 [oa], q0;\n"                             \
     "@pv st.global.b32 [oa+4], q2;\n"                           \
     "@pv st.global.b32 [oa+8], q4;\n"
 #define AWQ_EMIT_WD                                             \
-    AWQ_VBLEND                                                  \
+    AWQ_OWN12_BEGIN                                             \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
     "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
     "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
@@ -167,7 +172,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
     AWQ_STORE_OWN12
 #define AWQ_EMIT_LD                                             \
-    AWQ_VBLEND                                                  \
+    AWQ_OWN12_BEGIN                                             \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
     "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
@@ -207,8 +212,10 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
     "@pe ld.shared.u8 o, [pedge];\n"                            \
     "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n" \
-    "@pe st.global.u8 [oa], o;\n"
+    "@pe st.global.u8 [oa], o;\n"                               \
+    "mov.b32 ex, fx;\n mov.b32 ey, fy;\n mov.b32 ez, fz;\n mov.b32 ew, fw;\n"
 #define AWQ_EMIT_WU                                             \
+    "ld.shared.v4.b32 {fx, fy, fz, fw}, [rp+16];\n"             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
     "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
@@ -223,6 +230,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
 #define AWQ_EMIT_LU                                             \
+    "ld.shared.v4.b32 {fx, fy, fz, fw}, [rp+16];\n"             \
     AWQ_VBLEND                                                  \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
@@ -237,14 +245,13 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q4, q5, tm, 0x6542;\n"                            \
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
-// rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  The entry of the row AFTER the
-// one being emitted is requested before the emit, so the loop-carried compare never waits for a shared-memory load
-// (the entry after the sentinel is read too: still inside the CTA's shared memory, never used)
+// rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  Every emit variant also fetches the
+// table entry of the row AFTER the one being emitted, early enough for the loop-carried compare (MODE 2, which needs
+// `ez` to the end, into f and rotates; the entry after the sentinel is read too: still inside the CTA's shared
+// memory, never used)
 #define AWQ_ROW_STEP(EMIT)                                      \
-    "ld.shared.v4.b32 {fx, fy, fz, fw}, [rp+16];\n"             \
     EMIT                                                        \
-    "add.u32 rp, rp, 16;\n"                                     \
-    "mov.b32 ex, fx;\n mov.b32 ey, fy;\n mov.b32 ez, fz;\n mov.b32 ew, fw;\n"
+    "add.u32 rp, rp, 16;\n"
 #define AWQ_ROWS(L, EMIT)                                       \
     "setp.ne.u32 q, ew, s;\n"                                   \
     "@q bra.uni " L "_NEXT;\n"                                  \
@@ -1130,18 +1137,79 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     AW_CUDA(cudaMemcpyAsync(dev_sorted, sorted.data(), sizeof(RaggedImage) * sorted.size(), cudaMemcpyHostToDevice, st));
     return ATTWARP_OK;
 }
-// Step 2: one launch per non-empty class.
+// Step 2: one launch per non-empty class.  The classes write disjoint images, so their launches fan out over up to
+// three streams (the caller's + two of the library's, forked and joined with events -- also legal inside a stream
+// capture): every launch is a persistent grid with a ramp (first chunk ~8 us) and a ragged tail, which the next
+// class's CTAs fill as SMs come free.  ATTWARP_RAGGED_STREAMS=1 keeps everything on the caller's stream.
+namespace {
+struct FanOut {
+    static constexpr int kAux = 2;
+    int dev = -1;
+    cudaStream_t aux[kAux] = {};
+    cudaEvent_t fork = nullptr, join[kAux] = {};
+    void release() {
+        if (dev < 0) return;
+        for (int i = 0; i < kAux; ++i) {
+            if (aux[i]) cudaStreamDestroy(aux[i]);
+            if (join[i]) cudaEventDestroy(join[i]);
+            aux[i] = nullptr;
+            join[i] = nullptr;
+        }
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
+        dev = -1;
+    }
+    int ensure(int d) {
+        if (dev == d) return ATTWARP_OK;
+        release();
+        for (int i = 0; i < kAux; ++i) {
+            AW_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            AW_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        AW_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        dev = d;
+        return ATTWARP_OK;
+    }
+    ~FanOut() { release(); }
+};
+}  // namespace
+
+int ragged_quad_launches(const RaggedQuadPlan& plan) {
+    int n_launch = 0;
+    for (int c = 0; c < kRaggedClasses; ++c) n_launch += plan.count[c] != 0 && plan.total_units[c] != 0;
+    return n_launch;
+}
+
 int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImage* dev_sorted, cudaStream_t st) {
-    for (int c = 0; c < kRaggedClasses; ++c) {
+    const int n_launch = ragged_quad_launches(plan);
+    int lanes = env_int("ATTWARP_RAGGED_STREAMS", 1 + FanOut::kAux);
+    lanes = lanes < 1 ? 1 : (lanes > 1 + FanOut::kAux ? 1 + FanOut::kAux : lanes);
+    if (lanes > n_launch) lanes = n_launch;
+    static thread_local FanOut fo;
+    if (lanes > 1) {
+        int dev = 0;
+        AW_CUDA(cudaGetDevice(&dev));
+        const int rc = fo.ensure(dev);
+        if (rc != ATTWARP_OK) return rc;
+        AW_CUDA(cudaEventRecord(fo.fork, st));
+        for (int i = 0; i + 1 < lanes; ++i) AW_CUDA(cudaStreamWaitEvent(fo.aux[i], fo.fork, 0));
+    }
+    int k = 0, rc = ATTWARP_OK;
+    for (int c = 0; c < kRaggedClasses && rc == ATTWARP_OK; ++c) {
         if (plan.count[c] == 0 || plan.total_units[c] == 0) continue;
         QuadArgs a{};
         a.imgs = dev_sorted + plan.offset[c];
         a.n_img = plan.count[c];
         a.total_units = plan.total_units[c];
-        const int rc = launch_direct(a, plan.max_strip[c], plan.mode[c] == 1, st);
-        if (rc != ATTWARP_OK) return rc;
+        const int lane = k++ % lanes;
+        rc = launch_direct(a, plan.max_strip[c], plan.mode[c] == 1, lane == 0 ? st : fo.aux[lane - 1]);
     }
-    return ATTWARP_OK;
+    // join even after a failed launch: the caller's stream must not run ahead of work already enqueued
+    for (int i = 0; i + 1 < lanes; ++i) {
+        AW_CUDA(cudaEventRecord(fo.join[i], fo.aux[i]));
+        AW_CUDA(cudaStreamWaitEvent(st, fo.join[i], 0));
+    }
+    return rc;
 }
 
 }  // namespace aw

@@ -500,4 +500,5 @@ class RaggedBatch:
         with torch.cuda.device(self.device):
             check(lib.attwarp_warp_ragged_from_tokens(ptr(tok), self.n, gh, gw, self._table_p, self.C, C.byref(tp),
                                                       ptr(self._ws), self._ws.numel(), current_stream(self.device)))
+            self.launches = int(lib.attwarp_ragged_last_launches())      # kernels this call enqueued
         return self.outs

@@ -729,11 +729,10 @@ def bench_ragged(ctx):
 
     # the descriptor table is a function of the buffers: built once (ops.RaggedBatch), re-used by every step
     batch = ops.RaggedBatch(imgs, outs=outs)
-    n_classes = len({0 if t.shape[1] <= 352 else (1 if t.shape[1] <= 704 else 2) for t in imgs})
 
     def step(i):
         batch.run(tok)
-        return 1 + n_classes                     # maps + one resample launch per width class
+        return batch.launches                    # maps + one resample launch per class (counted by the library)
 
     for i in range(args.warmup):
         step(i)
@@ -782,8 +781,11 @@ def bench_ragged(ctx):
                         "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": total_bytes // world,
                         "note": "per GPU: the slowest rank's step time over its share of the bytes"},
            "check": check, "e2e": None,
-           "run": {"launch": "one maps launch + one resample launch per width class (<= 352, <= 704, wider) per step over "
-                             "the rank's shard; descriptor table planned once per buffer set (ops.RaggedBatch)"}}
+           "run": {"launch": "one maps launch + one resample launch per class of images (grouped by the consumer warps "
+                             "their strips need, 3..16, and by whether their rows are 4-byte aligned; classes fan out "
+                             "over three streams) per step over the rank's shard; descriptor table planned once per "
+                             "buffer set (ops.RaggedBatch)",
+                   "launches_per_step": batch.launches}}
     torch.cuda.empty_cache()
     return res
 

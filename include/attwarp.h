@@ -245,6 +245,11 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
                                     const attwarp_transform_params* tp, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* Kernel launches the calling thread's last attwarp_warp_ragged_from_tokens call enqueued: one maps launch + one
+ * stage-5 launch per non-empty class (images are grouped by the consumer warps their strips need and by whether
+ * their destination rows are 4-byte aligned).  For accounting (bench.py's gpu_launches). */
+int attwarp_ragged_last_launches(void);
+
 /* attwarp_warp_image_host: the whole of warp_image_by_attention (AGW/new_method.py:198-283) for
  * ONE image with HOST buffers, as the NumPy signature implies: H2D, stages 2b-5 on the device,
  * D2H, blocking.  image_host: uint8/float32 [H][W][C]; att_host: U8/F32/F64 [H][W];
