@@ -36,21 +36,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// the same with a suspend-time hint (ns): the hardware may park the thread that long before it reports "not yet",
-// so a warp that waits for microseconds executes a handful of polls instead of thousands
-__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity), "r"(hint_ns)
-        : "memory");
-}
 // global -> shared, completion counted in bytes on an mbarrier; addresses and size multiples of 16
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile(

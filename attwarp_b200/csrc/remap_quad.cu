@@ -192,31 +192,34 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
 // the block (%53: validity bits [4 k + m] for the four alignments) and the <= 3 + 3 bytes of the partial first and
 // last word are stored byte by byte by lanes 4..6 and 0..2 (%60: bit k = this lane stores its edge byte at
 // alignment k, %61 = the byte's offset in the block, %62 = its address in P).
-#define AWQ_UNALIGNED_TAIL                                      \
-    "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
-    "ld.shared.b32 q3, [pr+-4];\n ld.shared.b32 q4, [pr+124];\n ld.shared.b32 q5, [pr+252];\n" \
+// everything that depends on the row's table entry first (k, the two addresses, the predicates, the shift), so that the
+// next row's entry can be loaded over it
+#define AWQ_UNALIGNED_BEGIN                                     \
+    AWQ_VBLEND                                                  \
     "and.b32 uk, ez, 3;\n"                                      \
-    "shl.b32 tm, uk, 3;\n sub.u32 tm, 32, tm;\n"                \
-    "shf.r.clamp.b32 q0, q3, q0, tm;\n shf.r.clamp.b32 q1, q4, q1, tm;\n shf.r.clamp.b32 q2, q5, q2, tm;\n" \
     "sub.u32 tm, ez, uk;\n"                                     \
     "cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n"          \
     "cvt.u64.u32 ro64, %50;\n add.u64 oa, oa, ro64;\n"          \
+    "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oae, %49, ro64;\n" \
+    "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp+16];\n"             \
     "shl.b32 tm, uk, 2;\n shr.u32 tm, %53, tm;\n"               \
     "and.b32 o, tm, 1;\n setp.ne.u32 pw0, o, 0;\n"              \
     "and.b32 o, tm, 2;\n setp.ne.u32 pw1, o, 0;\n"              \
     "and.b32 o, tm, 4;\n setp.ne.u32 pw2, o, 0;\n"              \
+    "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
+    "shl.b32 us, uk, 3;\n sub.u32 us, 32, us;\n"
+#define AWQ_UNALIGNED_TAIL                                      \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
+    "ld.shared.b32 q3, [pr+-4];\n ld.shared.b32 q4, [pr+124];\n ld.shared.b32 q5, [pr+252];\n" \
+    "shf.r.clamp.b32 q0, q3, q0, us;\n shf.r.clamp.b32 q1, q4, q1, us;\n shf.r.clamp.b32 q2, q5, q2, us;\n" \
     "@pw0 st.global.b32 [oa], q0;\n"                            \
     "@pw1 st.global.b32 [oa+128], q1;\n"                        \
     "@pw2 st.global.b32 [oa+256], q2;\n"                        \
-    "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
     "@pe ld.shared.u8 o, [pedge];\n"                            \
-    "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n" \
-    "@pe st.global.u8 [oa], o;\n"                               \
-    "mov.b32 ex, fx;\n mov.b32 ey, fy;\n mov.b32 ez, fz;\n mov.b32 ew, fw;\n"
+    "@pe st.global.u8 [oae], o;\n"
 #define AWQ_EMIT_WU                                             \
-    "ld.shared.v4.b32 {fx, fy, fz, fw}, [rp+16];\n"             \
-    AWQ_VBLEND                                                  \
+    AWQ_UNALIGNED_BEGIN                                         \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
     "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
     "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
@@ -230,8 +233,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
 #define AWQ_EMIT_LU                                             \
-    "ld.shared.v4.b32 {fx, fy, fz, fw}, [rp+16];\n"             \
-    AWQ_VBLEND                                                  \
+    AWQ_UNALIGNED_BEGIN                                         \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
     "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
@@ -246,9 +248,8 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
     AWQ_UNALIGNED_TAIL
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  Every emit variant also fetches the
-// table entry of the row AFTER the one being emitted, early enough for the loop-carried compare (MODE 2, which needs
-// `ez` to the end, into f and rotates; the entry after the sentinel is read too: still inside the CTA's shared
-// memory, never used)
+// table entry of the row AFTER the one being emitted, early enough for the loop-carried compare (the entry after the
+// sentinel is read too: still inside the CTA's shared memory, never used)
 #define AWQ_ROW_STEP(EMIT)                                      \
     EMIT                                                        \
     "add.u32 rp, rp, 16;\n"
@@ -262,9 +263,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
     ".reg .pred p, q, pv, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, fx, fy, fz, fw, o, sx, sq, pw, pr, tm, uk, pedge;\n" \
+    ".reg .b32 s, rp, ex, ey, ez, ew, o, sx, sq, pw, pr, tm, uk, us, pedge;\n" \
     ".reg .pred pw0, pw1, pw2, pe;\n"                               \
-    ".reg .b64 ro64, oa;\n"                 \
+    ".reg .b64 ro64, oa, oae;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
     ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
     ".reg .b32 ka, kb, kc, kd, ua, ub, uc, ud, sa, sb, sc, sd, ma, mb, mc, md, na, nb, nc, nd;\n" \
@@ -391,9 +392,6 @@ struct QuadArgs {
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int rows;                // output rows per chunk (<= kMaxRows)
     int stages;              // ring depth: source-row stages (chunks whose loads are in flight)
-    int wait_hint_ns;        // suspend-time hint of the mbarrier waits (0: plain try_wait polling)
-    int roles_first;         // 1: the producer warp is the CTA's first warp (the consumers get the higher warp ids),
-                             // 0: it is its last warp (no measurable difference: profiles/r02p_*)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
                              // 1: always QUAD, 2: LANE wherever word stores apply
     int drift;               // map_policy 0: pixels of drift from "4 source columns per lane" that switch a warp to LANE
@@ -495,16 +493,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
     const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
 
-    // warp roles: consumers 0 .. n_cons_warps-1, then the producer (logical indices)
-    const int hw_warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
-    const int warp_idx = a.roles_first ? (hw_warp < 1 ? n_cons_warps + hw_warp : hw_warp - 1) : hw_warp;
+    // warp roles: consumers 0 .. n_cons_warps-1, then the producer.  Waits on mbarriers are plain try_wait loops
+    // (suspend-time hints, a sleeping producer and the producer as the CTA's first warp were measured: no change,
+    // profiles/r02p_*, r03b_*)
+    const int warp_idx = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
     const int lane = (int)threadIdx.x & 31;
-    const int tid = warp_idx * 32 + lane;                  // logical thread index: consumers first
-    const uint32_t hint = (uint32_t)a.wait_hint_ns;
-    auto wait = [&](uint32_t bar, uint32_t parity) {
-        if (hint != 0u) mbar_wait_hint(bar, parity, hint);
-        else mbar_wait(bar, parity);
-    };
+    const int tid = (int)threadIdx.x;
+    auto wait = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
 
     if (warp_idx >= n_cons_warps) {
         {
@@ -907,8 +902,6 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
                               (size_t)scratch;
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     a.drift = env_int("ATTWARP_QUAD_DRIFT", 2);
-    a.wait_hint_ns = env_int("ATTWARP_QUAD_WAIT_HINT", 0);
-    a.roles_first = env_int("ATTWARP_QUAD_ROLES_FIRST", 0);
     // per (kernel, device): the largest shared-memory size configured so far; per (kernel, device, threads, smem): occupancy
     struct Key {
         QuadKernel k; int dev, threads; size_t smem;
