@@ -147,6 +147,9 @@ __device__ __forceinline__ uint32_t clip8(int acc) { return (uint32_t)clampi(acc
 // sums per (tile, row group) chunk in colpart[b][chunk][Wo], whole row sums in rowpart[b][0][Ho], each with the
 // + 1e-9 per element of new_method.py:212 added as count x 1e-9 -- for maps_from_partials_kernel to finish.  All
 // sums are exact integers (<= 255 x 65535), whatever the order the threads add them in.
+// Measured (profiles/r03d_row_kernels.txt): this saves the B x H x W buffer, not time -- the resize is bound by the
+// fma pipe, so the write it skips was free, and the sums cost about what the separate marginals kernel does
+// (256 x 336^2: 53.5 us fused vs 52.5 us in two steps; 64 x 1344^2: 188 vs 167 us).
 constexpr int kUpMaxThreads = 512;
 template <int TAPS, bool MARG>     // taps per axis actually used (7 for pure up-scaling)
 __global__ void __launch_bounds__(kUpMaxThreads)

@@ -1041,8 +1041,8 @@ int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, in
 // 300-wide image in a CTA built for 1408 columns would leave eight of its eleven consumer warps idle):
 //   classes 0 .. 13   destination rows 4-byte aligned (MODE 1): strips of <= 384 columns (3 consumer warps), then one
 //                     class per extra 128 columns up to 2048 (16 warps); wider images are cut into strips.  A class
-//                     with less than ~2 M output pixels (less work than a launch's ramp) joins the next wider
-//                     non-empty one.
+//                     with less than ~24 M output pixels (the launch would cost more than the warps it saves) joins
+//                     the next wider non-empty one.
 //   classes 14 .. 27  the same widths for rows at any alignment (MODE 2)
 // Step 1: `host` (n + 1 entries, batch order) gets each image's strip plan and is uploaded to dev_main (the maps
 // kernel reads shapes and map pointers from it); a copy grouped by class, every group followed by an entry that
@@ -1069,10 +1069,12 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     }
     // An aligned class next to a non-empty any-alignment class of the same width joins it unless it is big enough
     // to pay for a launch of its own (MODE 2 handles aligned rows too, ~20 % slower; a launch's ramp and tail cost
-    // ~10 us).  Then small classes join the next wider non-empty one.
+    // ~10 us, a third of it exposed with three streams).  Then small classes join the next wider non-empty one: a
+    // class wastes ~1 / warps of its work there, so below ~24 M output pixels the launch costs more than the waste
+    // (profiles/r03c_c4_class_min_px.txt: 0.377 -> 0.35 ms for a 128-image shard, nothing lost at 1024 images).
     int join[kRaggedClasses];
     for (int c = 0; c < kRaggedClasses; ++c) join[c] = c;
-    const int64_t min_px = (int64_t)env_int("ATTWARP_QUAD_CLASS_MIN_PX", 2000000);
+    const int64_t min_px = (int64_t)env_int("ATTWARP_QUAD_CLASS_MIN_PX", 24000000);
     const int64_t min_aligned_px = (int64_t)env_int("ATTWARP_QUAD_ALIGNED_MIN_PX", 32000000);
     for (int c = 0; c < kDirectClasses; ++c) {
         if (px[c] == 0 || px[c] >= min_aligned_px || px[c + kDirectClasses] == 0) continue;

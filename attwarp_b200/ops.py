@@ -159,18 +159,19 @@ def mota_mask(tok: torch.Tensor, image_hw, kernel_size: int = 3, enhance_coe: fl
 
 
 def maps_from_mota_tokens(tok: torch.Tensor, image_hw, out_size=None, kernel_size: int = 3, enhance_coe: float = 10.0,
-                          apply_inverse: bool = False):
+                          apply_inverse: bool = False, fused: bool = True):
     """tok [B,gh,gw] -> (map_x, map_y) of the driver flow ``blend_mask`` -> ``save_warped_image(..., "identity")``
-    (llava.py:240-256 then new_method.py:207-261) for callers that only warp: the image-size uint8 mask is never
-    written, its marginals are summed where the LANCZOS resize computes it.  Same maps as
-    ``maps_from_attention(mota_mask(tok, image_hw), out_size)``."""
+    (llava.py:240-256 then new_method.py:207-261) for callers that only warp.  ``fused=True``: the image-size uint8
+    mask is never written, its marginals are summed where the LANCZOS resize computes it (saves the B x H x W
+    buffer; about the same time at 336^2, ~10 % slower than the two steps at 1344^2 -- the resize is compute-bound).
+    Same maps as ``maps_from_attention(mota_mask(tok, image_hw), out_size)``, which ``fused=False`` runs."""
     lib = load()
     _, u8 = revise_mask(tok, kernel_size, enhance_coe, return_u8=True)
     B, gh, gw = u8.shape
     H, W = int(image_hw[0]), int(image_hw[1])
     Ho, Wo = (H, W) if out_size is None else (int(out_size[0]), int(out_size[1]))
-    wsb = lib.attwarp_maps_from_mask_workspace_bytes(B, gh, gw, H, W)
-    if wsb == 0:        # not an up-scaling the fused kernel takes: the two device steps
+    wsb = lib.attwarp_maps_from_mask_workspace_bytes(B, gh, gw, H, W) if fused else 0
+    if wsb == 0:        # not fused, or not an up-scaling the fused kernel takes: the two device steps
         return maps_from_attention(resize_lanczos_u8(u8, (H, W)), (Ho, Wo), apply_inverse=apply_inverse)
     tp = _tp("identity", 1.0, 1.0, apply_inverse)
     map_x = torch.empty(B, Wo, dtype=torch.float32, device=tok.device)

@@ -734,6 +734,9 @@ def bench_ragged(ctx):
         batch.run(tok)
         return batch.launches                    # maps + one resample launch per class (counted by the library)
 
+    step(0)
+    launches_per_step = batch.launches
+
     for i in range(args.warmup):
         step(i)
     elapsed_ms, launches = timed_steps(ctx, step, steps, 0)
@@ -785,7 +788,7 @@ def bench_ragged(ctx):
                              "their strips need, 3..16, and by whether their rows are 4-byte aligned; classes fan out "
                              "over three streams) per step over the rank's shard; descriptor table planned once per "
                              "buffer set (ops.RaggedBatch)",
-                   "launches_per_step": batch.launches}}
+                   "launches_per_step": launches_per_step}}
     torch.cuda.empty_cache()
     return res
 
