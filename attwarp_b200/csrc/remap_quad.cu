@@ -13,10 +13,10 @@
 //     apart at unit scale, 12-byte lane stride: every 32-bit load of a warp is conflict-free) or columns t, t + 32,
 //     t + 64, t + 96 of its warp's 128-column block (LANE mapping, chosen per warp and strip where the map's local
 //     scale would make the QUAD windows collide);
-//   * the 384 output bytes of a warp and row change hands through a per-warp shared-memory scratch so that lane t
-//     ends up with words t, t + 32, t + 64 of them: three fully coalesced 128-byte global stores per row.  Rows at
-//     any byte alignment are handled by a second build (MODE 2: funnel-shifted words + byte stores at the two ends
-//     of the block), so no destination needs an output tile;
+//   * each lane stores the 12 bytes of its four adjacent pixels itself: three 32-bit stores at a 12-byte lane
+//     stride (a warp's three stores cover 384 contiguous bytes; L2 merges the partial sectors).  Destination rows
+//     at any byte alignment are handled by a second build (MODE 2: one halo pixel per warp, lane-local funnel
+//     shifts + one shuffle, byte stores only at the two ends of a row), so no destination needs an output tile;
 //   * the horizontal blends of the two most recent source rows are held per channel in an EVEN-row and an
 //     ODD-row register (source row r goes to E when r is even), so a new source row overwrites one of them
 //     without re-packing; the vertical blend of an output row is  t = wO*O + (wE*E + 512 * 2^14)  with the row's
@@ -185,41 +185,51 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q2, q3, q5, 0x5421;\n"                            \
     "prmt.b32 q4, q5, tm, 0x6542;\n"                            \
     AWQ_STORE_OWN12
-// Destination rows at ANY byte alignment (MODE 2).  The row-table offset `ez` is taken from the 4-byte aligned address
-// below the image's first byte, so k = ez & 3 is the misalignment of this row's block.  The lanes put their 12 bytes
-// into P (P + 12 * lane = %51; one pad word in front); aligned global word j of the block is the funnel shift of
-// packed words j - 1 and j by 8 (4 - k) bits, read back from P + 4 * lane (%52), %50 = 4 * lane.  Lane t stores words t, t + 32, t + 64 where they lie wholly inside
-// the block (%53: validity bits [4 k + m] for the four alignments) and the <= 3 + 3 bytes of the partial first and
-// last word are stored byte by byte by lanes 4..6 and 0..2 (%60: bit k = this lane stores its edge byte at
-// alignment k, %61 = the byte's offset in the block, %62 = its address in P).
-// everything that depends on the row's table entry first (k, the two addresses, the predicates, the shift), so that the
-// next row's entry can be loaded over it
-#define AWQ_UNALIGNED_BEGIN                                     \
+// Destination rows at ANY byte alignment (MODE 2).  A warp's 32 lanes x 4 pixels start ONE PIXEL BEFORE its block of
+// 127 pixels: lane 0's first pixel is the last pixel of the previous warp's block (computed twice, stored once).
+// With P0 = row offset of the strip (from the 4-byte aligned address below the image: `ez`) + 3 * (first column of
+// the warp's lanes) (%50) and a = P0 & 3, lane t holds stream bytes P0 + 12 t .. + 11; the aligned word that starts
+// a bytes before them is the funnel shift of the previous lane's last word (one shuffle) and its own first word,
+// the next two of its own words.  A warp stores every aligned word whose LAST byte lies in its 127 pixels: the word
+// that straddles two blocks belongs to the second one, which has all its bytes thanks to the halo pixel -- no byte
+// stores between blocks.  Only the first word of a row (first warp of the first strip) and the last one (last warp
+// of the last strip) can be partial: those two warps (%52 != 0) put their bytes into P and lanes 4..6 / 0..2 store
+// the <= 3 + 3 bytes one by one (%60: bit a = this lane stores its edge byte at alignment a, %61 = the byte's
+// offset from P0, %62 = its address in P).  %53: validity bits [4 a + m] of the lane's three words.
+#define AWQ_HALO_BEGIN                                          \
     AWQ_VBLEND                                                  \
-    "and.b32 uk, ez, 3;\n"                                      \
-    "sub.u32 tm, ez, uk;\n"                                     \
-    "cvt.u64.u32 ro64, tm;\n add.u64 oa, %49, ro64;\n"          \
-    "cvt.u64.u32 ro64, %50;\n add.u64 oa, oa, ro64;\n"          \
-    "add.u32 tm, ez, %61;\n cvt.u64.u32 ro64, tm;\n add.u64 oae, %49, ro64;\n" \
+    "add.s32 up0, ez, %50;\n"                                   \
+    "and.b32 uk, up0, 3;\n"                                     \
+    "add.s32 tm, up0, %35;\n"                                   \
+    "and.b32 tm, tm, 0xfffffffc;\n"                             \
+    "cvt.s64.s32 ro64, tm;\n add.s64 oa, %49, ro64;\n"          \
     "ld.shared.v4.b32 {ex, ey, ez, ew}, [rp+16];\n"             \
+    "shl.b32 us, uk, 3;\n sub.u32 us, 32, us;\n"                \
     "shl.b32 tm, uk, 2;\n shr.u32 tm, %53, tm;\n"               \
     "and.b32 o, tm, 1;\n setp.ne.u32 pw0, o, 0;\n"              \
     "and.b32 o, tm, 2;\n setp.ne.u32 pw1, o, 0;\n"              \
-    "and.b32 o, tm, 4;\n setp.ne.u32 pw2, o, 0;\n"              \
-    "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
-    "shl.b32 us, uk, 3;\n sub.u32 us, 32, us;\n"
-#define AWQ_UNALIGNED_TAIL                                      \
+    "and.b32 o, tm, 4;\n setp.ne.u32 pw2, o, 0;\n"
+#define AWQ_HALO_STORE                                          \
+    "shfl.sync.up.b32 q1, q4, 1, 0, 0xffffffff;\n"              \
+    "shf.r.clamp.b32 q1, q1, q0, us;\n"                         \
+    "shf.r.clamp.b32 q3, q0, q2, us;\n"                         \
+    "shf.r.clamp.b32 q5, q2, q4, us;\n"                         \
+    "@pw0 st.global.b32 [oa], q1;\n"                            \
+    "@pw1 st.global.b32 [oa+4], q3;\n"                          \
+    "@pw2 st.global.b32 [oa+8], q5;\n"                          \
+    "{\n"                                                       \
+    "@!pew bra.uni HALO_DONE;\n"                                \
     "bar.warp.sync 0xffffffff;\n"                               \
-    "ld.shared.b32 q0, [pr];\n ld.shared.b32 q1, [pr+128];\n ld.shared.b32 q2, [pr+256];\n" \
-    "ld.shared.b32 q3, [pr+-4];\n ld.shared.b32 q4, [pr+124];\n ld.shared.b32 q5, [pr+252];\n" \
-    "shf.r.clamp.b32 q0, q3, q0, us;\n shf.r.clamp.b32 q1, q4, q1, us;\n shf.r.clamp.b32 q2, q5, q2, us;\n" \
-    "@pw0 st.global.b32 [oa], q0;\n"                            \
-    "@pw1 st.global.b32 [oa+128], q1;\n"                        \
-    "@pw2 st.global.b32 [oa+256], q2;\n"                        \
+    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
+    "bar.warp.sync 0xffffffff;\n"                               \
+    "shr.u32 tm, %60, uk;\n and.b32 tm, tm, 1;\n setp.ne.u32 pe, tm, 0;\n" \
     "@pe ld.shared.u8 o, [pedge];\n"                            \
-    "@pe st.global.u8 [oae], o;\n"
+    "add.s32 tm, up0, %61;\n cvt.s64.s32 ro64, tm;\n add.s64 oae, %49, ro64;\n" \
+    "@pe st.global.u8 [oae], o;\n"                              \
+    "HALO_DONE:\n"                                              \
+    "}\n"
 #define AWQ_EMIT_WU                                             \
-    AWQ_UNALIGNED_BEGIN                                         \
+    AWQ_HALO_BEGIN                                              \
     "prmt.b32 q0, va0, va1, 0x0073;\n"                          \
     "prmt.b32 q1, va2, vb0, 0x0073;\n"                          \
     "prmt.b32 q2, vb1, vb2, 0x0073;\n"                          \
@@ -229,11 +239,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q0, q0, q1, 0x5410;\n"                            \
     "prmt.b32 q2, q2, q3, 0x5410;\n"                            \
     "prmt.b32 q4, q4, q5, 0x5410;\n"                            \
-    "bar.warp.sync 0xffffffff;\n"                               \
-    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
-    AWQ_UNALIGNED_TAIL
+    AWQ_HALO_STORE
 #define AWQ_EMIT_LU                                             \
-    AWQ_UNALIGNED_BEGIN                                         \
+    AWQ_HALO_BEGIN                                              \
     "prmt.b32 q0, va0, va1, 0x0073;\n prmt.b32 q0, q0, va2, 0x0710;\n"  \
     "prmt.b32 q1, vb0, vb1, 0x0073;\n prmt.b32 q1, q1, vb2, 0x0710;\n"  \
     "prmt.b32 q2, vc0, vc1, 0x0073;\n prmt.b32 q2, q2, vc2, 0x0710;\n"  \
@@ -245,8 +253,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "prmt.b32 q0, q1, q3, 0x4210;\n"                            \
     "prmt.b32 q2, q3, q5, 0x5421;\n"                            \
     "prmt.b32 q4, q5, tm, 0x6542;\n"                            \
-    "st.shared.b32 [pw], q0;\n st.shared.b32 [pw+4], q2;\n st.shared.b32 [pw+8], q4;\n" \
-    AWQ_UNALIGNED_TAIL
+    AWQ_HALO_STORE
 // rows emitted after slot s (label prefix L keeps the two unrolled halves apart).  Every emit variant also fetches the
 // table entry of the row AFTER the one being emitted, early enough for the loop-carried compare (the entry after the
 // sentinel is read too: still inside the CTA's shared memory, never used)
@@ -263,8 +270,8 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "add.s32 s, s, 1;\n"
 #define AWQ_DECL                                                \
     ".reg .pred p, q, pv, podd;\n"                              \
-    ".reg .b32 s, rp, ex, ey, ez, ew, o, sx, sq, pw, pr, tm, uk, us, pedge;\n" \
-    ".reg .pred pw0, pw1, pw2, pe;\n"                               \
+    ".reg .b32 s, rp, ex, ey, ez, ew, o, sx, sq, pw, tm, uk, us, up0, pedge;\n" \
+    ".reg .pred pw0, pw1, pw2, pe, pew;\n"                               \
     ".reg .b64 ro64, oa, oae;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
     ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
@@ -286,7 +293,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
     "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
-    "mov.b32 pw, %51;\n mov.b32 pr, %52;\n mov.b32 pedge, %62;\n"  \
+    "mov.b32 pw, %51;\n mov.b32 pedge, %62;\n setp.ne.u32 pew, %52, 0;\n" \
     "and.b32 tm, %53, 1;\n setp.ne.u32 pw0, tm, 0;\n"           \
     "and.b32 tm, %53, 2;\n setp.ne.u32 pw1, tm, 0;\n"           \
     "and.b32 tm, %53, 4;\n setp.ne.u32 pw2, tm, 0;\n"           \
@@ -345,16 +352,21 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
       "r"(n_slots), "r"(sx), "r"(d.sq), "r"(d.lane12), "r"(pitch), "r"(rp), "r"(0), "r"(odd_first), "r"(store_ok), \
       "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3]),       \
-      "l"(d.obase), "r"(d.lane4), "r"(d.pw), "r"(d.pr), "r"(d.wmask), "r"(0), "r"(0), "r"(0),                     \
+      "l"(d.obase), "r"(d.cb), "r"(d.pw), "r"(d.edge_warp), "r"(d.wmask), "r"(0), "r"(0), "r"(0),                 \
       "r"(0), "r"(0), "r"(0), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                                       \
     : "memory"
 
-// what the emit variants need (see AWQ_EMIT_WD / AWQ_EMIT_LD / AWQ_UNALIGNED_TAIL)
+// what the emit variants need (see AWQ_OWN12_BEGIN / AWQ_HALO_BEGIN / AWQ_HALO_STORE)
 struct DirectOps {
-    uint64_t obase;
-    uint32_t lane4, pw, pr, wmask;      // MODE 2 (wmask: validity bits of the lane's three words per alignment)
-    uint32_t emask, eoff, pedge;        // MODE 2 only
-    uint32_t sq, lane12;                // MODE 1: scratch address of my four adjacent RGBX pixels (LANE), 12 * lane
+    uint64_t obase;                     // MODE 1: the warp's first destination byte at row offset 0; MODE 2: the
+                                        // 4-byte aligned address at or below the image's first byte
+    uint32_t sq, lane12;                // scratch address of my four adjacent RGBX pixels (LANE mapping), 12 * lane
+    // MODE 2 only
+    uint32_t cb;                        // 3 * (strip-relative column of the warp's first lane pixel; -1 for warp 0)
+    uint32_t pw;                        // scratch address of my 12 bytes in P (edge warps)
+    uint32_t edge_warp;                 // this warp holds the first or the last word of the row
+    uint32_t wmask;                     // validity bits [4 a + m] of the lane's three words
+    uint32_t emask, eoff, pedge;        // edge byte: alignments at which this lane stores it, offset from P0, address in P
 };
 
 // FIXED: win = word addresses, sh = shifts.  !FIXED: win = byte addresses (sh unused).
@@ -543,7 +555,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     slot_pitch = row_bytes;
                 } else {
                     int lo = 0x7fffffff, hi = -1;
-                    for (int x = lane; x < ncols; x += 32) {
+                    // (MODE 2: the first warp of a strip that is not the image's first also computes the column before it)
+                    for (int x = lane - ((MODE == 2 && x_first > 0) ? 1 : 0); x < ncols; x += 32) {
                         int xb, w0, w1;
                         column_taps(__ldg(mx + x), W, xb, w0, w1);
                         lo = min(lo, xb);
@@ -675,10 +688,12 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     }
 
     // =============================== consumer warps ==============================================
-    // this thread's output columns inside the strip.  QUAD mapping: 4 tid .. 4 tid + 3.  LANE mapping: columns
-    // 32 j + lane of the warp's 128-column block.
-    const int x0 = tid * 4;
-    const int xw = (tid & ~31) * 4;   // first column of the warp's block
+    // this thread's output columns inside the strip.  A warp's lanes cover 128 consecutive columns from xw: its block
+    // of kBlockPx columns and, in MODE 2, the column before it (the halo: see AWQ_HALO_BEGIN).  QUAD mapping: columns
+    // xw + 4 lane .. + 3.  LANE mapping: columns xw + 32 j + lane.
+    constexpr int kBlockPx = MODE == 2 ? 127 : 128, kHalo = MODE == 2 ? 1 : 0;
+    const int xw = warp_idx * kBlockPx - kHalo;
+    const int x0 = xw + 4 * lane;
     int wo[4];                        // byte offset of each column's window inside a staged row span
     uint32_t wl[4], wh[4], E[12], O[12];
 #pragma unroll
@@ -690,29 +705,32 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     uint32_t store_ok = 0u;           // this thread owns at least one column of the strip (QUAD position)
     const uint32_t sx_s = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 4);     // scratch: my RGBX pixels in
     DirectOps dops{};
-    dops.lane4 = 4u * (uint32_t)lane;
     dops.lane12 = 12u * (uint32_t)lane;
     dops.sq = scratch_s + (uint32_t)(warp_idx * 1024 + lane * 16);
-    // packed row P (one pad word in front of it for MODE 2's funnel shifts): my 12 bytes in, my three words out
-    dops.pw = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 12);
-    dops.pr = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + lane * 4);
+    dops.cb = (uint32_t)(3 * xw);
+    const uint32_t p_s = scratch_s + (uint32_t)(warp_idx * 1024 + 512);       // P: the warp's 384 bytes (edge warps)
+    dops.pw = p_s + (uint32_t)(lane * 12);
     int xba[4];                       // source column of each of my pixels' left tap (-1: none yet)
 
-    // per-strip setup: taps and weights of this thread's columns, choice of the mapping
-    auto setup_strip = [&](const float* mx, int W, int ncols) {
-        store_ok = x0 < ncols ? 1u : 0u;
-        warp_live = __any_sync(0xffffffffu, store_ok != 0u);
+    // per-strip setup: taps and weights of this thread's columns, choice of the mapping.  A column outside the strip
+    // gets zero weights and the window of a neighbour; the halo column (-1) exists when the strip is not the first.
+    auto setup_strip = [&](const float* mx, int W, int ncols, int x_first) {
+        const int x_min = (kHalo && x_first > 0) ? -1 : 0;
+        auto in_strip = [&](int x) { return x >= x_min && x < ncols; };
+        store_ok = (in_strip(x0) || in_strip(x0 + 3)) ? 1u : 0u;
+        // the warp works if it has a column of its own block (the halo alone does not count)
+        warp_live = warp_idx * kBlockPx < ncols;
         int xb = -1, xb_first = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            // a column past the strip's end keeps the previous column's window and gets zero weights
             int w0 = 0, w1 = 0;
-            if (x0 + j < ncols) column_taps(__ldg(mx + x0 + j), W, xb, w0, w1);
-            if (j == 0) xb_first = xb;
+            if (in_strip(x0 + j)) column_taps(__ldg(mx + x0 + j), W, xb, w0, w1);
             xba[j] = xb;
             wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
             wh[j] = wl[j] << 16;
         }
+        // where the lane's first pixel taps (extrapolated from the second one when the first is outside the strip)
+        xb_first = xba[0] >= 0 ? xba[0] : xba[1] - 1;
         // QUAD loads are conflict-free only while the lanes' windows stay 3 words apart: when the source column
         // of some lane's first pixel has drifted two or more pixels from "4 per lane", switch the warp to the
         // LANE mapping
@@ -728,7 +746,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             for (int j = 0; j < 4; ++j) {
                 const int x = xw + 32 * j + lane;
                 int w0 = 0, w1 = 0;
-                if (x < ncols) column_taps(__ldg(mx + x), W, xb, w0, w1);
+                if (in_strip(x)) column_taps(__ldg(mx + x), W, xb, w0, w1);
                 xba[j] = xb;
                 wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
                 wh[j] = wl[j] << 16;
@@ -746,7 +764,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             if (local < v.n_strips * v.n_rowtiles && v.unit_begin + local * v.tile_units < u1) {
                 const int strip = local / v.n_rowtiles;
                 const int x_first = strip * v.strip_cols;
-                setup_strip(v.mx + x_first, v.W, min(v.strip_cols, v.Wo - x_first));
+                setup_strip(v.mx + x_first, v.W, min(v.strip_cols, v.Wo - x_first), x_first);
                 pre_img = img;
                 pre_x_first = x_first;
             }
@@ -768,7 +786,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             if ((int)h1.x != pre_img || (int)h1.y != pre_x_first) {
                 const uint4 hx = ld128(tab + kTabStrip);
                 const float* mx = reinterpret_cast<const float*>(((uint64_t)hx.y << 32) | hx.x);
-                setup_strip(mx, (int)hx.z, (int)hx.w);
+                setup_strip(mx, (int)hx.z, (int)hx.w, (int)h1.y);
             }
             pre_img = -1;                                    // the early setup serves the first segment only
 #pragma unroll
@@ -786,6 +804,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 const int ay = sy & 31;
                 const int ya = clampi(sy >> 5, 0, H - 1), yb = clampi((sy >> 5) + 1, 0, H - 1);
                 for (int j = 0; j < 4 && x0 + j < ncols; ++j) {
+                    if (x0 + j < warp_idx * kBlockPx) continue;          // the halo column belongs to the previous block
                     const int sx = quantise_coord(__ldg(v.mx + x_first + x0 + j));
                     const int ax = sx & 31;
                     const int xa = clampi(sx >> 5, 0, W - 1), xc = clampi((sx >> 5) + 1, 0, W - 1);
@@ -805,33 +824,40 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             const uint32_t odd = (flags & kFlagOddFirst) ? 1u : 0u;
             uint32_t win[4], sh[4];
             {
-                // the warp's 384 bytes of a row start 384 * warp bytes after the strip's first byte
-                const uint4 hs = ld128(tab + kTabStore);                         // {image lo, hi, strip row bytes, -}
-                dops.obase = (((uint64_t)hs.y << 32) | hs.x) + (uint64_t)(warp_idx * 384);
-                const int nb = (int)hs.z - warp_idx * 384;                       // bytes of the warp's block in the strip
+                const uint4 hs = ld128(tab + kTabStore);                         // {image lo, hi, strip row bytes, Wo * 3}
+                const uint64_t img_al = ((uint64_t)hs.y << 32) | hs.x;
                 if (MODE == 1) {
-                    dops.wmask = (4 * lane + 4 <= nb ? 1u : 0u) | (4 * lane + 132 <= nb ? 2u : 0u) | (4 * lane + 260 <= nb ? 4u : 0u);
+                    // the warp's 384 bytes of a row start 384 * warp bytes after the strip's first byte
+                    dops.obase = img_al + (uint64_t)(warp_idx * 384);
                 } else {
-                    // the block's bytes sit at [k, k + nb) of the aligned word stream, nb = min(bytes left, 384)
-                    const int nbb = nb < 384 ? nb : 384;
+                    // stream positions relative to P0 (lane 0's first byte): the block's own bytes are [3, 3 + 3 n)
+                    const uint4 h1 = ld128(tab + 16);
+                    const int ncols = (int)hs.z / kC, x_first = (int)h1.y;
+                    const int n = min(kBlockPx, ncols - warp_idx * kBlockPx);
+                    const bool head_warp = warp_idx == 0 && x_first == 0;
+                    const bool tail_warp = warp_idx * kBlockPx + n == ncols && (x_first + ncols) * kC == (int)hs.w;
                     uint32_t vm = 0u, em = 0u;
-                    const int edge = lane < 3 ? lane : lane - 4;                   // tail byte nbb - 3 + i | head byte i
-                    const int boff = lane < 3 ? nbb - 3 + lane : lane - 4;
+                    const int rel = lane < 3 ? 3 * n + lane : 3 + (lane - 4);       // tail byte i | head byte i
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int al = 0; al < 4; ++al) {
 #pragma unroll
                         for (int m = 0; m < 3; ++m) {
-                            const int j = lane + 32 * m;
-                            if ((j > 0 || k == 0) && 4 * j + 4 <= k + nbb) vm |= 1u << (4 * k + m);
+                            const int r = 12 * lane + 4 * m - al;                   // first byte of the aligned word
+                            if (r >= (head_warp ? 3 : 0) && r < 3 * n) vm |= 1u << (4 * al + m);
                         }
-                        const bool tail = lane < 3 && k + nbb - 3 + edge >= ((k + nbb) & ~3);
-                        const bool head = lane >= 4 && lane < 7 && k > 0 && k + edge < 4;
-                        if (tail || head) em |= 1u << k;
+                        const int tc = (al + 3 + 3 * n) & 3;                        // bytes of the row's last, partial word
+                        const int h0 = (al + 3) & 3;                                // misalignment of the row's first byte
+                        const bool tail = tail_warp && lane < 3 && lane >= 3 - tc;
+                        const bool head = head_warp && lane >= 4 && lane < 7 && h0 != 0 && (lane - 4) < 4 - h0 &&
+                                          (lane - 4) < 3 * n;
+                        if (tail || head) em |= 1u << al;
                     }
+                    dops.obase = img_al;
                     dops.wmask = vm;
-                    dops.emask = nbb >= 3 ? em : 0u;
-                    dops.eoff = (uint32_t)boff;
-                    dops.pedge = scratch_s + (uint32_t)(warp_idx * 1024 + 512 + 16 + (boff > 0 ? boff : 0));
+                    dops.emask = em;
+                    dops.eoff = (uint32_t)rel;
+                    dops.pedge = p_s + (uint32_t)rel;
+                    dops.edge_warp = (head_warp || tail_warp) ? 1u : 0u;
                 }
             }
             if (flags & kFlagFixedShift) {
@@ -976,18 +1002,21 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
 // per SM), <= 6 (2-3 CTAs), <= 11 and 12 (one CTA, ~120 registers) and a 96-register build that runs 7..9 warps with
 // two CTAs per SM and 13..16 (strips of <= 2048 columns) with one.
 constexpr int kDirectMaxWarps = 16;
-inline int direct_warps(int cols) {
-    const int w = (cols + 127) / 128;
+// columns a consumer warp owns: 128, or 127 + the halo column when rows may be unaligned (MODE 2)
+inline int block_px(bool aligned) { return aligned ? 128 : 127; }
+inline int direct_warps(int cols, bool aligned) {
+    const int w = (cols + block_px(aligned) - 1) / block_px(aligned);
     return w < 3 ? 3 : w;
 }
-// ATTWARP_QUAD_MAXW = 3 .. 16 narrows the widest strip to that many warps (tuning experiments)
-inline int direct_max_cols() {
+// ATTWARP_QUAD_MAXW = 3 .. 16 narrows the widest strip to that many warps (tuning experiments); strips are cut at
+// multiples of 16 columns
+inline int direct_max_cols(bool aligned) {
     const int w = env_int("ATTWARP_QUAD_MAXW", kDirectMaxWarps);
-    return (w >= 3 && w <= kDirectMaxWarps ? w : kDirectMaxWarps) * 128;
+    return ((w >= 3 && w <= kDirectMaxWarps ? w : kDirectMaxWarps) * block_px(aligned)) & ~15;
 }
 template <int MODE>
 int launch_direct_mode(QuadArgs& a, int cols, cudaStream_t st) {
-    const int w = direct_warps(cols);
+    const int w = direct_warps(cols, MODE == 1);
     if (w <= 3) return launch_core(remap_u8_quad_kernel<128, 5, MODE>, w, 5, a, cols, st);
     if (w <= 6) return launch_core(remap_u8_quad_kernel<224, 2, MODE>, w, w == 4 ? 3 : 2, a, cols, st);
     if (w <= 9) return launch_core(remap_u8_quad_kernel<(kDirectMaxWarps + 1) * 32, 1, MODE>, w, 2, a, cols, st);
@@ -1019,7 +1048,10 @@ bool remap_quad_enabled() {
 int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, int Ho, int Wo, const float* map_x,
                          const float* map_y, cudaStream_t st) {
     QuadArgs a{};
-    const StripPlan sp = plan_strips(Wo, direct_max_cols());
+    // row offsets inside an image travel as 32-bit values (signed in MODE 2)
+    if ((int64_t)Ho * Wo * kC > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: output image of %d x %d exceeds 2 GB", Ho, Wo);
+    const bool aligned = rows_word_aligned(dst, Wo);
+    const StripPlan sp = plan_strips(Wo, direct_max_cols(aligned));
     a.n_strips = sp.n_strips;
     a.strip_cols = sp.strip_cols;
     a.src = static_cast<const uint8_t*>(src);
@@ -1034,7 +1066,7 @@ int launch_remap_u8_quad(const void* src, void* dst, int n_img, int H, int W, in
     if (total > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: too many tiles");
     a.total_units = (int)total;
     const int cols = Wo < a.strip_cols ? Wo : a.strip_cols;
-    return launch_direct(a, cols, rows_word_aligned(dst, Wo), st);
+    return launch_direct(a, cols, aligned, st);
 }
 
 // Ragged batch.  Images are grouped into width classes, one launch per class with the geometry that fits it (a
@@ -1057,13 +1089,14 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     sorted.assign((size_t)n + kRaggedClasses, RaggedImage{});
     cls.assign((size_t)n, 0);
     *plan = RaggedQuadPlan{};
-    const int dmax = direct_max_cols();
     int64_t px[kRaggedClasses] = {};
     for (int i = 0; i < n; ++i) {
         const RaggedImage& im = host[i];
-        const StripPlan sp = plan_strips(im.Wo, dmax);
-        const int c = direct_warps(im.Wo < sp.strip_cols ? im.Wo : sp.strip_cols) - 3 +
-                      (rows_word_aligned(im.dst, im.Wo) ? 0 : kDirectClasses);
+        if ((int64_t)im.Ho * im.Wo * kC > 0x7fffffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: output image %d exceeds 2 GB", i);
+        const bool aligned = rows_word_aligned(im.dst, im.Wo);
+        const StripPlan sp = plan_strips(im.Wo, direct_max_cols(aligned));
+        const int c = direct_warps(im.Wo < sp.strip_cols ? im.Wo : sp.strip_cols, aligned) - 3 +
+                      (aligned ? 0 : kDirectClasses);
         cls[(size_t)i] = c;
         px[c] += (int64_t)im.Wo * im.Ho;
     }
@@ -1110,9 +1143,11 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     int64_t total[kRaggedClasses] = {};
     for (int i = 0; i < n; ++i) {
         const int c = cls[(size_t)i];
-        const StripPlan sp = plan_strips(host[i].Wo, dmax);
+        // (an aligned image that joined an any-alignment class is planned like the rest of that class)
+        const bool aligned = plan->mode[c] == 1;
+        const StripPlan sp = plan_strips(host[i].Wo, direct_max_cols(aligned));
         const int cols = host[i].Wo < sp.strip_cols ? host[i].Wo : sp.strip_cols;
-        const int units = (cols + 127) / 128;
+        const int units = (cols + block_px(aligned) - 1) / block_px(aligned);
         if (sp.n_strips > 0xffff) return fail(ATTWARP_ERR_UNSUPPORTED, "remap: image %d is too wide", i);
         host[i].strips_units = sp.n_strips | (units << 16);
         host[i].strip_cols = sp.strip_cols;

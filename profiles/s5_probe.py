@@ -33,19 +33,21 @@ def maps(B, side, grid, kind):
     return ops.maps_from_tokens(tok, (side, side))
 
 
-def run(name, B, side, grid, kind, layout="hwc", C=3, R=4, wside=None):
+def run(name, B, side, grid, kind, layout="hwc", C=3, R=4, wside=None, woside=None):
     if args.only and not name.strip().startswith(args.only):
         return
-    wside = side if wside is None else wside
+    wside = side if wside is None else wside          # source width
+    woside = wside if woside is None else woside      # output width
     shape = (B, side, wside, C) if layout == "hwc" else (B, C, side, wside)
+    oshape = (B, side, woside, C) if layout == "hwc" else (B, C, side, woside)
     imgs = [torch.randint(0, 256, shape, device=dev, dtype=torch.uint8, generator=gen) for _ in range(R)]
-    outs = [torch.empty_like(i) for i in imgs]
-    if wside != side:
+    outs = [torch.empty(oshape, device=dev, dtype=torch.uint8) for _ in imgs]
+    if wside != side or woside != side:
         tok = torch.rand(B, grid, grid, device=dev, generator=gen) ** 3
-        mx, my = ops.maps_from_tokens((tok / tok.sum(dim=(1, 2), keepdim=True)).contiguous(), (side, wside))
+        mx, my = ops.maps_from_tokens((tok / tok.sum(dim=(1, 2), keepdim=True)).contiguous(), (side, wside), (side, woside))
     else:
         mx, my = maps(B, side, grid, kind)
-    by = 2 * imgs[0].numel()
+    by = imgs[0].numel() + outs[0].numel()
     for dbg in (["0", "1"] if args.dbg else ["0"]):
         os.environ["ATTWARP_REMAP_DBG"] = dbg
         for i in range(3):
@@ -68,6 +70,8 @@ run("c2  256x336^2 hwc near-uniform", 256, 336, 24, "c2", R=8)
 run("c2  256x336^2 hwc rand^3", 256, 336, 24, "c3", R=8)
 run("c2u 256x336x335 rows unaligned", 256, 336, 24, "c3", R=8, wside=335)
 run("c3u 64x1344x1343 rows unaligned", 64, 1344, 48, "c3", wside=1343)
+run("c3us 64x1344: 1343 -> 1344 (source rows unaligned only)", 64, 1344, 48, "c3", wside=1343, woside=1344)
+run("c3ud 64x1344: 1344 -> 1343 (destination rows unaligned only)", 64, 1344, 48, "c3", wside=1344, woside=1343)
 run("    1024x336^2 hwc near-uniform", 1024, 336, 24, "c2", R=3)
 run("c3  64x1344^2 hwc rand^3 48x48", 64, 1344, 48, "c3")
 run("    256x1344^2 hwc rand^3 48x48", 256, 1344, 48, "c3", R=2)

@@ -52,6 +52,12 @@ def test_strong_minification(C):
     mx = np.sort(rng.random((B, Wo)) * W, axis=1).astype(np.float32)
     my = np.sort(rng.random((B, Ho)) * H, axis=1).astype(np.float32)
     _check(img, mx, my)
+    # wide, strongly minified rows with an odd width: the rows whose source span does not fit a stage are gathered
+    # pixel by pixel by several warps (each skips the halo column it shares with its neighbour)
+    if C == 3:
+        mx3 = np.sort(rng.random((B, 301)) * W, axis=1).astype(np.float32)
+        my3 = np.sort(rng.random((B, 33)) * H, axis=1).astype(np.float32)
+        _check(img, mx3, my3)
     # moderate vertical minification only (3.7x): rows are skipped but the pass still fits
     my2 = (np.arange(400, dtype=np.float32) * 3.7)[None]
     mx2 = (np.arange(500, dtype=np.float32) * 1.01 + 0.3)[None]
