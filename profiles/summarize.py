@@ -36,7 +36,7 @@ def launches(path, out):
     seq = []
     for r in rows[1:]:
         ns = float(r[iv].replace(",", ""))
-        if "aw::" in r[ik]:
+        if "aw::" in r[ik] or "unnamed>::" in r[ik]:
             k = short(r[ik])
             d = ours.setdefault(k, {"n": 0, "ns": 0.0, "grid": r[ig], "block": r[ib]})
             d["n"] += 1
