@@ -198,10 +198,12 @@ __device__ __forceinline__ float pool_value(float v, bool take_sqrt) {
 }
 template <int MODE>
 __global__ void __launch_bounds__(128)
-adaptive_avg_pool2d_kernel(const float* __restrict__ A, const uint8_t* __restrict__ sqrt_mask, int H, int W, int gh,
-                           int gw, float* __restrict__ out) {
+adaptive_avg_pool2d_kernel(const float* __restrict__ A, const uint8_t* __restrict__ sqrt_mask, int n_img, int H, int W,
+                           int gh, int gw, float* __restrict__ out) {
     extern __shared__ double cs[];                         // [W] column sums over the window's rows
-    const int i = blockIdx.x, b = blockIdx.y;
+    // (image, output row) pairs are dealt round-robin to a grid sized for whole rounds: every CTA takes the same number
+    for (int pair = blockIdx.x; pair < gh * n_img; pair += gridDim.x) {
+    const int i = pair % gh, b = pair / gh;
     const int y0 = (int)(((int64_t)i * H) / gh), y1 = (int)(((int64_t)(i + 1) * H + gh - 1) / gh);
     const float* img = A + (int64_t)b * H * W;
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
@@ -238,6 +240,8 @@ adaptive_avg_pool2d_kernel(const float* __restrict__ A, const uint8_t* __restric
         double t = 0.0;
         for (int x = x0; x < x1; ++x) t += cs[x];
         out[((int64_t)b * gh + i) * gw + j] = (float)(t / (double)((y1 - y0) * (x1 - x0)));
+    }
+    __syncthreads();                                       // cs is reused by the next pair
     }
 }
 
@@ -415,7 +419,21 @@ int launch_adaptive_avg_pool2d(const float* A, const uint8_t* sqrt_mask, int B, 
     auto kern = sqrt_mask ? adaptive_avg_pool2d_kernel<1> : adaptive_avg_pool2d_kernel<0>;
     if (smem > 48 * 1024)
         AW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(gh, B), 128, smem, st>>>(A, sqrt_mask, H, W, gh, gw, out);
+    // one resident wave of CTAs, each with the same number of (image, output row) pairs where that divides evenly
+    // (3072 pairs over 2368 slots would run a full round and a 30 % one: 0.63 of the HBM peak; 1536 CTAs x 2: see
+    // profiles/r03*_row_kernels.txt)
+    static thread_local size_t occ_smem[2] = {~(size_t)0, ~(size_t)0};
+    static thread_local int occ_val[2] = {0, 0};
+    const int v = sqrt_mask ? 1 : 0;
+    if (occ_smem[v] != smem) {
+        AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_val[v], kern, 128, smem));
+        occ_smem[v] = smem;
+    }
+    const int occ = occ_val[v];
+    const int64_t slots = (int64_t)(occ < 1 ? 1 : occ) * sm_count(), pairs = (int64_t)gh * B;
+    const int64_t rounds = (pairs + slots - 1) / slots;
+    const int grid = (int)((pairs + rounds - 1) / rounds);
+    kern<<<grid, 128, smem, st>>>(A, sqrt_mask, B, H, W, gh, gw, out);
     return check_launch("adaptive_avg_pool2d_kernel");
 }
 
