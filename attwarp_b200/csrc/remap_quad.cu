@@ -40,6 +40,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -1224,14 +1225,21 @@ int launch_remap_u8_quad_ragged_run(const RaggedQuadPlan& plan, const RaggedImag
         AW_CUDA(cudaEventRecord(fo.fork, st));
         for (int i = 0; i + 1 < lanes; ++i) AW_CUDA(cudaStreamWaitEvent(fo.aux[i], fo.fork, 0));
     }
-    int k = 0, rc = ATTWARP_OK;
-    for (int c = 0; c < kRaggedClasses && rc == ATTWARP_OK; ++c) {
-        if (plan.count[c] == 0 || plan.total_units[c] == 0) continue;
+    // biggest classes first (longest-processing-time order over the lanes): the small ones fill the gaps at the end
+    int order[kRaggedClasses], n_order = 0;
+    for (int c = 0; c < kRaggedClasses; ++c)
+        if (plan.count[c] != 0 && plan.total_units[c] != 0) order[n_order++] = c;
+    std::sort(order, order + n_order, [&](int x, int y) {
+        return plan.total_units[x] != plan.total_units[y] ? plan.total_units[x] > plan.total_units[y] : x < y;
+    });
+    int rc = ATTWARP_OK;
+    for (int k = 0; k < n_order && rc == ATTWARP_OK; ++k) {
+        const int c = order[k];
         QuadArgs a{};
         a.imgs = dev_sorted + plan.offset[c];
         a.n_img = plan.count[c];
         a.total_units = plan.total_units[c];
-        const int lane = k++ % lanes;
+        const int lane = k % lanes;
         rc = launch_direct(a, plan.max_strip[c], plan.mode[c] == 1, lane == 0 ? st : fo.aux[lane - 1]);
     }
     // join even after a failed launch: the caller's stream must not run ahead of work already enqueued

@@ -112,6 +112,8 @@ def warp_files(image_sources: Sequence, tok: torch.Tensor, output_paths: Sequenc
     The attention the reference warps with in this flow is ``blend_mask``'s image-size uint8 mask; use
     ``ops.mota_mask`` + ``ops.maps_from_attention`` when that exact quantisation is wanted -- this entry point warps
     with the token map index-upsampled on the fly (BASELINE configs[3])."""
+    if len(image_sources) == 0:
+        return []
     imgs = decode_jpeg_batch(image_sources, device)
     dev = imgs[0].device
     outs = ops.warp_ragged_from_tokens(tok.to(dev), imgs, out_sizes, transform=transform, exp_scale=exp_scale,

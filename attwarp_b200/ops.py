@@ -405,7 +405,10 @@ def warp_ragged_from_tokens(tok: torch.Tensor, images, out_sizes=None, grid_hw=N
     AGW/main_batched.py:243-287 (one warp_image_by_attention call per image)."""
     lib = load()
     n = len(images)
-    assert n > 0 and tok.shape[0] == n
+    if tok.shape[0] != n:
+        raise ValueError(f"warp_ragged_from_tokens: {tok.shape[0]} token maps for {n} images")
+    if n == 0:                      # the reference's per-image loop over an empty list does nothing
+        return []
     if tok.dim() == 3:
         gh, gw = tok.shape[1], tok.shape[2]
     else:

@@ -84,6 +84,9 @@ def test_ragged_degenerate_and_errors():
     need_gpu()
     from attwarp_b200 import ops
     from attwarp_b200._lib import AttWarpError
+    assert ops.warp_ragged_from_tokens(torch.empty(0, 8, 8, device="cuda"), []) == []
+    with pytest.raises(ValueError):
+        ops.warp_ragged_from_tokens(torch.empty(2, 8, 8, device="cuda"), [])
     rng = np.random.default_rng(4)
     sizes = [(1, 50), (40, 40), (30, 1)]
     imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
