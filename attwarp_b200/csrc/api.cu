@@ -360,6 +360,14 @@ int attwarp_warp_ragged_from_tokens(const float* tok, int n, int gh, int gw,
     if (workspace_bytes < need)
         return fail(ATTWARP_ERR_WORKSPACE, "warp_ragged: workspace too small (%zu < %zu)", workspace_bytes, need);
     cudaStream_t st = as_stream(stream);
+    {
+        // the descriptor tables are uploaded from this thread's host buffers: a captured copy node would read them at
+        // replay time, after later calls have rewritten them
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        AW_CUDA(cudaStreamIsCapturing(st, &cap));
+        if (cap != cudaStreamCaptureStatusNone)
+            return fail(ATTWARP_ERR_UNSUPPORTED, "warp_ragged: cannot be captured into a CUDA graph (host-side descriptor tables)");
+    }
     RaggedImage* dev_table = static_cast<RaggedImage*>(workspace);
     float* pool = reinterpret_cast<float*>(static_cast<char*>(workspace) + ragged_table_bytes(n));
     static thread_local std::vector<RaggedImage> host;

@@ -1169,9 +1169,8 @@ int launch_remap_u8_quad_ragged_prepare(RaggedImage* host, int n, RaggedImage* d
     return ATTWARP_OK;
 }
 // Step 2: one launch per non-empty class.  The classes write disjoint images, so their launches fan out over up to
-// three streams (the caller's + two of the library's, forked and joined with events -- also legal inside a stream
-// capture): every launch is a persistent grid with a ramp (first chunk ~8 us) and a ragged tail, which the next
-// class's CTAs fill as SMs come free.  ATTWARP_RAGGED_STREAMS=1 keeps everything on the caller's stream.
+// three streams (the caller's + two of the library's, forked and joined with events): every launch is a
+// persistent grid with a ramp (first chunk ~8 us) and a ragged tail, which the next class's CTAs fill as SMs come free.  ATTWARP_RAGGED_STREAMS=1 keeps everything on the caller's stream.
 namespace {
 struct FanOut {
     static constexpr int kAux = 2;

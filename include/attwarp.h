@@ -232,6 +232,8 @@ int attwarp_warp_from_pdfs(const float* px, const float* py, int B, int Nx, int 
  *             image's H x W exactly like attwarp_maps_from_tokens
  * workspace : attwarp_ragged_workspace_bytes(images, n) bytes of device scratch (descriptor table
  *             + the per-image map rows)
+ * The call uploads its descriptor tables from host memory and fans the stage-5 launches out over internal streams;
+ * it returns ATTWARP_ERR_UNSUPPORTED on a stream that is being captured into a CUDA graph.
  */
 typedef struct attwarp_ragged_image {
     const void* src;
