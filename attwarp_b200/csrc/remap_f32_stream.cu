@@ -289,7 +289,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_f32_stream_kernel(const F32A
                 const int prev_ya = __shfl_up_sync(0xffffffffu, ya, 1);
                 const int prev_yb = __shfl_up_sync(0xffffffffu, yb, 1);
                 const int r0 = __shfl_sync(0xffffffffu, ya, 0);
-                const int r_lo = (r0 == carry_row - 1 || r0 == carry_row) ? carry_row + 1 : r0;
+                const int yb0 = __shfl_sync(0xffffffffu, yb, 0);
+                // A chunk either extends the pair the consumers hold or starts afresh.  A fresh start stages at least
+                // TWO contiguous rows, so that "the consumers hold carry_row - 1 and carry_row" stays true: a first row
+                // on the bottom border taps row H - 1 twice (ya == yb), and staging that row alone would leave an
+                // older row in the other register for a later chunk that starts at H - 2 to pick up.
+                const int r_lo = (r0 == carry_row - 1 || r0 == carry_row) ? carry_row + 1
+                                                                          : ((r0 == yb0 && r0 > 0) ? r0 - 1 : r0);
                 const int need = yb + 1 - r_lo;
                 // (rows are emitted in table order as the slots advance: both taps must be non-decreasing)
                 const unsigned bad = __ballot_sync(0xffffffffu, !live || (lane > 0 && (ya < prev_ya || yb < prev_yb)) ||

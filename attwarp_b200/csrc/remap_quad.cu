@@ -403,6 +403,7 @@ struct QuadArgs {
     int n_img;
     int total_units;         // length of the cost axis (uniform batch: one unit per output row of a strip)
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
+    int smem_total;          // dynamic shared memory of the CTA
     int rows;                // output rows per chunk (<= kMaxRows)
     int stages;              // ring depth: source-row stages (chunks whose loads are in flight)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     // pitch congruent to the row pitch modulo 16 so that slot k keeps the phase of source row k
                     slot_pitch = ((row_bytes + 45 + 15) & ~15) + (int)(row_pitch & 15);
                 }
-                const int max_slots = min((a.stage_bytes - 64) / slot_pitch, 2 * R);
+                const int arena_slots = min((a.stage_bytes - 64) / slot_pitch, 2 * R);
                 const uint8_t* scol = simg + (int64_t)c_lo * kC;
                 const bool fixed = (slot_pitch & 3) == 0;
                 uint32_t seg_flags = kFlagNewStrip | (fixed ? kFlagFixedShift : 0u);
@@ -589,6 +590,10 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 while (y_cur < y_end) {
                     const int tab = tab_off0 + st * kTabBytes;
                     const uint32_t stage_s = smem_s + (uint32_t)(st * a.stage_bytes);
+                    // The sweep requests the window of slot s + 1 before it blends slot s, also after the last slot: that
+                    // read (never used) must stay inside the CTA's shared memory.  With slots much wider than the
+                    // strip (a narrow strip that taps whole source rows) the last stage has less room behind it.
+                    const int max_slots = min(arena_slots, (a.smem_total - st * a.stage_bytes - 32) / slot_pitch - 1);
                     if (y_cur - y_win >= 32) {
                         y_win += 32;
                         sy_cur = sy_nxt;
@@ -718,7 +723,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     auto setup_strip = [&](const float* mx, int W, int ncols, int x_first) {
         const int x_min = (kHalo && x_first > 0) ? -1 : 0;
         auto in_strip = [&](int x) { return x >= x_min && x < ncols; };
-        store_ok = (in_strip(x0) || in_strip(x0 + 3)) ? 1u : 0u;
+        store_ok = (x0 + 3 >= x_min && x0 < ncols) ? 1u : 0u;          // one of my four columns is in the strip
         // the warp works if it has a column of its own block (the halo alone does not count)
         warp_live = warp_idx * kBlockPx < ncols;
         int xb = -1, xb_first = 0;
@@ -927,6 +932,7 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
     a.stage_bytes = ((R + 2) * unit_pitch + 64 + 127) & ~127;
     const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + 2 * (size_t)stages * sizeof(uint64_t) + 16 +
                               (size_t)scratch;
+    a.smem_total = (int)smem_bytes;
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     a.drift = env_int("ATTWARP_QUAD_DRIFT", 2);
     // per (kernel, device): the largest shared-memory size configured so far; per (kernel, device, threads, smem): occupancy
