@@ -148,3 +148,48 @@ def test_lanczos_random(case):
         for x, y in zip(a, b_):
             ulp = np.abs(x.cpu().numpy().view(np.int32).astype(np.int64) - y.cpu().numpy().view(np.int32).astype(np.int64))
             assert ulp.max() <= 1, (case, "fused vs two-step", int(ulp.max()))
+
+
+@pytest.mark.parametrize("case", range(max(8, N_CASES // 2)))
+def test_torch_helpers_random(case):
+    """The torch-path helpers at random sizes: safe_softmax (with non-finite logits), mix_with_uniform and their fused
+    form, cdf_from_density, the right-inverse upsample at lengths that are and are not multiples of the grid,
+    gt_marginals and adaptive pooling at sizes that miss the vectorised paths."""
+    need_gpu()
+    from attwarp_b200 import checkpoint_utils as CU, model as M
+    rng = np.random.default_rng(8500 + case)
+    B, N = int(rng.integers(1, 200)), int(rng.integers(1, 80))
+    z = (rng.standard_normal((B, N)) * 4).astype(np.float32)
+    if case % 3 == 0:
+        z[rng.random((B, N)) < 0.05] = np.nan
+        z[rng.random((B, N)) < 0.05] = np.inf
+        z[rng.random((B, N)) < 0.05] = -np.inf
+    alpha = float(rng.choice([0.0, 0.03, 0.5]))
+    with np.errstate(all="ignore"):
+        p_ref = OT.safe_softmax(z)
+        m_ref = OT.mix_with_uniform(p_ref, alpha)
+    p = M.safe_softmax(dev(z))
+    assert rel_err(p.cpu().numpy(), p_ref, 1e-7) <= 2e-5, (case, "safe_softmax", B, N)
+    assert rel_err(M.mix_with_uniform(p, alpha).cpu().numpy(), OT.mix_with_uniform(p.cpu().numpy(), alpha), 1e-7) <= 1e-5
+    assert rel_err(M.safe_softmax_mix(dev(z), alpha).cpu().numpy(), m_ref, 1e-7) <= 2e-5, (case, "softmax_mix")
+    # CDFs
+    d = (rng.random((B, N)) ** 2 - 0.1).astype(np.float32)
+    assert np.abs(CU.cdf_from_density(dev(d)).cpu().numpy() - OT.cdf_from_density(d)).max() <= 1e-5, (case, "cdf")
+    # right-inverse upsample
+    L_out = int(rng.integers(2, 30))
+    L_in = int(rng.choice([L_out * int(rng.integers(1, 30)), int(rng.integers(L_out, 700))]))
+    y = rng.random((min(B, 16), L_out)).astype(np.float32)
+    y /= y.sum(axis=1, keepdims=True)
+    got = CU.upsample_pdf_right_inverse(dev(y), L_in).cpu().numpy()
+    ref = OT.upsample_pdf_right_inverse(y, L_in)
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (case, "upsample", L_out, L_in)
+    # marginals and pooling of a full-resolution map
+    H, W = int(rng.integers(1, 300)), int(rng.integers(1, 700))
+    A = (rng.random((min(B, 3), 1, H, W)) - 0.2).astype(np.float32)
+    px, py = CU.gt_marginals(dev(A))
+    rx, ry = OT.gt_marginals(A)
+    assert rel_err(px.cpu().numpy(), rx, 1e-9) <= 2e-5 and rel_err(py.cpu().numpy(), ry, 1e-9) <= 2e-5, (case, "gt_marginals", H, W)
+    gh, gw = int(rng.integers(1, min(H, 30) + 1)), int(rng.integers(1, min(W, 30) + 1))
+    got = CU.adaptive_avg_pool2d_24(dev(A), (gh, gw)).cpu().numpy()
+    ref = OT.adaptive_avg_pool2d(A, (gh, gw))
+    assert np.abs(got - ref).max() <= 1e-5, (case, "pool", (H, W), (gh, gw))
