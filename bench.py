@@ -411,12 +411,13 @@ def timed_steps(ctx, step, n_steps, first_index, fork=None, join=None):
 
 
 def pick_roofline(ctx, kernels, workload, total_bytes):
-    """`roofline` = the kernel that dominates the step; when two kernels are within 10 % of each other in time,
-    the one FURTHER from the peak.  `worst` = the kernel furthest below peak of all, `worst_streaming` = among the
+    """`roofline` = the kernel that dominates the step; when two kernels are within 15 % of each other in time
+    (a margin wider than the 10 % box-to-box spread of the two c2 kernels, so that the choice does not flip between
+    runs), the one FURTHER from the peak.  `worst` = the kernel furthest below peak of all, `worst_streaming` = among the
     kernels that move >= 5 % of the step's bytes (the others are latency-bound: a few KB per image)."""
     streaming = {k: v for k, v in kernels.items() if v["algorithmic_bytes"] >= 0.05 * total_bytes}
     dom_ms = max(v["ms"] for v in streaming.values())
-    cands = [k for k, v in streaming.items() if v["ms"] >= 0.9 * dom_ms]
+    cands = [k for k, v in streaming.items() if v["ms"] >= 0.85 * dom_ms]
     dom = min(cands, key=lambda k: kernels[k]["frac"])
     worst = min(kernels, key=lambda k: kernels[k]["frac"])
     worst_s = min(streaming, key=lambda k: kernels[k]["frac"])
@@ -424,7 +425,7 @@ def pick_roofline(ctx, kernels, workload, total_bytes):
             "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": ncu_traffic(dom, workload),
             "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
             "kernel_ms": kernels[dom]["ms"],
-            "selection": "dominant kernel by CUDA-event time; of kernels within 10 % in time, the lower fraction",
+            "selection": "dominant kernel by CUDA-event time; of kernels within 15 % in time, the lower fraction",
             "worst": {"kernel": worst, "frac": kernels[worst]["frac"], "achieved": kernels[worst]["achieved_gbs"],
                       "note": "latency-bound launch (a few KB per image)" if worst not in streaming else "streaming kernel"},
             "worst_streaming": {"kernel": worst_s, "frac": kernels[worst_s]["frac"],
