@@ -22,8 +22,8 @@
 //     without re-packing; the vertical blend of an output row is  t = wO*O + (wE*E + 512 * 2^14)  with the row's
 //     weights pre-shifted by 14 bits -- two 32-bit multiply-adds (the sum stays below 2^32) whose TOP BYTE is the
 //     output byte ((v + 512) >> 10 with nothing to shift or mask: prmt picks the top bytes when packing);
-//   * the horizontal blend pairs the taps of a channel with one prmt per two channels (bytes p0c0 p1c0 p0c1
-//     p1c1) so that a pixel needs two weight words instead of five;
+//   * the horizontal blend of a pixel is three dp4a: channel 0 on the aligned window word itself (bytes p0c0 p0c1
+//     p0c2 p1c0, weights w0 . . w1), channels 1 and 2 on one prmt of the window (p0c1 p1c1 p0c2 p1c2);
 //   * source rows are staged at a UNIFORM shared-memory pitch whatever the alignment of the image: a strip that
 //     spans whole rows is fetched with ONE bulk copy per chunk (global rows are contiguous; the shared-memory
 //     image is the global one shifted by a multiple of 16 bytes), narrower strips with one copy per row into
@@ -112,20 +112,20 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "shl.b32 n" #J ", u" #J ", 3;\n"
 #define AWQ_ADDR_F AWQ_ADDR_F1(a) AWQ_ADDR_F1(b) AWQ_ADDR_F1(c) AWQ_ADDR_F1(d)
 #define AWQ_ADDR_V AWQ_ADDR_V1(a) AWQ_ADDR_V1(b) AWQ_ADDR_V1(c) AWQ_ADDR_V1(d)
-// align the 8-byte window, pair the taps: X = p0c0 p1c0 p0c1 p1c1,  Y = p0c2 p1c2 . .
+// align the 8-byte window: A = p0c0 p0c1 p0c2 p1c0 (channel 0 is a dp4a of A itself with the weights w0 . . w1),
+// B = p1c1 p1c2 . . ; pair the taps of the other two channels: X = p0c1 p1c1 p0c2 p1c2
 #define AWQ_ALIGN1(J, SH)                                       \
     "shf.r.wrap.b32 A" #J ", lo" #J ", mi" #J ", " SH ";\n"     \
     "shf.r.wrap.b32 B" #J ", mi" #J ", hi" #J ", " SH ";\n"     \
-    "prmt.b32 X" #J ", A" #J ", B" #J ", 0x4130;\n"             \
-    "prmt.b32 Y" #J ", A" #J ", B" #J ", 0x0052;\n"
+    "prmt.b32 X" #J ", A" #J ", B" #J ", 0x5241;\n"
 #define AWQ_ALIGN_F AWQ_ALIGN1(a, "sa") AWQ_ALIGN1(b, "sb") AWQ_ALIGN1(c, "sc") AWQ_ALIGN1(d, "sd")
 #define AWQ_ALIGN_V AWQ_ALIGN1(a, "ma") AWQ_ALIGN1(b, "mb") AWQ_ALIGN1(c, "mc") AWQ_ALIGN1(d, "md")
 // the shift of the CURRENT slot must survive the address update of the next one
 #define AWQ_KEEP_V "mov.b32 ma, na;\n mov.b32 mb, nb;\n mov.b32 mc, nc;\n mov.b32 md, nd;\n"
 #define AWQ_DOT1(P, J)                                          \
-    "dp4a.u32.u32 " #P #J "0, X" #J ", wl" #J ", 0;\n"          \
-    "dp4a.u32.u32 " #P #J "1, X" #J ", wh" #J ", 0;\n"          \
-    "dp4a.u32.u32 " #P #J "2, Y" #J ", wl" #J ", 0;\n"
+    "dp4a.u32.u32 " #P #J "0, A" #J ", wa" #J ", 0;\n"          \
+    "dp4a.u32.u32 " #P #J "1, X" #J ", wl" #J ", 0;\n"          \
+    "dp4a.u32.u32 " #P #J "2, X" #J ", wh" #J ", 0;\n"
 #define AWQ_DOT(P) AWQ_DOT1(P, a) AWQ_DOT1(P, b) AWQ_DOT1(P, c) AWQ_DOT1(P, d)
 // vertical blend of one byte: top byte of the 32-bit  E * (wE << 14) + O * (wO << 14) + (512 << 14)
 #define AWQ_V1(J, K)                                            \
@@ -275,9 +275,9 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     ".reg .pred pw0, pw1, pw2, pe, pew;\n"                               \
     ".reg .b64 ro64, oa, oae;\n"                 \
     ".reg .b32 loa, mia, hia, lob, mib, hib, loc, mic, hic, lod, mid, hid;\n"   \
-    ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Ya, Xb, Yb, Xc, Yc, Xd, Yd;\n" \
+    ".reg .b32 Aa, Ba, Ab, Bb, Ac, Bc, Ad, Bd, Xa, Xb, Xc, Xd;\n" \
     ".reg .b32 ka, kb, kc, kd, ua, ub, uc, ud, sa, sb, sc, sd, ma, mb, mc, md, na, nb, nc, nd;\n" \
-    ".reg .b32 wla, wha, wlb, whb, wlc, whc, wld, whd;\n"       \
+    ".reg .b32 wla, wha, wlb, whb, wlc, whc, wld, whd, waa, wab, wac, wad;\n" \
     ".reg .b32 Ea0, Ea1, Ea2, Eb0, Eb1, Eb2, Ec0, Ec1, Ec2, Ed0, Ed1, Ed2;\n"   \
     ".reg .b32 Oa0, Oa1, Oa2, Ob0, Ob1, Ob2, Oc0, Oc1, Oc2, Od0, Od1, Od2;\n"   \
     ".reg .b32 va0, va1, va2, vb0, vb1, vb2, vc0, vc1, vc2, vd0, vd1, vd2;\n"   \
@@ -293,6 +293,7 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     "mov.b32 Oc0, %18;\n mov.b32 Oc1, %19;\n mov.b32 Oc2, %20;\n mov.b32 Od0, %21;\n mov.b32 Od1, %22;\n mov.b32 Od2, %23;\n" \
     "mov.b32 wla, %41;\n mov.b32 wha, %42;\n mov.b32 wlb, %43;\n mov.b32 whb, %44;\n"  \
     "mov.b32 wlc, %45;\n mov.b32 whc, %46;\n mov.b32 wld, %47;\n mov.b32 whd, %48;\n"  \
+    "mov.b32 waa, %54;\n mov.b32 wab, %55;\n mov.b32 wac, %56;\n mov.b32 wad, %57;\n"  \
     "mov.b32 sx, %33;\n mov.b32 sq, %34;\n"                     \
     "mov.b32 pw, %51;\n mov.b32 pedge, %62;\n setp.ne.u32 pew, %52, 0;\n" \
     "and.b32 tm, %53, 1;\n setp.ne.u32 pw0, tm, 0;\n"           \
@@ -353,8 +354,8 @@ __device__ __forceinline__ void column_taps(float m, int W, int& xb, int& w0, in
     : "r"(win[0]), "r"(win[1]), "r"(win[2]), "r"(win[3]), "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]),   \
       "r"(n_slots), "r"(sx), "r"(d.sq), "r"(d.lane12), "r"(pitch), "r"(rp), "r"(0), "r"(odd_first), "r"(store_ok), \
       "r"(wl[0]), "r"(wh[0]), "r"(wl[1]), "r"(wh[1]), "r"(wl[2]), "r"(wh[2]), "r"(wl[3]), "r"(wh[3]),       \
-      "l"(d.obase), "r"(d.cb), "r"(d.pw), "r"(d.edge_warp), "r"(d.wmask), "r"(0), "r"(0), "r"(0),                 \
-      "r"(0), "r"(0), "r"(0), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                                       \
+      "l"(d.obase), "r"(d.cb), "r"(d.pw), "r"(d.edge_warp), "r"(d.wmask), "r"(wa[0]), "r"(wa[1]), "r"(wa[2]),     \
+      "r"(wa[3]), "r"(0), "r"(0), "r"(d.emask), "r"(d.eoff), "r"(d.pedge)                                   \
     : "memory"
 
 // what the emit variants need (see AWQ_OWN12_BEGIN / AWQ_HALO_BEGIN / AWQ_HALO_STORE)
@@ -375,7 +376,8 @@ struct DirectOps {
 // stores per lane); 2: rows at any alignment (+ byte stores at the two ends of the warp's block).
 template <bool FIXED, bool LANE, int MODE>
 __device__ __forceinline__ void sweep_quad(uint32_t* E, uint32_t* O, const uint32_t* win, const uint32_t* sh,
-                                           const uint32_t* wl, const uint32_t* wh, int n_slots, uint32_t pitch,
+                                           const uint32_t* wl, const uint32_t* wh, const uint32_t* wa, int n_slots,
+                                           uint32_t pitch,
                                            uint32_t rp, uint32_t odd_first, uint32_t sx, uint32_t store_ok,
                                            const DirectOps& d) {
 #define AWQ_RUN(BODY, EMIT) asm volatile("{\n" AWQ_DECL AWQ_PROLOGUE BODY(EMIT) AWQ_EPILOGUE "}\n" AWQ_OPERANDS)
@@ -701,11 +703,11 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const int xw = warp_idx * kBlockPx - kHalo;
     const int x0 = xw + 4 * lane;
     int wo[4];                        // byte offset of each column's window inside a staged row span
-    uint32_t wl[4], wh[4], E[12], O[12];
+    uint32_t wl[4], wh[4], wa[4], E[12], O[12];   // weight words per pixel: w0 w1 . . | . . w0 w1 | w0 . . w1
 #pragma unroll
     for (int k = 0; k < 12; ++k) E[k] = O[k] = 0u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { wo[j] = 0; wl[j] = wh[j] = 0u; }
+    for (int j = 0; j < 4; ++j) { wo[j] = 0; wl[j] = wh[j] = wa[j] = 0u; }
     bool warp_live = false;           // some lane of this warp owns a column of the strip
     bool lane_map = false;            // this warp runs the LANE mapping in the current strip
     uint32_t store_ok = 0u;           // this thread owns at least one column of the strip (QUAD position)
@@ -734,6 +736,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             xba[j] = xb;
             wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
             wh[j] = wl[j] << 16;
+            wa[j] = (uint32_t)w0 | ((uint32_t)w1 << 24);
         }
         // where the lane's first pixel taps (extrapolated from the second one when the first is outside the strip)
         xb_first = xba[0] >= 0 ? xba[0] : xba[1] - 1;
@@ -756,6 +759,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 xba[j] = xb;
                 wl[j] = (uint32_t)w0 | ((uint32_t)w1 << 8);
                 wh[j] = wl[j] << 16;
+                wa[j] = (uint32_t)w0 | ((uint32_t)w1 << 24);
             }
         }
     };
@@ -873,13 +877,13 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     win[j] = b & ~3u;
                     sh[j] = b << 3;
                 }
-                if (!lane_map) sweep_quad<true, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
-                else sweep_quad<true, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                if (!lane_map) sweep_quad<true, false, MODE>(E, O, win, sh, wl, wh, wa, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                else sweep_quad<true, true, MODE>(E, O, win, sh, wl, wh, wa, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { win[j] = base + (uint32_t)wo[j]; sh[j] = 0u; }
-                if (!lane_map) sweep_quad<false, false, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
-                else sweep_quad<false, true, MODE>(E, O, win, sh, wl, wh, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                if (!lane_map) sweep_quad<false, false, MODE>(E, O, win, sh, wl, wh, wa, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
+                else sweep_quad<false, true, MODE>(E, O, win, sh, wl, wh, wa, n_slots, h0.z, rp_s, odd, sx_s, store_ok, dops);
             }
         }
         __syncwarp();
