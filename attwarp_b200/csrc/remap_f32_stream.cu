@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_f32_stream_kernel(const F32A
                 const uint32_t bytes = lane < n_slots ? (uint32_t)((off + row_bytes + 15) & ~15) : 0u;
                 const uint32_t tx = one_copy ? (uint32_t)((phase0 + n_slots * slot_pitch + 15) & ~15)
                                              : __reduce_add_sync(0xffffffffu, bytes);
-                mbar_wait(sfree_s + 8u * st, ph ^ 1u);
+                mbar_wait_relaxed(sfree_s + 8u * st, ph ^ 1u);       // (the producer runs ahead: it sleeps between polls)
                 if (lane < n_rows) {
                     const float fy = fmul_nofma((float)ay, 1.0f / 32.0f);
                     st128(tab + kTabRows + 16 * lane,
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_f32_stream_kernel(const F32A
             }
             u += seg_rows;
         }
-        mbar_wait(sfree_s + 8u * st, ph ^ 1u);
+        mbar_wait_relaxed(sfree_s + 8u * st, ph ^ 1u);
         if (lane == 0) {
             st128(tab_off0 + st * kTabBytes, make_uint4(0xffffffffu, 0u, 0u, 0u));
             mbar_arrive(full_s + 8u * st);

@@ -509,9 +509,9 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
     const int u0 = (int)(((int64_t)a.total_units * blockIdx.x) / gridDim.x);
     const int u1 = (int)(((int64_t)a.total_units * (blockIdx.x + 1)) / gridDim.x);
 
-    // warp roles: consumers 0 .. n_cons_warps-1, then the producer.  Waits on mbarriers are plain try_wait loops
-    // (suspend-time hints, a sleeping producer and the producer as the CTA's first warp were measured: no change,
-    // profiles/r02p_*, r03b_*)
+    // warp roles: consumers 0 .. n_cons_warps-1, then the producer.  The consumers' waits are plain try_wait loops;
+    // the producer, which runs ahead, sleeps between polls (suspend-time hints, sleep lengths and the producer as the
+    // CTA's first warp were measured: no change in run time, profiles/r02p_*, r03b_*)
     const int warp_idx = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
     const int lane = (int)threadIdx.x & 31;
     const int tid = (int)threadIdx.x;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                                                  : __reduce_add_sync(0xffffffffu, bytes);
                     const uintptr_t gd = dimg + (uintptr_t)(((int64_t)y * Wo + x_first) * kC);   // this row's first byte
 
-                    wait(sfree_s + 8u * st, ph ^ 1u);             // stage free again
+                    mbar_wait_relaxed(sfree_s + 8u * st, ph ^ 1u);    // stage free again (the producer runs ahead)
                     if (lane < n_rows) {
                         const uint32_t wu = (uint32_t)wa << 14, wl_ = (uint32_t)(32 - wa) << 14;   // upper / lower tap
                         const bool up_even = (ra & 1) == 0;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                 local = local_end;
             }
             // terminator
-            wait(sfree_s + 8u * st, ph ^ 1u);
+            mbar_wait_relaxed(sfree_s + 8u * st, ph ^ 1u);
             if (lane == 0) {
                 st128(tab_off0 + st * kTabBytes, make_uint4(0xffffffffu, 0u, 0u, 0u));
                 mbar_arrive(full_s + 8u * st);
