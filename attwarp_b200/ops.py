@@ -485,6 +485,7 @@ class RaggedBatch:
         self._table = table
         self._table_p = table.ctypes.data_as(C.c_void_p)
         self.n = n
+        self.launches = 0            # kernels the last run() enqueued (maps + one resample launch per class)
         self._ws = torch.empty(max(int(lib.attwarp_ragged_workspace_bytes(self._table_p, n)), 256), dtype=torch.uint8,
                                device=self.device)
 
