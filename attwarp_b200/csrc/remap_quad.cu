@@ -56,7 +56,7 @@ namespace {
 using namespace ptx;
 
 constexpr int kMaxRing = 4;            // source-row stages per CTA are a launch parameter (2 .. 4)
-constexpr int kMaxRows = 16;          // capacity of a chunk table; the rows per chunk are a launch parameter
+constexpr int kMaxRows = 30;          // capacity of a chunk table (a lane plans a row, one carries the sentinel); the rows per chunk are a launch parameter
 constexpr int kC = 3;
 
 extern __shared__ __align__(128) uint8_t smem[];
@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     // pitch congruent to the row pitch modulo 16 so that slot k keeps the phase of source row k
                     slot_pitch = ((row_bytes + 45 + 15) & ~15) + (int)(row_pitch & 15);
                 }
-                const int arena_slots = min((a.stage_bytes - 64) / slot_pitch, 2 * R);
+                // (one bulk copy per slot is issued by one lane each: at most 32 slots without the single-copy path)
+                const int arena_slots = min(min((a.stage_bytes - 64) / slot_pitch, 2 * R), one_copy ? 2 * kMaxRows : 32);
                 const uint8_t* scol = simg + (int64_t)c_lo * kC;
                 const bool fixed = (slot_pitch & 3) == 0;
                 uint32_t seg_flags = kFlagNewStrip | (fixed ? kFlagFixedShift : 0u);
@@ -1010,8 +1011,8 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
 
 // The CTA gets exactly the consumer warps the strips need -- ceil(columns / 128), at least 3 -- and the SM as many
 // CTAs as its registers hold.  Builds of the kernel by register budget (launch bounds): <= 3 consumer warps (5 CTAs
-// per SM), <= 6 (2-3 CTAs), <= 11 and 12 (one CTA, ~120 registers) and a 96-register build that runs 7..9 warps with
-// two CTAs per SM and 13..16 (strips of <= 2048 columns) with one.
+// per SM by registers, run with 4), <= 6 (2-3 CTAs), <= 11 and 12 (one CTA, ~120 registers) and a 96-register build
+// that runs 7..9 warps with two CTAs per SM and 13..16 (strips of <= 2048 columns) with one.
 constexpr int kDirectMaxWarps = 16;
 // columns a consumer warp owns: 128, or 127 + the halo column when rows may be unaligned (MODE 2)
 inline int block_px(bool aligned) { return aligned ? 128 : 127; }
@@ -1028,7 +1029,9 @@ inline int direct_max_cols(bool aligned) {
 template <int MODE>
 int launch_direct_mode(QuadArgs& a, int cols, cudaStream_t st) {
     const int w = direct_warps(cols, MODE == 1);
-    if (w <= 3) return launch_core(remap_u8_quad_kernel<128, 5, MODE>, w, 5, a, cols, st);
+    // (<= 3 warps: four CTAs per SM with ~22-row chunks beat five with 16-row chunks -- fewer chunk turn-arounds:
+    // 43.9 -> 42.6 us at configs[1], profiles/r04b_rows.txt)
+    if (w <= 3) return launch_core(remap_u8_quad_kernel<128, 5, MODE>, w, 4, a, cols, st);
     if (w <= 6) return launch_core(remap_u8_quad_kernel<224, 2, MODE>, w, w == 4 ? 3 : 2, a, cols, st);
     if (w <= 9) return launch_core(remap_u8_quad_kernel<(kDirectMaxWarps + 1) * 32, 1, MODE>, w, 2, a, cols, st);
     if (w <= 11) return launch_core(remap_u8_quad_kernel<384, 1, MODE>, w, 1, a, cols, st);
