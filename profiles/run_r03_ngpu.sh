@@ -3,7 +3,7 @@
 N=$1
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-P=gpurun_out/r03_${N}gpu
+P=gpurun_out/r05_${N}gpu
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > ${P}_bench.json 2> ${P}_bench.err; tail -c 300 ${P}_bench.err | grep -v "OMP_NUM\|^\*\*\*"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > ${P}_bench_ref.json 2> ${P}_bench_ref.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 profiles/h2d_ceiling.py > ${P}_h2d_ceiling.txt 2> ${P}_h2d_ceiling.err; tail -5 ${P}_h2d_ceiling.txt
