@@ -406,6 +406,7 @@ struct QuadArgs {
     int total_units;         // length of the cost axis (uniform batch: one unit per output row of a strip)
     int stage_bytes;         // bytes of the source-row arena of one stage (multiple of 128)
     int smem_total;          // dynamic shared memory of the CTA
+    int first_rows;          // rows of a CTA's first chunk (the second has twice as many, then `rows`)
     int rows;                // output rows per chunk (<= kMaxRows)
     int stages;              // ring depth: source-row stages (chunks whose loads are in flight)
     int map_policy;          // 0: per warp and strip (LANE when the map's local scale would make QUAD loads conflict),
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
             int st = 0;
             uint32_t ph = 0;                 // parity of the stage's current use
             bool first_copy = true;
+            int n_chunks_done = 0;
             int img = first_image(a, u0, lane);
             View v = get_view(a, img);
             int local = (u0 - v.unit_begin + v.tile_units - 1) / v.tile_units;   // first tile starting at >= u0
@@ -604,7 +606,8 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     }
                     // ---- plan: lane i <-> output row y_cur + i --------------------------------
                     const int y = y_cur + lane;
-                    const bool live = y < y_end && lane < R;
+                    // (the CTA's first chunks are short: their rows land sooner and the sweep starts earlier)
+                    const bool live = y < y_end && lane < (n_chunks_done < 2 ? min(R, a.first_rows << n_chunks_done) : R);
                     const int wsel = y - y_win;                       // 0 .. 31 + R - 1
                     const int sy_a = __shfl_sync(0xffffffffu, sy_cur, wsel & 31);
                     const int sy_b = __shfl_sync(0xffffffffu, sy_nxt, wsel & 31);
@@ -680,6 +683,7 @@ __global__ void __launch_bounds__(MAXT, MINB) remap_u8_quad_kernel(const QuadArg
                     }
                     if (first_copy && lane == 0) trace_stamp(a, 1);    // first chunk planned, its copy issued
                     first_copy = false;
+                    ++n_chunks_done;
                     carry_row = n_rows > 0 ? ra_last + 1 : kNoCarry;
                     y_cur += max(n_rows, 1);
                     if (++st == kStages) { st = 0; ph ^= 1u; }
@@ -938,6 +942,7 @@ int launch_core(QuadKernel kern, int warps, int ctas, QuadArgs& a, int cols, cud
     const size_t smem_bytes = (size_t)stages * (a.stage_bytes + kTabBytes) + 2 * (size_t)stages * sizeof(uint64_t) + 16 +
                               (size_t)scratch;
     a.smem_total = (int)smem_bytes;
+    a.first_rows = env_int("ATTWARP_QUAD_FIRST_ROWS", 8);    // 8, 16, then full chunks: -1..2 % (profiles/r04e_first_rows.txt)
     a.map_policy = env_int("ATTWARP_QUAD_MAP", 0);          // 0 auto, 1 QUAD only, 2 LANE wherever possible
     a.drift = env_int("ATTWARP_QUAD_DRIFT", 2);
     // per (kernel, device): the largest shared-memory size configured so far; per (kernel, device, threads, smem): occupancy
