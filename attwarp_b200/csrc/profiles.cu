@@ -182,14 +182,26 @@ maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
 //   row sums are reduced per row with a warp-shuffle tree and combined across warps in shared
 //   memory (per-column-tile partials).  Both partial sets are summed in fixed order by the
 //   finish kernel -> deterministic.
-//   MODE 0: NumPy path  (clamp, transform, + 1e-9)   MODE 1: gt_marginals (clamp only)
+//   TR >= 0: NumPy path (clamp, transform TR, + 1e-9)   TR == kClampOnly: gt_marginals (clamp only).
+//   The transform is a template parameter: with a run-time switch in the pixel loop the unrolled bodies of the
+//   five transforms (float64 exp and log among them) did not fit the instruction cache and a float32 sqrt map
+//   ran at 0.12 of the HBM rate.  uint8 maps (TR == kByteTable) look their 256 possible values up in a
+//   shared-memory table the CTA fills with the run-time transform first.
 // -------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+constexpr int kClampOnly = -1;
+constexpr int kByteTable = 8;
+template <typename T, int TR>
 __global__ void __launch_bounds__(kMargThreads)
 marginals_partial_kernel(const T* __restrict__ att, int H, int W, TransformArgs ta,
                          double* __restrict__ colpart, double* __restrict__ rowpart,
                          int n_row_chunks, int n_col_tiles) {
     __shared__ double s_row[kMargRows][kMargThreads / 32];
+    __shared__ double s_tab[TR == kByteTable ? 256 : 1];
+    if (TR == kByteTable) {
+        for (int v = threadIdx.x; v < 256; v += kMargThreads)
+            s_tab[v] = transform_fwd((double)v, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
+        __syncthreads();
+    }
     const int b = blockIdx.z, chunk = blockIdx.y, tile = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int x0 = tile * kMargCols + threadIdx.x * kMargColsPerThread;
@@ -206,8 +218,13 @@ marginals_partial_kernel(const T* __restrict__ att, int H, int W, TransformArgs 
         for (int k = 0; k < kMargColsPerThread; ++k) {
             const int x = x0 + k;
             if (x < W) {
-                double a = clamp_nonneg(load_as_double<T>(img + (int64_t)y * W + x));
-                if (MODE == 0) a = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
+                double a;
+                if (TR == kByteTable) {
+                    a = s_tab[(int)__ldg(reinterpret_cast<const uint8_t*>(img + (int64_t)y * W + x))];
+                } else {
+                    a = clamp_nonneg(load_as_double<T>(img + (int64_t)y * W + x));
+                    if (TR >= 0) a = transform_fwd_t<TR>(a, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
+                }
                 col[k] += a;
                 rs += a;
             }
@@ -336,46 +353,94 @@ static int rows_per_cta(int B, int H, int nct, int ctas_per_sm, int max_rows) {
     return best;
 }
 
+// sqrt of a non-negative float32 as a float32 pair hi + lo with relative error < 2^-47 (the correctly rounded float64
+// sqrt has 2^-53; summing a 1344-pixel row in float64 in another order already moves the sum by up to 2^-43):
+// hardware rsqrt seed, one Newton step in float32 for hi (2^-23), the exact residual x - hi^2 by fma, and
+// lo = residual / (2 hi) with a refined reciprocal (2^-47.5 worst case over [1e-28, 3e38) with the seed off by
+// +-2 ulp, checked on the host).  0 -> (0, 0); tiny, infinite and NaN inputs take the float64 sqrt.
+__device__ __forceinline__ void sqrt_pair(float x, float& hi, float& lo) {
+    if (x >= 1.0e-27f && x < 3.0e38f) {              // the residual below stays a normal float32
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        const float s = __fmul_rn(x, y);
+        float h = __fmul_rn(0.5f, y);
+        hi = __fmaf_rn(__fmaf_rn(-s, s, x), h, s);
+        h = __fmaf_rn(__fadd_rn(h, h), __fmaf_rn(-hi, h, 0.5f), h);     // h -> 1 / (2 hi)
+        lo = __fmul_rn(__fmaf_rn(-hi, hi, x), h);
+    } else if (x == 0.f) {
+        hi = 0.f;
+        lo = 0.f;
+    } else {
+        const double r = sqrt((double)x);
+        hi = (float)r;
+        lo = hi < __int_as_float(0x7f800000) ? (float)(r - (double)hi) : 0.f;   // NaN: hi < inf is false
+    }
+}
+
 // (P2c) float32 attention maps with rows that are multiples of 4 floats (gt_marginals' A_full,
 // checkpoint_utils.py:43-51; float att maps of the NumPy path): the (P2b) organisation in float64.
 // A warp owns whole rows of a 512-column tile (4 float4 loads per lane and row, two rows in flight), column
 // sums stay in 16 float64 registers per lane, the row sum is one shuffle tree per ROW (the generic kernel
 // pays one per 128 columns), warps are combined in shared memory in warp order -> deterministic.
 constexpr int kF32TileCols = 512;
-template <int MODE>
-__global__ void __launch_bounds__(kMargThreads)
-marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_per_cta, TransformArgs ta,
+// T = uint8_t (TR == kByteTable): uint8 maps with a transform other than the identity (or rows the integer kernel
+// (P2b) does not take): the same organisation, four pixels per 32-bit load, each pixel's transformed value looked up
+// in a 256-entry float64 table the CTA fills first (the generic kernel ran these at 0.04-0.09 of the HBM rate).
+template <typename T, int TR>
+__global__ void __launch_bounds__(kMargThreads, 2)      // 128 registers: two CTAs per SM (136 registers ran one: 76 us vs 45)
+marginals_f32_rows_kernel(const T* __restrict__ att, int H, int W, int rows_per_cta, TransformArgs ta,
                           double* __restrict__ colpart, double* __restrict__ rowpart, int n_row_chunks,
                           int n_col_tiles) {
     constexpr int kWarps = kMargThreads / 32, kSteps = kF32TileCols / 128, U = 2;
+    constexpr bool kBytes = std::is_same<T, uint8_t>::value;
+    static_assert(kBytes == (TR == kByteTable), "uint8 maps use the table, float32 maps a compiled transform");
+    using Vec = typename std::conditional<kBytes, uint32_t, float4>::type;     // four pixels
     extern __shared__ double cwd[];                        // [kWarps][kF32TileCols]
+    __shared__ double s_tab[kBytes ? 256 : 1];
+    if (kBytes) {
+        for (int v = threadIdx.x; v < 256; v += kMargThreads)
+            s_tab[v] = transform_fwd((double)v, ta.transform, ta.exp_scale, ta.exp_divisor);
+        __syncthreads();
+    }
     const int b = blockIdx.z, chunk = blockIdx.y, tile = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int y0 = chunk * rows_per_cta, y1 = min(y0 + rows_per_cta, H);
     const int xt = tile * kF32TileCols;
     const int tile_cols = min(kF32TileCols, W - xt);
-    const float* img = att + (int64_t)b * H * W + xt;
+    const T* img = att + (int64_t)b * H * W + xt;
+    // float64 instructions are the scarce resource here (a float64 sqrt per pixel ran the kernel at 0.13 of the HBM
+    // rate, the clamp + bias + two sums of the identity at 0.36).  For the transforms whose value is a float32 PAIR
+    // (identity: x; sqrt: hi + lo to 2^-47, see sqrt_pair; x^2 as an exact pair measured slower than one float64
+    // multiplication) the clamp and the transform
+    // run in float32, the float64 sums take the converted hi part (one conversion + two adds per pixel) and the lo
+    // parts are summed in float32 beside them (they are 2^-24 of the hi parts); the + 1e-9 of every pixel is added once
+    // per row / column as count x 1e-9, like the uint8 kernel does.  exp and log keep their float64 evaluation.
+    constexpr bool kPair = TR < 0 || TR == T_IDENTITY || TR == T_SQRT;
+    constexpr bool kHasLo = TR == T_SQRT;
     double acc[kSteps][4];
+    float acc_lo[kHasLo ? kSteps : 1][4];
 #pragma unroll
     for (int s = 0; s < kSteps; ++s)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[s][k] = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            acc[s][k] = 0.0;
+            if (kHasLo) acc_lo[s][k] = 0.f;
+        }
     double* rp = rowpart + ((int64_t)b * n_col_tiles + tile) * H;
     // double-buffered like (P2b): the next two rows are in flight while these two are summed
-    auto fetch = [&](int y, float4 (&v)[U][kSteps]) {
+    auto fetch = [&](int y, Vec (&v)[U][kSteps]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool row_in = y + u * kWarps < y1;
-            const float* r = img + (int64_t)(y + u * kWarps) * W;
+            const T* r = img + (int64_t)(y + u * kWarps) * W;
 #pragma unroll
             for (int s = 0; s < kSteps; ++s) {
                 const int x = s * 128 + lane * 4;
-                v[u][s] = (row_in && x < tile_cols) ? __ldg(reinterpret_cast<const float4*>(r + x))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][s] = (row_in && x < tile_cols) ? __ldg(reinterpret_cast<const Vec*>(r + x)) : Vec();
             }
         }
     };
-    float4 v[U][kSteps], nx[U][kSteps];
+    Vec v[U][kSteps], nx[U][kSteps];
     fetch(y0 + wid, v);
     for (int y = y0 + wid; y < y1; y += U * kWarps) {
         fetch(y + U * kWarps, nx);
@@ -383,19 +448,41 @@ marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_
         for (int u = 0; u < U; ++u) {
             const bool row_in = y + u * kWarps < y1;
             double rs = 0.0;
+            float rs_lo = 0.f;
 #pragma unroll
             for (int s = 0; s < kSteps; ++s) {
+                if (s * 128 >= tile_cols) continue;            // (uniform) a narrow tile's empty steps
                 const bool in = row_in && s * 128 + lane * 4 < tile_cols;
+                if constexpr (kBytes) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double a = s_tab[(v[u][s] >> (8 * k)) & 0xffu];
+                        if (in) { acc[s][k] += a; rs += a; }
+                    }
+                } else {
                 const float f[4] = {v[u][s].x, v[u][s].y, v[u][s].z, v[u][s].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    double a = clamp_nonneg((double)f[k]);
-                    if (MODE == 0) a = transform_fwd(a, ta.transform, ta.exp_scale, ta.exp_divisor) + kBaseAttention;
-                    if (in) { acc[s][k] += a; rs += a; }
+                    if (kPair) {
+                        const float x = (f[k] > 0.f || f[k] != f[k]) ? f[k] : 0.f;   // np.maximum(a, 0): NaN stays
+                        float hi = x, lo = 0.f;
+                        if (TR == T_SQRT) sqrt_pair(x, hi, lo);
+                        const double a = (double)hi;
+                        if (in) {
+                            acc[s][k] += a;
+                            rs += a;
+                            if (kHasLo) { acc_lo[s][k] += lo; rs_lo += lo; }
+                        }
+                    } else {
+                        const double a = transform_fwd_t<TR>(clamp_nonneg((double)f[k]), ta.exp_scale, ta.exp_divisor);
+                        if (in) { acc[s][k] += a; rs += a; }
+                    }
+                }
                 }
             }
+            if (kHasLo) rs += (double)rs_lo;
             rs = warp_sum(rs);
-            if (lane == 0 && row_in) rp[y + u * kWarps] = rs;
+            if (lane == 0 && row_in) rp[y + u * kWarps] = TR >= 0 ? rs + (double)tile_cols * kBaseAttention : rs;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -405,14 +492,16 @@ marginals_f32_rows_kernel(const float* __restrict__ att, int H, int W, int rows_
 #pragma unroll
     for (int s = 0; s < kSteps; ++s)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cwd[wid * kF32TileCols + s * 128 + lane * 4 + k] = acc[s][k];
+        for (int k = 0; k < 4; ++k)
+            cwd[wid * kF32TileCols + s * 128 + lane * 4 + k] = kHasLo ? acc[s][k] + (double)acc_lo[s][k] : acc[s][k];
     __syncthreads();
     double* cp = colpart + ((int64_t)b * n_row_chunks + chunk) * W + xt;
+    const double col_base = TR >= 0 ? (double)(y1 - y0) * kBaseAttention : 0.0;
     for (int c = threadIdx.x; c < tile_cols; c += kMargThreads) {
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) t += cwd[w * kF32TileCols + c];
-        cp[c] = t;
+        cp[c] = t + col_base;
     }
 }
 
@@ -569,11 +658,11 @@ int launch_maps_from_tokens_ragged(const float* tok, int n, int gh, int gw, cons
 
 // One pass over the attention maps -> column / row partials.  Picks the kernel, launches it and reports the
 // number of row chunks / column tiles it wrote (<= marginals_geometry's, which sizes the workspace).
-template <typename T, int MODE>
-static int launch_marginals(const void* att, int B, int H, int W, const TransformArgs& ta,
-                            double* colpart, double* rowpart, cudaStream_t st, int* nrc_out, int* nct_out) {
+template <typename T, int TR>
+static int launch_marginals_t(const void* att, int B, int H, int W, const TransformArgs& ta,
+                              double* colpart, double* rowpart, cudaStream_t st, int* nrc_out, int* nct_out) {
     const bool aligned16 = (reinterpret_cast<uintptr_t>(att) & 15) == 0;
-    if (std::is_same<T, uint8_t>::value && MODE == 0 && ta.transform == T_IDENTITY && (W & 15) == 0 && aligned16) {
+    if constexpr (std::is_same<T, uint8_t>::value) if (ta.transform == T_IDENTITY && (W & 15) == 0 && aligned16) {
         static_assert(kU8MaxRows / (kMargThreads / 32) * 255 < 65536, "16-bit column lanes would overflow");
         const int nct = (W + kU8TileCols - 1) / kU8TileCols;
         const int cols = W < kU8TileCols ? W : kU8TileCols;
@@ -592,27 +681,47 @@ static int launch_marginals(const void* att, int B, int H, int W, const Transfor
         *nrc_out = nrc; *nct_out = nct;
         return check_launch("marginals_u8_identity_kernel");
     }
-    if (std::is_same<T, float>::value && (W & 3) == 0 && aligned16) {
+    const bool rows_ok = std::is_same<T, float>::value ? (W & 3) == 0 && aligned16
+                                                       : (W & 3) == 0 && (reinterpret_cast<uintptr_t>(att) & 3) == 0;
+    if constexpr (std::is_same<T, float>::value || std::is_same<T, uint8_t>::value) if (rows_ok) {
         const int nct = (W + kF32TileCols - 1) / kF32TileCols;
-        auto kern = marginals_f32_rows_kernel<MODE>;
+        auto kern = marginals_f32_rows_kernel<T, TR>;
         const size_t smem = sizeof(double) * (kMargThreads / 32) * kF32TileCols;
-        static thread_local int occ = 0;
+        static thread_local int occ = 0;          // per instantiation = per transform
         if (occ == 0) {
             AW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMargThreads, smem));
             if (occ < 1) occ = 1;
         }
         const int rows = rows_per_cta(B, H, nct, occ, 256);
         const int nrc = (H + rows - 1) / rows;
-        kern<<<dim3(nct, nrc, B), kMargThreads, smem, st>>>(static_cast<const float*>(att), H, W, rows, ta, colpart,
+        kern<<<dim3(nct, nrc, B), kMargThreads, smem, st>>>(static_cast<const T*>(att), H, W, rows, ta, colpart,
                                                          rowpart, nrc, nct);
         *nrc_out = nrc; *nct_out = nct;
         return check_launch("marginals_f32_rows_kernel");
     }
     const int nrc = (H + kMargRows - 1) / kMargRows, nct = (W + kMargCols - 1) / kMargCols;
-    marginals_partial_kernel<T, MODE><<<dim3(nct, nrc, B), kMargThreads, 0, st>>>(
+    marginals_partial_kernel<T, TR><<<dim3(nct, nrc, B), kMargThreads, 0, st>>>(
         static_cast<const T*>(att), H, W, ta, colpart, rowpart, nrc, nct);
     *nrc_out = nrc; *nct_out = nct;
     return check_launch("marginals_partial_kernel");
+}
+
+// MODE 0: NumPy path (the run-time transform picks the instantiation; unknown ids are the identity, like
+// transform_fwd's default).  MODE 1: gt_marginals (clamp only).
+template <typename T, int MODE>
+static int launch_marginals(const void* att, int B, int H, int W, const TransformArgs& ta,
+                            double* colpart, double* rowpart, cudaStream_t st, int* nrc_out, int* nct_out) {
+    if constexpr (MODE == 1) {
+        return launch_marginals_t<T, kClampOnly>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+    } else if constexpr (std::is_same<T, uint8_t>::value) {
+        return launch_marginals_t<T, kByteTable>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+    } else switch (ta.transform) {
+        case T_SQUARE: return launch_marginals_t<T, T_SQUARE>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+        case T_SQRT: return launch_marginals_t<T, T_SQRT>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+        case T_EXP: return launch_marginals_t<T, T_EXP>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+        case T_LOG: return launch_marginals_t<T, T_LOG>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+        default: return launch_marginals_t<T, T_IDENTITY>(att, B, H, W, ta, colpart, rowpart, st, nrc_out, nct_out);
+    }
 }
 
 size_t maps_workspace_bytes_impl(int B, int H, int W) {

@@ -227,7 +227,9 @@ static bool force_direct() {
 static int launch_u8_fast(const void* src, void* dst, int n_img, int C, int H, int W, int Ho, int Wo,
                           const float* map_x, const float* map_y, int map_div, cudaStream_t st) {
     // 3-channel interleaved images (the benchmark format): four adjacent pixels per thread (remap_quad.cu);
-    // grey / 4-channel / planar images: remap_stream.cu
+    // grey / 4-channel / planar images: remap_stream.cu.  (A column-walking kernel for those formats -- four output
+    // bytes per thread, taps read ahead with cp.async -- was measured in round 2 and dropped: correct, but no faster
+    // than remap_stream.cu except for large 4-channel images; profiles/r06_walk_kernel.md.)
     if (C == 3 && map_div == 1 && remap_quad_enabled())
         return launch_remap_u8_quad(src, dst, n_img, H, W, Ho, Wo, map_x, map_y, st);
     return launch_remap_u8_stream(src, dst, n_img, C, H, W, Ho, Wo, map_x, map_y, map_div, st);

@@ -150,6 +150,12 @@ AW_HD double transform_fwd(double x, int t, double exp_scale, double exp_divisor
         default: return x;
     }
 }
+// The same with the transform known at compile time (TR < 0: no transform at all): per-pixel loops are
+// instantiated once per transform, so their bodies hold one transform instead of a five-way switch.
+template <int TR>
+AW_HD double transform_fwd_t(double x, double exp_scale, double exp_divisor) {
+    return TR < 0 ? x : transform_fwd(x, TR, exp_scale, exp_divisor);
+}
 AW_HD double transform_inv(double x, int t, double exp_scale, double exp_divisor) {
     switch (t) {
         case T_SQUARE: return sqrt(x > 0.0 ? x : 0.0);

@@ -164,3 +164,55 @@ def test_f32_marginals_rows_kernel(H, W, transform):
     rpy = a.sum(2) / np.maximum(a.sum(2).sum(1, keepdims=True), 1e-6)
     assert np.abs(px.cpu().numpy() - rpx).max() <= 1e-5 * rpx.max() + 1e-9
     assert np.abs(py.cpu().numpy() - rpy).max() <= 1e-5 * rpy.max() + 1e-9
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32", "f64"])
+@pytest.mark.parametrize("transform", ["identity", "square", "sqrt", "exp", "log"])
+@pytest.mark.parametrize("H,W", [(48, 336), (37, 203)])
+def test_marginals_every_transform_and_dtype(dtype, transform, H, W):
+    """The marginals kernels are instantiated once per transform (float32 / float64 maps) and uint8 maps go
+    through a 256-entry table of the transformed values: every (dtype, transform) pair, on rows the row-owning
+    kernels take (W = 336) and on rows only the generic kernel takes (W = 203), against the float64 oracle
+    (new_method.py:207-216 with the registry of :133-188)."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(H * 7 + W + len(transform))
+    B = 2
+    if dtype == "u8":
+        att = rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+        att[1, :, : W // 2] = 0
+    else:
+        att = (rng.random((B, H, W)) ** 3).astype(np.float32 if dtype == "f32" else np.float64)
+        att[1] -= 0.2                                      # negatives are clamped
+    # exp of byte values needs a scale that keeps float64 finite and the profile non-degenerate
+    es, ed = (0.02, 3.0) if dtype == "u8" else (2.0, 3.0)
+    Ho, Wo = H + 3, W + 5
+    mx, my = ops.maps_from_attention(dev(att), (Ho, Wo), transform, es, ed)
+    for b in range(B):
+        _, rx, ry = ON.warp_image_by_attention(np.zeros((H, W, 3), np.uint8), att[b], Wo, Ho, transform, es, ed,
+                                               return_maps=True)
+        assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4
+
+
+@pytest.mark.parametrize("transform", ["sqrt", "square", "identity"])
+def test_f32_marginals_extreme_values(transform):
+    """The float32-pair evaluation of sqrt / square (profiles.cu: sqrt_pair) on the inputs that leave its
+    fast path: zeros, denormals, values below 1e-27, large finite values -- maps still match the float64 oracle."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(11)
+    H, W = 40, 336
+    att = (rng.random((3, H, W)) ** 3).astype(np.float32)
+    att[0, ::3, ::5] = 0.0
+    att[0, 1::7, 2::11] = 1e-40            # denormal
+    att[0, 2::7, 3::11] = 3e-30            # normal, below the fast path's range
+    att[1] *= 1e-20                        # a whole map of tiny values (sqrt ~1e-10, square underflows to ~0)
+    att[2] *= 1e15 if transform == "square" else 1e30
+    Ho, Wo = H + 5, W + 7
+    mx, my = ops.maps_from_attention(dev(att), (Ho, Wo), transform)
+    for b in range(3):
+        _, rx, ry = ON.warp_image_by_attention(np.zeros((H, W, 3), np.uint8), att[b], Wo, Ho, transform,
+                                               return_maps=True)
+        assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
+        assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4

@@ -186,3 +186,64 @@ def test_quad_kernel_mappings_agree(H, W, Ho, Wo, monkeypatch):
         from oracle import numpy_path as ON
         ref = ON.remap_u8(img[0].cpu().numpy(), mx[0].cpu().numpy(), my[0].cpu().numpy())
         assert np.array_equal(outs["0"][0].cpu().numpy(), ref)
+
+
+def _maps_family(rng, kind, n_out, n_in, B):
+    """Separable map rows of one family: attention-like (monotone, near the identity), random monotone, unsorted,
+    strongly shrinking, constant / out of range."""
+    rows = []
+    for _ in range(B):
+        if kind == "near_identity":
+            m = np.linspace(0, n_in - 1, n_out) + rng.normal(0, 0.4, n_out)
+        elif kind == "monotone":
+            m = np.sort(rng.random(n_out) * n_in)
+        elif kind == "unsorted":
+            m = rng.random(n_out) * (n_in + 4) - 2
+        elif kind == "shrink":
+            m = np.sort(rng.random(n_out)) ** 3 * n_in
+        else:
+            m = np.concatenate([np.full(n_out // 2, -3.0), np.full(n_out - n_out // 2, n_in + 2.5)])
+        rows.append(m.astype(np.float32))
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("kind", ["near_identity", "monotone", "unsorted", "shrink", "out_of_range"])
+@pytest.mark.parametrize("C,layout", [(1, "hwc"), (4, "hwc"), (3, "chw"), (2, "chw"), (4, "chw")])
+@pytest.mark.parametrize("H,W,Ho,Wo", [(61, 64, 70, 64), (45, 336, 129, 500), (33, 203, 40, 131), (130, 8, 67, 4)])
+def test_walk_kernel_formats(kind, C, layout, H, W, Ho, Wo):
+    """Grey, 4-channel and planar uint8 images (remap_stream.cu; written for the column-walking kernel of
+    profiles/r06_walk_kernel.md, which passed it too): bit-equal to the cv2.remap restatement for every map family,
+    with word-aligned and odd pitches on both sides, tall outputs and border rows."""
+    need_gpu()
+    rng = np.random.default_rng(H * 131 + W * 7 + C)
+    B = 2
+    img = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    _check(img, _maps_family(rng, kind, Wo, W, B), _maps_family(rng, kind, Ho, H, B), layout)
+
+
+@pytest.mark.parametrize("C,layout", [(1, "hwc"), (4, "hwc"), (3, "chw")])
+@pytest.mark.parametrize("src_off,dst_off", [(0, 1), (1, 0), (2, 3), (4, 4)])
+def test_walk_kernel_misaligned_bases(C, layout, src_off, dst_off):
+    """Views with non-zero storage offsets: source and destination bases at every phase of a 32-bit word."""
+    need_gpu()
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(C * 17 + src_off * 5 + dst_off)
+    B, H, W, Ho, Wo = 2, 50, 64, 70, 72
+    img = rng.integers(0, 256, (B, H, W, C), dtype=np.uint8)
+    mx = _maps_family(rng, "monotone", Wo, W, B)
+    my = _maps_family(rng, "near_identity", Ho, H, B)
+    arr = img if layout == "hwc" else np.ascontiguousarray(np.transpose(img, (0, 3, 1, 2)))
+    flat = torch.zeros(arr.size + src_off, dtype=torch.uint8, device="cuda")
+    flat[src_off:] = torch.from_numpy(arr).cuda().reshape(-1)
+    src = flat[src_off:].view(arr.shape)
+    oshape = (B, Ho, Wo, C) if layout == "hwc" else (B, C, Ho, Wo)
+    oflat = torch.full((int(np.prod(oshape)) + dst_off + 8,), 0xAB, dtype=torch.uint8, device="cuda")
+    out = oflat[dst_off:dst_off + int(np.prod(oshape))].view(oshape)
+    ops.remap_bilinear(src, dev(mx), dev(my), layout, out=out)
+    got = out.cpu().numpy()
+    if layout == "chw":
+        got = np.transpose(got, (0, 2, 3, 1))
+    for b in range(B):
+        assert np.array_equal(got[b], hwc(ON.remap(img[b] if C > 1 else img[b][..., 0], mx[b], my[b])))
+    # nothing written outside the destination view
+    assert bool((oflat[:dst_off] == 0xAB).all()) and bool((oflat[dst_off + int(np.prod(oshape)):] == 0xAB).all())
