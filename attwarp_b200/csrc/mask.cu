@@ -13,6 +13,7 @@
 // Everything here is a few hundred KB per batch: one CTA per image (revise) / per tile of output rows
 // (resize, the horizontal pass of the token rows recomputed per CTA into shared memory).
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -147,7 +148,8 @@ __device__ __forceinline__ uint32_t clip8(int acc) { return (uint32_t)clampi(acc
 // sums per (tile, row group) chunk in colpart[b][chunk][Wo], whole row sums in rowpart[b][0][Ho], each with the
 // + 1e-9 per element of new_method.py:212 added as count x 1e-9 -- for maps_from_partials_kernel to finish.  All
 // sums are exact integers (<= 255 x 65535), whatever the order the threads add them in.
-// Measured (profiles/r03d_row_kernels.txt): this saves the B x H x W buffer, not time -- the resize is bound by the
+// Measured (profiles/r03d_row_kernels.txt), for THIS kernel (resize_lanczos_up_mma_kernel below replaced it wherever
+// its geometry fits, and there the fusion does save time): this saves the B x H x W buffer, not time -- the resize is bound by the
 // fma pipe, so the write it skips was free, and the sums cost about what the separate marginals kernel does
 // (256 x 336^2: 53.5 us fused vs 52.5 us in two steps; 64 x 1344^2: 188 vs 167 us).
 constexpr int kUpMaxThreads = 512;
@@ -273,6 +275,206 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
     }
 }
 
+// ---- the up-scaling case on the tensor cores -------------------------------------------------------------------
+// The vertical pass of an up-scaling IS a matrix product: out[y][x] = clip8((sum_k Wv[y][k] tmp[k][x] + 2^21) >> 22)
+// with Wv the [Ho x h] band matrix of 22-bit coefficients and tmp the [h x Wo] horizontal pass -- and the kernel above
+// spends 7 IMAD per output byte on it (bound by the fma pipe at a fifth of the HBM rate).  Integer MMA is exact, so
+// the product can go to the tensor cores bit for bit: a coefficient (|w| < 2^23) is split into three bytes
+// w = b0 + 2^8 b1 + 2^16 b2 (b0, b1 unsigned, b2 signed), three mma.sync.m16n8k16 (u8 x u8, u8 x u8, s8 x u8) give
+// exact int32 partial products (< 2^21 each) and d0 + (d1 << 8) + (d2 << 16) is Pillow's int32 accumulator
+// (two's-complement wrap-around cancels, the true sum fits).  K = 16 source rows: a tile of output rows taps at
+// most 16 of them (the launcher sizes the tiles so), all relative to the tile's first tapped row.
+//   CTA  = (tile of output rows) x (up to 8 strips of 64 columns), one warp per strip;
+//   tmpT [column][16] bytes: the horizontal pass of the tile's source rows, transposed, so that a B fragment
+//        (4 consecutive source rows of one column) is one aligned 32-bit shared load; a warp keeps its 8 B fragments
+//        (64 columns) in registers for the whole tile;
+//   Apl  [3][row][16] bytes: the byte planes of the coefficient band, an A fragment is two 32-bit loads per plane;
+//   the 8 column tiles of a strip interleave their columns (tile j holds columns 16 c + 2 j, + 1 of the strip) so
+//   that a thread ends up with 16 ADJACENT output bytes of rows g and g + 8: two 128-bit stores per 16 x 64 block.
+// Measured (profiles/r06h_row_kernels.txt, r06i ncu): 176 warp instructions per 16 x 64 block (24 IMMA, 62 shift-adds
+// of the Horner combination, 32 shifts, 16 saturating packs) instead of ~10 per byte; revise + resize 64 x 24^2 ->
+// 1344^2 127 -> 57 us, 256 x 24^2 -> 336^2 37 -> 28.5 us; with MARG the fused mask -> maps path 188 -> 78 us.  Issue
+// slots are 58 % busy (a third of the instructions are the per-CTA prologue), DRAM at 13 %: still not its output stream.
+constexpr int kMmaK = 16, kMmaStrip = 64, kMmaMaxWarps = 8;
+__device__ __forceinline__ void mma_u8u8(int (&d)[4], const uint32_t (&a)[2], uint32_t b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b));
+}
+__device__ __forceinline__ void mma_s8u8(int (&d)[4], const uint32_t (&a)[2], uint32_t b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b));
+}
+template <bool MARG>
+__device__ __forceinline__ void mma_write_row_sums(const int* rsum, int rows, int b, int y0, int Ho, int Wo, int x_base,
+                                                   int cols_cta, double* __restrict__ rowpart);
+// MARG (the fusion of llava.py:243-255 with new_method.py:215-216, as resize_lanczos_up_kernel<., true>): the mask is
+// not written; column sums go to colpart [b][row tile][Wo], row sums to rowpart [b][x CTA][Ho] (exact integers).
+template <bool MARG>
+__global__ void __launch_bounds__(kMmaMaxWarps * 32)
+resize_lanczos_up_mma_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, int Wo,
+                             const int2* __restrict__ bx, const int* __restrict__ kx, int ksx,
+                             const int2* __restrict__ by, const int* __restrict__ ky, int ksy,
+                             int rows_per_tile, uint8_t* __restrict__ dst, double* __restrict__ colpart,
+                             double* __restrict__ rowpart) {
+    extern __shared__ __align__(16) uint8_t sm_b[];
+    const int n_warps = blockDim.x >> 5, cols_cta = n_warps * kMmaStrip;
+    const int b = blockIdx.z;
+    const int x_base = blockIdx.x * cols_cta;
+    const int y0 = blockIdx.y * rows_per_tile, y1 = min(y0 + rows_per_tile, Ho);
+    const int r0 = by[y0].x;
+    const int nr = by[y1 - 1].x + by[y1 - 1].y - r0;     // source rows the tile taps: [r0, r0 + nr), nr <= 16
+    uint8_t* tmpT = sm_b;                                              // [cols_cta][16]
+    uint8_t* apl = tmpT + (size_t)cols_cta * kMmaK;                    // [3][rows_per_tile][16]
+    int* rsum = reinterpret_cast<int*>(apl + (size_t)3 * rows_per_tile * kMmaK);   // [rows_per_tile] (MARG)
+    uint8_t* in = reinterpret_cast<uint8_t*>(rsum + rows_per_tile);    // [nr][w]
+    const uint8_t* img = src + ((int64_t)b * h + r0) * w;
+    for (int i = threadIdx.x; i < nr * w; i += blockDim.x) in[i] = img[i];
+    for (int i = threadIdx.x; i < 3 * rows_per_tile * kMmaK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(apl)[i] = 0u;
+    if (MARG)
+        for (int i = threadIdx.x; i < rows_per_tile; i += blockDim.x) rsum[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (y1 - y0) * ksy; i += blockDim.x) {      // the coefficient band, byte planes
+        const int yy = i / ksy, t = i - yy * ksy;
+        const int2 bd = by[y0 + yy];
+        if (t < bd.y) {
+            const int wv = __ldg(ky + (int64_t)(y0 + yy) * ksy + t);
+            const int k = bd.x - r0 + t;
+            apl[(0 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)(wv & 0xff);
+            apl[(1 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)((wv >> 8) & 0xff);
+            apl[(2 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)((wv >> 16) & 0xff);
+        }
+    }
+    for (int xl = threadIdx.x; xl < cols_cta; xl += blockDim.x) {          // horizontal pass, column x, transposed
+        const int x = x_base + xl;
+        uint32_t packed[4] = {0u, 0u, 0u, 0u};
+        if (x < Wo) {
+            int k[kUpTaps];
+            const int c0 = bx[x].x;
+#pragma unroll
+            for (int t = 0; t < kUpTaps; ++t) k[t] = t < ksx ? __ldg(kx + (int64_t)x * ksx + t) : 0;
+#pragma unroll
+            for (int r = 0; r < kMmaK; ++r) {            // (unrolled: packed[] stays in registers)
+                if (r < nr) {
+                    int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll
+                    for (int t = 0; t < kUpTaps; ++t) acc += (int)in[r * w + min(c0 + t, w - 1)] * k[t];
+                    packed[r >> 2] |= clip8(acc) << (8 * (r & 3));
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(tmpT + (size_t)xl * kMmaK) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int xs = x_base + wid * kMmaStrip;             // the warp's strip of 64 columns
+    if (!MARG && xs >= Wo) return;
+    if (xs < Wo) {
+    uint32_t bf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int xl = wid * kMmaStrip + 16 * (g >> 1) + 2 * j + (g & 1);
+        bf[j] = *reinterpret_cast<const uint32_t*>(tmpT + (size_t)xl * kMmaK + 4 * tig);
+    }
+    const bool store_ok = xs + 16 * tig < Wo;            // Wo is a multiple of 16: whole 16-byte groups
+    uint8_t* out = MARG ? nullptr : dst + ((int64_t)b * Ho + y0) * Wo + xs + 16 * tig;
+    // MARG: column sums of the thread's 16 columns over its rows, two columns per register (16-bit lanes:
+    // <= 2 rows x 32 blocks x 255); csum[2 m] = columns 4 m, 4 m + 2, csum[2 m + 1] = columns 4 m + 1, 4 m + 3
+    uint32_t csum[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (int m0 = 0; m0 < y1 - y0; m0 += 16) {
+        uint32_t a[3][2];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            a[p][0] = *reinterpret_cast<const uint32_t*>(apl + ((size_t)p * rows_per_tile + m0 + g) * kMmaK + 4 * tig);
+            a[p][1] = *reinterpret_cast<const uint32_t*>(apl + ((size_t)p * rows_per_tile + m0 + g + 8) * kMmaK + 4 * tig);
+        }
+        uint32_t lo[4], hi[4];                           // 16 bytes of row m0 + g, of row m0 + g + 8
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            int v[2][4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                // Horner over the byte planes: ((A2 B) 2^8 + A1 B) 2^8 + A0 B + 2^21, the accumulator chained through
+                // the three MMAs (int32 wrap-around as in the flat sum)
+                int d[4] = {0, 0, 0, 0};
+                mma_s8u8(d, a[2], bf[2 * jj + q]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = (int)((uint32_t)d[i] << 8);
+                mma_u8u8(d, a[1], bf[2 * jj + q]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = (int)(((uint32_t)d[i] << 8) + (1u << (kPrecisionBits - 1)));
+                mma_u8u8(d, a[0], bf[2 * jj + q]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[q][i] = d[i] >> kPrecisionBits;
+            }
+            // cvt.pack saturates two int32 to uint8 and packs them under the previous pair: bytes 4 jj .. 4 jj + 3
+            uint32_t t;
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v[1][1]), "r"(v[1][0]), "r"(0));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo[jj]) : "r"(v[0][1]), "r"(v[0][0]), "r"(t));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v[1][3]), "r"(v[1][2]), "r"(0));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi[jj]) : "r"(v[0][3]), "r"(v[0][2]), "r"(t));
+        }
+        if (MARG) {
+            // rows past the tile's end have zero coefficients: their bytes are 0 and add nothing
+            uint32_t rlo = 0u, rhi = 0u;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                rlo = __dp4a(lo[m], 0x01010101u, rlo);
+                rhi = __dp4a(hi[m], 0x01010101u, rhi);
+                csum[2 * m] += (lo[m] & 0x00ff00ffu) + (hi[m] & 0x00ff00ffu);
+                csum[2 * m + 1] += ((lo[m] >> 8) & 0x00ff00ffu) + ((hi[m] >> 8) & 0x00ff00ffu);
+            }
+            rlo += __shfl_xor_sync(0xffffffffu, rlo, 1);
+            rhi += __shfl_xor_sync(0xffffffffu, rhi, 1);
+            rlo += __shfl_xor_sync(0xffffffffu, rlo, 2);
+            rhi += __shfl_xor_sync(0xffffffffu, rhi, 2);
+            if (tig == 0) {
+                atomicAdd(&rsum[m0 + g], (int)rlo);
+                atomicAdd(&rsum[m0 + g + 8], (int)rhi);
+            }
+        } else if (store_ok) {
+            if (m0 + g < y1 - y0)
+                *reinterpret_cast<uint4*>(out + (int64_t)(m0 + g) * Wo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (m0 + g + 8 < y1 - y0)
+                *reinterpret_cast<uint4*>(out + (int64_t)(m0 + g + 8) * Wo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
+    }
+    if (MARG) {
+        // column sums: add up the 8 row groups g (lanes 4 apart hold the same columns), then lanes g == 0 write their
+        // 16 columns of this tile's chunk; the + 1e-9 per element of new_method.py:212 is added as count x 1e-9
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            uint32_t lo16 = csum[m] & 0xffffu, hi16 = csum[m] >> 16;
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1) {
+                lo16 += __shfl_xor_sync(0xffffffffu, lo16, d);
+                hi16 += __shfl_xor_sync(0xffffffffu, hi16, d);
+            }
+            if (g == 0) {
+                double* cp = colpart + ((int64_t)b * gridDim.y + blockIdx.y) * Wo;
+                const double base = (double)(y1 - y0) * kBaseAttention;
+                const int c = xs + 16 * tig + 4 * (m >> 1) + (m & 1);       // and c + 2
+                if (c < Wo) cp[c] = (double)lo16 + base;
+                if (c + 2 < Wo) cp[c + 2] = (double)hi16 + base;
+            }
+        }
+    }
+    }   // xs < Wo
+    if (MARG) {
+        __syncthreads();
+        mma_write_row_sums<MARG>(rsum, y1 - y0, b, y0, Ho, Wo, x_base, cols_cta, rowpart);
+    }
+}
+// MARG: the row sums of the CTA's columns, one partial per CTA column (rowpart [b][x CTA][Ho])
+template <bool MARG>
+__device__ __forceinline__ void mma_write_row_sums(const int* rsum, int rows, int b, int y0, int Ho, int Wo, int x_base,
+                                                   int cols_cta, double* __restrict__ rowpart) {
+    if (!MARG) return;
+    const int cols = min(cols_cta, Wo - x_base);
+    const double row_base = (double)cols * kBaseAttention;
+    double* rp = rowpart + ((int64_t)b * gridDim.x + blockIdx.x) * Ho + y0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) rp[i] = (double)rsum[i] + row_base;
+}
+
 // ---- coefficient tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc, Lanczos, support 3) ----
 double sinc_filter(double x) {
     if (x == 0.0) return 1.0;
@@ -375,9 +577,75 @@ static UpGeometry up_geometry(int B, int h, int w, int Ho, int Wo) {
     return g;
 }
 
-// Partial-sum chunks per image the fused kernel writes (0: this resize is not taken by the fused kernel).
-int lanczos_marginals_chunks(int B, int h, int w, int H, int W) {
+// Pillow's window of output coordinate xx (Resample.c precompute_coeffs, as build_table above): first tap, taps.
+static void tap_window(int in_size, int out_size, int xx, int* first, int* count) {
+    const double scale = (double)in_size / (double)out_size;
+    const double fscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 3.0 * fscale;
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    *first = xmin;
+    *count = xmax - xmin;
+}
+
+// Launch geometry of the tensor-core up-scaling kernel: strips of 64 columns, one warp each, up to 8 per CTA; tiles
+// of `rows` output rows (a multiple of 16) that tap at most 16 source rows; enough CTAs to fill the GPU a few times.
+struct MmaGeometry { bool ok; int x_ctas, warps, rows, n_tiles; size_t smem; };
+static MmaGeometry mma_geometry(int B, int h, int w, int Ho, int Wo, const uint8_t* dst, bool marg) {
+    MmaGeometry g{};
+    if (w > 1024 || B > 65535) return g;
+    // the mask is stored in 16-byte groups; the marginals variant stores nothing and takes any width
+    if (!marg && ((Wo & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)) return g;
+    const int strips = (Wo + kMmaStrip - 1) / kMmaStrip;
+    g.x_ctas = (strips + kMmaMaxWarps - 1) / kMmaMaxWarps;
+    g.warps = (strips + g.x_ctas - 1) / g.x_ctas;
+    int want_tiles = (4 * sm_count() + B * g.x_ctas - 1) / (B * g.x_ctas);
+    if (want_tiles < 1) want_tiles = 1;
+    int rows = ((Ho + want_tiles - 1) / want_tiles + 15) & ~15;
+    if (rows < 32) rows = 32;
+    if (rows > 512) rows = 512;
+    for (; rows >= 16; rows -= 16) {                     // the tallest tile whose rows tap <= 16 source rows
+        bool fits = true;
+        for (int y0 = 0; y0 < Ho && fits; y0 += rows) {
+            const int y1 = (y0 + rows < Ho ? y0 + rows : Ho) - 1;
+            int f0, c0, f1, c1;
+            tap_window(h, Ho, y0, &f0, &c0);
+            tap_window(h, Ho, y1, &f1, &c1);
+            fits = f1 + c1 - f0 <= kMmaK;
+        }
+        if (fits) break;
+    }
+    if (rows < 16) return g;
+    g.rows = rows;
+    g.n_tiles = (Ho + rows - 1) / rows;
+    if (g.n_tiles > 65535) return g;
+    g.smem = (size_t)g.warps * kMmaStrip * kMmaK + (size_t)3 * rows * kMmaK + (size_t)rows * 4 + (((size_t)kMmaK * w + 15) & ~(size_t)15);
+    g.ok = g.smem <= 160 * 1024;
+    return g;
+}
+static bool lanczos_mma_enabled() {
+    static const bool v = [] {
+        const char* e = getenv("ATTWARP_LANCZOS_MMA");
+        return e == nullptr || e[0] != '0';
+    }();
+    return v;
+}
+
+// Partial sums per image the fused kernel writes: column-sum chunks (0: this resize is not taken by the fused kernel)
+// and row-sum partials (column tiles).  The tensor-core kernel when its geometry fits, else the register-window one.
+int lanczos_marginals_chunks(int B, int h, int w, int H, int W, int* n_col_tiles) {
+    *n_col_tiles = 1;
     if (H <= h || W <= w || h > 0xffff || w > 0xffff) return 0;
+    if (lanczos_mma_enabled()) {
+        const MmaGeometry mg = mma_geometry(B, h, w, H, W, nullptr, true);
+        if (mg.ok) {
+            *n_col_tiles = mg.x_ctas;
+            return mg.n_tiles;
+        }
+    }
     // pure up-scaling: 3 * 2 + 1 = 7 taps per axis
     const UpGeometry g = up_geometry(B, h, w, H, W);
     return g.ok ? g.n_tiles * g.n_rg : 0;
@@ -386,7 +654,27 @@ int lanczos_marginals_chunks(int B, int h, int w, int H, int W) {
 // mask_u8 [B][h][w] (revise_mask's uint8 output) -> marginal partial sums of its LANCZOS resize to H x W, which is
 // never written: colpart [B][chunks][W], rowpart [B][1][H].
 int launch_lanczos_marginals(const uint8_t* src, int B, int h, int w, int H, int W, double* colpart, double* rowpart,
-                             int* n_chunks, cudaStream_t st) {
+                             int* n_chunks, int* n_col_tiles, cudaStream_t st) {
+    *n_col_tiles = 1;
+    if (H > h && W > w && lanczos_mma_enabled()) {
+        const MmaGeometry mg = mma_geometry(B, h, w, H, W, nullptr, true);
+        CoeffTable tx, ty;
+        if (mg.ok) {
+            int rc = get_table(w, W, &tx);
+            if (rc != ATTWARP_OK) return rc;
+            rc = get_table(h, H, &ty);
+            if (rc != ATTWARP_OK) return rc;
+        }
+        if (mg.ok && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps) {
+            if (mg.smem > 48 * 1024)
+                AW_CUDA(cudaFuncSetAttribute(resize_lanczos_up_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.smem));
+            resize_lanczos_up_mma_kernel<true><<<dim3(mg.x_ctas, mg.n_tiles, B), mg.warps * 32, mg.smem, st>>>(
+                src, h, w, H, W, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, mg.rows, nullptr, colpart, rowpart);
+            *n_chunks = mg.n_tiles;
+            *n_col_tiles = mg.x_ctas;
+            return check_launch("resize_lanczos_up_mma_kernel<marginals>");
+        }
+    }
     const UpGeometry ug = up_geometry(B, h, w, H, W);
     if (H <= h || W <= w || !ug.ok)
         return fail(ATTWARP_ERR_UNSUPPORTED, "lanczos_marginals: %dx%d -> %dx%d is not an up-scaling that fits shared memory", h, w, H, W);
@@ -415,6 +703,17 @@ int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, in
     if (Ho != h) {
         const int rc = get_table(h, Ho, &ty);
         if (rc != ATTWARP_OK) return rc;
+    }
+    // pure up-scaling of both axes (7 taps), 16-byte aligned output rows: the vertical pass on the tensor cores
+    if (Wo > w && Ho > h && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps && lanczos_mma_enabled()) {
+        const MmaGeometry mg = mma_geometry(B, h, w, Ho, Wo, dst, false);
+        if (mg.ok) {
+            if (mg.smem > 48 * 1024)
+                AW_CUDA(cudaFuncSetAttribute(resize_lanczos_up_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.smem));
+            resize_lanczos_up_mma_kernel<false><<<dim3(mg.x_ctas, mg.n_tiles, B), mg.warps * 32, mg.smem, st>>>(
+                src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, mg.rows, dst, nullptr, nullptr);
+            return check_launch("resize_lanczos_up_mma_kernel");
+        }
     }
     // up-scaling (or any resize with <= 8 taps per axis) of both axes: the register-window kernel
     const UpGeometry ug = up_geometry(B, h, w, Ho, Wo);

@@ -759,12 +759,13 @@ int launch_maps_from_attention(const void* att, int att_dtype, int B, int H, int
 
 // (P2d) maps from the token-grid mask of the driver flow, its LANCZOS resize to image size never written
 // (mask.cu, resize_lanczos_up_kernel<.., MARG>), identity transform only (sums of bytes stay exact integers).
-int lanczos_marginals_chunks(int B, int h, int w, int H, int W);
+int lanczos_marginals_chunks(int B, int h, int w, int H, int W, int* n_col_tiles);
 int launch_lanczos_marginals(const uint8_t* src, int B, int h, int w, int H, int W, double* colpart, double* rowpart,
-                             int* n_chunks, cudaStream_t st);
+                             int* n_chunks, int* n_col_tiles, cudaStream_t st);
 size_t maps_from_mask_workspace_bytes_impl(int B, int h, int w, int H, int W) {
-    const int chunks = lanczos_marginals_chunks(B, h, w, H, W);
-    return chunks == 0 ? 0 : sizeof(double) * (size_t)B * ((size_t)chunks * W + (size_t)H);
+    int nct = 1;
+    const int chunks = lanczos_marginals_chunks(B, h, w, H, W, &nct);
+    return chunks == 0 ? 0 : sizeof(double) * (size_t)B * ((size_t)chunks * W + (size_t)nct * H);
 }
 int launch_maps_from_mask(const uint8_t* mask, int B, int h, int w, int H, int W, int Wo, int Ho,
                           const attwarp_transform_params& tp, void* ws, size_t ws_bytes, float* map_x, float* map_y,
@@ -774,16 +775,17 @@ int launch_maps_from_mask(const uint8_t* mask, int B, int h, int w, int H, int W
     const size_t need = maps_from_mask_workspace_bytes_impl(B, h, w, H, W);
     if (need == 0) return fail(ATTWARP_ERR_UNSUPPORTED, "maps_from_mask: %dx%d -> %dx%d is not an up-scaling the fused kernel takes", h, w, H, W);
     if (ws == nullptr || ws_bytes < need) return fail(ATTWARP_ERR_WORKSPACE, "maps_from_mask: workspace too small (%zu < %zu)", ws_bytes, need);
-    int chunks = lanczos_marginals_chunks(B, h, w, H, W);
+    int nct = 1;
+    int chunks = lanczos_marginals_chunks(B, h, w, H, W, &nct);
     double* colpart = static_cast<double*>(ws);
     double* rowpart = colpart + (size_t)B * chunks * W;
-    int rc = launch_lanczos_marginals(mask, B, h, w, H, W, colpart, rowpart, &chunks, st);
+    int rc = launch_lanczos_marginals(mask, B, h, w, H, W, colpart, rowpart, &chunks, &nct, st);
     if (rc != ATTWARP_OK) return rc;
     const TransformArgs ta = to_args(tp);
     const size_t smem = maps_smem_bytes(0, H, W);
     rc = opt_in_smem(maps_from_partials_kernel, smem, "maps_from_mask");
     if (rc != ATTWARP_OK) return rc;
-    maps_from_partials_kernel<<<B, 2 * kProfThreads, smem, st>>>(colpart, rowpart, chunks, 1, H, W, Wo, Ho, ta, map_x,
+    maps_from_partials_kernel<<<B, 2 * kProfThreads, smem, st>>>(colpart, rowpart, chunks, nct, H, W, Wo, Ho, ta, map_x,
                                                              map_y, nullptr);
     return check_launch("maps_from_partials_kernel");
 }
