@@ -88,6 +88,36 @@ def test_gpu_lanczos_vs_pillow_batched():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,w,Ho,Wo", [(24, 24, 336, 336), (48, 48, 1344, 1344), (24, 32, 333, 512), (7, 5, 50, 16),
+                                       (59, 60, 61, 64), (2, 2, 700, 1008), (24, 24, 2048, 224), (1, 3, 17, 48),
+                                       (33, 9, 1000, 80), (24, 24, 336, 2000)])
+def test_gpu_lanczos_tensor_core_path(h, w, Ho, Wo):
+    """Up-scalings with 16-byte output rows take the tensor-core kernel (mask.cu: resize_lanczos_up_mma_kernel:
+    byte-split coefficients, three chained integer MMAs per block): bit-equal to PIL for token grids of any shape,
+    tall and wide outputs, extreme ratios (tiles that tap 16 source rows / one source row), saturated inputs (ringing
+    clipped at both ends), row counts that are not multiples of 16 and more than 8 strips of columns."""
+    _need_gpu()
+    from PIL import Image
+    from attwarp_b200 import ops
+    rng = np.random.default_rng(h * 1000 + Wo)
+    m = rng.integers(0, 256, (3, h, w), dtype=np.uint8)
+    m[1] = np.where(rng.random((h, w)) < 0.5, 0, 255)          # hard edges: over- and undershoot
+    m[2] = 255
+    got = ops.resize_lanczos_u8(torch.from_numpy(m).cuda(), (Ho, Wo)).cpu().numpy()
+    for b in range(3):
+        ref = np.array(Image.fromarray(m[b], mode="L").resize((Wo, Ho), Image.LANCZOS))
+        assert np.array_equal(got[b], ref), (h, w, Ho, Wo, b, int(np.abs(got[b].astype(int) - ref.astype(int)).max()))
+    # the fused marginals of the same resize (nothing written) against sums of the written mask
+    if h >= 2 and w >= 2:
+        tok = torch.from_numpy(rng.random((3, h, w)).astype(np.float32)).cuda()
+        a = ops.maps_from_mota_tokens(tok, (Ho, Wo), (Ho, Wo), fused=True)
+        b_ = ops.maps_from_mota_tokens(tok, (Ho, Wo), (Ho, Wo), fused=False)
+        for x, y in zip(a, b_):
+            ulp = np.abs(x.cpu().numpy().view(np.int32).astype(np.int64) - y.cpu().numpy().view(np.int32).astype(np.int64))
+            assert ulp.max() <= 1, int(ulp.max())
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,out_hw", [("c1_336", (500, 500)), ("c1_336", (336, 336)), ("wide_500x333", (500, 500)),
                                          ("big_1344", (1344, 1344))])
 def test_gpu_c1_driver_chain(gm, name, out_hw, record_property):
