@@ -27,7 +27,7 @@ for line in sass.splitlines():
     if m and cur:
         kernels[cur][m.group(1)] += 1
 
-KEYS = ["UBLKCP", "SYNCS", "IDP.4A", "IDP.2A", "IMAD", "PRMT", "SHF", "LOP3", "FFMA2", "FADD2", "FMUL2", "DFMA", "DADD",
+KEYS = ["UBLKCP", "SYNCS", "IMMA", "IDP.4A", "IDP.2A", "IMAD", "PRMT", "SHF", "LOP3", "FFMA2", "FADD2", "FMUL2", "DFMA", "DADD",
         "DMUL", "LDS", "STS", "STS.U8", "LDG", "STG", "SHFL", "REDUX", "BAR", "BRA"]
 
 
@@ -39,7 +39,7 @@ def family(counter, key):
 
 print("# SASS opcode histogram per kernel (`cuobjdump -sass attwarp_b200/libattwarp_sm100.so`)\n")
 print("Static instruction counts (not executed counts).  `UBLKCP` = cp.async.bulk (TMA bulk copy), `SYNCS` = mbarrier, "
-      "`IDP` = dp4a/dp2a.\n")
+      "`IDP` = dp4a/dp2a, `IMMA` = integer mma.sync (the LANCZOS vertical pass).\n")
 print("| kernel | total | " + " | ".join(KEYS) + " |")
 print("|---|---:|" + "---:|" * len(KEYS))
 for name, c in kernels.items():
