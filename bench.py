@@ -603,6 +603,24 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
                               "frac": step_bytes / (worst_ms / args.steps) / 1e6 / ctx.peak,
                               "note": f"all kernels of a step, {n_streams} steps in flight"}
 
+    # ---- the reference drivers' flow at this size (a labelled extra, not the headline): token map -> revise_mask ->
+    # Pillow-exact LANCZOS mask at image size + its marginals (one kernel, vertical pass on the tensor cores, the mask
+    # never written) -> maps -> stage 5; "Attention Guided Warping/main.py":361 -> 520.  Device-resident, graph replay.
+    driver_flow = None
+    try:
+        ms_maps = back_to_back(lambda s: ops.maps_from_mota_tokens(tokmap(s), side_hw))
+
+        def flow_step(s):
+            mx_, my_ = ops.maps_from_mota_tokens(tokmap(s), side_hw)
+            ops.remap_bilinear(s["img"], mx_, my_, "hwc", out=s["out"])
+        ms_flow = back_to_back(flow_step)
+        driver_flow = {"what": "tokens -> revise_mask -> LANCZOS mask + marginals (fused) -> maps -> resample, "
+                               "one batch at a time on one stream",
+                       "maps_from_mota_tokens_ms": ms_maps, "step_ms": ms_flow, "images_per_s": B / ms_flow * 1e3,
+                       "how": how}
+    except Exception as e:                                   # an extra must never cost the headline
+        driver_flow = {"error": repr(e)[:200]}
+
     # ---- e2e: pinned host buffers -> H2D -> kernels -> D2H, per step -----------------------------
     e2e = None
     if not args.no_e2e:
@@ -678,6 +696,7 @@ def bench_uniform(ctx, wl_key, with_clocks=True):
 
     res = {"value": value, "ms_per_step": worst_ms / args.steps, "per_rank_ms": [s[0] for s in stats],
            "launches": launches * world, "kernels": kernels, "roofline": roofline, "e2e": e2e, "clocks": clocks,
+           "driver_flow": driver_flow,
            "sustained": {"steps": sus_steps, "ms_per_step": max(s[0] for s in sus_stats) / sus_steps,
                          "value": sharding.aggregate_throughput(sus_stats)},
            "single_stream": {"ms_per_step": max(s[0] for s in one_stats) / max(args.steps, 20),
@@ -925,7 +944,7 @@ def run_gpu(args, rank, local_rank, world):
                      "scaling": "strong" if key == "c4" else "weak", "dtype": DTYPES[key],
                      "config": workload_config(key, world), "roofline": r["roofline"], "e2e": r["e2e"],
                      "per_rank_ms": r["per_rank_ms"], "gpu_launches": r["launches"], "run": r["run"]}
-            for k in ("kernels", "sustained", "single_stream", "images_per_rank", "shard_imbalance", "check", "steps"):
+            for k in ("kernels", "sustained", "single_stream", "driver_flow", "images_per_rank", "shard_imbalance", "check", "steps"):
                 if k in r:
                     entry[k] = r[k]
             extra[key] = entry
@@ -940,7 +959,7 @@ def run_gpu(args, rank, local_rank, world):
             "dtype": DTYPES[head_key], "data": "synthetic", "config": workload_config(head_key, world),
             "run": head["run"], "clocks": head.get("clocks"), "e2e": head["e2e"], "gpu_launches": head["launches"],
             "roofline": head["roofline"], "cpu_baseline": cpu_info, "per_rank_ms": head["per_rank_ms"]}
-    for k in ("kernels", "sustained", "single_stream", "images_per_rank", "shard_imbalance", "check"):
+    for k in ("kernels", "sustained", "single_stream", "driver_flow", "images_per_rank", "shard_imbalance", "check"):
         if k in head:
             line[k] = head[k]
     if extra:
