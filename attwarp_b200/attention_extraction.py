@@ -18,9 +18,15 @@ fp32 in the kernel (the reference divides in the tensor's dtype; see SURVEY.md s
 
 from __future__ import annotations
 
+import ctypes as _C
+import os as _os
+
 import torch
 
-from . import ops
+from . import _lib, ops
+
+# ATTWARP_HOOK_FAST=0 sends every hooked step through ops.aggregate_attention (A/B of the host-side cost)
+_HOOK_FAST = _os.environ.get("ATTWARP_HOOK_FAST", "1") != "0"
 
 
 class _RunningAttention:
@@ -31,6 +37,7 @@ class _RunningAttention:
         self.steps = 0
         self._starts_key = None          # (device, tuple of starts) of the cached offset tensor
         self._starts = None
+        self._fast = None                # (layout key, starts, ends, prepared C call) of the previous step
 
     def _start_tensor(self, starts, device):
         """int32 device tensor of the per-sample offsets, rebuilt only when they change: generate() calls
@@ -43,6 +50,19 @@ class _RunningAttention:
         return self._starts
 
     def add_step(self, attn_weights: torch.Tensor, starts, ends):
+        # generate() calls the hook once per layer and decoding step with the same layout and token ranges: after the
+        # first step of a layout the validated arguments are kept and a step is one C call: the hook is bound by its
+        # host side (slicing, checks, tensor conversions, device guard), 42-45 -> 24-25 us per hooked step
+        # (profiles/r08d_hook_overhead.txt)
+        fast = self._fast
+        if fast is not None and type(starts) is list and type(ends) is list:
+            shape = attn_weights.shape           # [B, Hh, q, kv]: q and kv change from step to step (KV cache)
+            if (fast[0] == (shape[0], shape[1], attn_weights.dtype, attn_weights.device) and shape[3] >= fast[4]
+                    and fast[1] == starts and fast[2] == ends and attn_weights.stride(3) == 1):
+                fast[3](attn_weights)
+                self.steps += 1
+                return
+        self._fast = None
         B, Hh, q, kv = attn_weights.shape
         starts = [int(s) for s in starts]
         ends = [min(int(e), kv) for e in ends]
@@ -68,6 +88,41 @@ class _RunningAttention:
         st = self._start_tensor(starts, rows.device)
         ops.aggregate_attention(rows, tok_start=st, num_tokens=T, out=self.sum, accumulate=True)
         self.steps += 1
+        if _HOOK_FAST and rows.data_ptr() == attn_weights.data_ptr() + (q - 1) * attn_weights.stride(2) * attn_weights.element_size():
+            # (the ranges as normalised above: a later step matches only if its raw ranges need no clipping)
+            self._fast = ((B, Hh, attn_weights.dtype, attn_weights.device), list(starts), list(ends),
+                          self._prepare(attn_weights, st, T), max(ends))
+
+    def _prepare(self, attn_weights, st, T):
+        """The C call of one more step on a ``[B, Hh, q, kv]`` tensor of this batch size, head count, dtype and
+        device (its data pointer, strides and last query row, the workspace of the current stream and the stream are
+        read per call; everything else is fixed)."""
+        lib = _lib.load()
+        fn = lib.attwarp_aggregate_attention
+        B, Hh = attn_weights.shape[0], attn_weights.shape[1]
+        dev = attn_weights.device
+        esize = attn_weights.element_size()
+        dtype_id = _lib.TORCH_DTYPE_IDS[attn_weights.dtype]
+        wsb = lib.attwarp_aggregate_workspace_bytes(B, 1, Hh, T)
+        st_ptr, sum_ptr = _C.c_void_p(st.data_ptr()), _C.c_void_p(self.sum.data_ptr())
+        keep = (st, self.sum)                                                         # the pointers above stay valid
+        dev_index = dev.index
+
+        def call(t):
+            s0, s1, s2, _ = t.stride()
+            row_off = (t.shape[2] - 1) * s2 * esize                                   # the last query row
+            ws = ops._workspace(wsb, dev)
+            stream = _C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if torch.cuda.current_device() == dev_index:
+                rc = fn(_C.c_void_p(t.data_ptr() + row_off), dtype_id, B, 1, Hh, T, s0, 0, s1, st_ptr, 1e-12,
+                        _C.c_void_p(ws.data_ptr()), ws.numel(), sum_ptr, 1, 1.0, stream)
+            else:
+                with torch.cuda.device(dev):
+                    rc = fn(_C.c_void_p(t.data_ptr() + row_off), dtype_id, B, 1, Hh, T, s0, 0, s1, st_ptr, 1e-12,
+                            _C.c_void_p(ws.data_ptr()), ws.numel(), sum_ptr, 1, 1.0, stream)
+            _lib.check(rc)
+            return keep
+        return call
 
     def mean(self):
         return self.sum / float(self.steps)

@@ -287,3 +287,43 @@ def test_pool_attention_prologue():
         assert rel_err(got, ref, floor=1e-6) <= 1e-5, (H, W)
         plain = cu.pool_attention(A.cuda(), None).cpu().numpy()
         assert rel_err(plain, torch.nn.functional.adaptive_avg_pool2d(A, (24, 24)).numpy(), floor=1e-6) <= 1e-4
+
+
+def test_hook_logger_prepared_call_with_growing_kv(monkeypatch):
+    """After the first step of a layout the hook reducer keeps a prepared C call (attention_extraction.py:
+    _RunningAttention._prepare).  Under generate() the tensor changes from step to step -- q = prompt length, then 1;
+    kv grows with the KV cache; the views are not contiguous -- so the prepared call reads strides and the last query
+    row per step: same result, bit for bit, as sending every step through ops.aggregate_attention, and equal to the
+    definition (llava.py:385-411) computed with torch."""
+    need_gpu()
+    from attwarp_b200 import attention_extraction as AE
+    gen = torch.Generator().manual_seed(5)
+    B, Hh, T = 3, 4, 576
+    starts, ends = [1, 7, 30], [577, 583, 606]
+    big = torch.softmax(torch.randn(B, Hh, 5, 700, generator=gen), -1).cuda().half()
+    steps = [big[:, :, :, :640]] + [big[:, :, 4 - (i % 3):5 - (i % 3), :641 + 3 * i] for i in range(9)]
+    results = []
+    for fast in (True, False):
+        monkeypatch.setattr(AE, "_HOOK_FAST", fast)
+        lg = AE.BatchMaskHookLogger(None, "cuda")
+        lg.set_batch_image_token_ranges(starts, ends)
+        for s in steps:
+            lg._process_attention(s)
+        assert (lg._acc._fast is not None) == fast
+        results.append(torch.stack([m.reshape(-1) for m in lg.finalize_batch()]))
+    assert torch.equal(results[0], results[1])
+    ref = torch.zeros(B, T, device="cuda")
+    for s in steps:
+        row = s[:, :, -1, :].float()
+        for b in range(B):
+            sl = row[b, :, starts[b]:ends[b]]
+            ref[b] += (sl / (sl.sum(-1, keepdim=True) + 1e-12)).mean(0)
+    ref /= len(steps)
+    assert rel_err(results[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+    # a change of batch size or of the ranges leaves the prepared call
+    lg = AE.MaskHookLogger(None, "cuda")
+    lg.set_image_token_range(1, 577)
+    lg._process_attention(big[:1, :, :, :640])
+    lg._process_attention(big[:1, :, -1:, :650])
+    with pytest.raises(ValueError):
+        lg._process_attention(big[:2, :, -1:, :650])          # running sum is [1, T]
