@@ -195,3 +195,32 @@ def test_gpu_maps_from_mota_tokens_fused(hw, out_hw):
     m = mask[0].cpu().numpy()
     ox, oy, _, _ = ON.inverse_maps(m, out_hw[1], out_hw[0], "identity")
     assert np.abs(got_x[0].cpu().numpy() - ox).max() <= 1e-3 and np.abs(got_y[0].cpu().numpy() - oy).max() <= 1e-3
+
+
+@pytest.mark.parametrize("h,Ho", [(24, 336), (48, 1344), (24, 1344), (2, 700), (59, 61), (33, 1000), (1, 17)])
+def test_byte_plane_horner_equals_the_int32_accumulator(h, Ho):
+    """Host check of the arithmetic behind mask.cu's tensor-core LANCZOS kernel: Pillow's 22-bit coefficients split
+    into three bytes (two unsigned, the top one signed and within int8), the three integer dot products chained with
+    8-bit shifts in wrapping int32 arithmetic, + 2^21 -- equal to Pillow's int32 accumulator for every output row, on
+    random and on worst-case (saturated, alternating) uint8 columns."""
+    from oracle import mask_path as OM
+    bounds, kk = OM.lanczos_coeffs(h, Ho)
+    rng = np.random.default_rng(h * 7 + Ho)
+    cols = rng.integers(0, 256, (h, 64), dtype=np.int64)
+    cols[:, 0], cols[:, 1] = 255, 0
+    cols[:, 2] = np.where(np.arange(h) % 2 == 0, 255, 0)          # worst-case ringing
+    for yy in range(Ho):
+        x0, n = int(bounds[yy][0]), int(bounds[yy][1])
+        w = kk[yy, :n].astype(np.int64)
+        assert np.abs(w).max() < (1 << 23)
+        b0, b1, b2 = w & 255, (w >> 8) & 255, w >> 16
+        assert b2.min() >= -128 and b2.max() <= 127
+        assert np.array_equal(b0 + 256 * b1 + 65536 * b2, w)
+        p = cols[x0:x0 + n]
+        ref = (1 << 21) + (p * w[:, None]).sum(0)                 # Resample.c: int accumulator from 1 << 21
+        assert np.abs(ref).max() < (1 << 31)
+        wrap = lambda v: ((v + (1 << 31)) % (1 << 32)) - (1 << 31)  # noqa: E731
+        d = wrap((p * b2[:, None]).sum(0))
+        d = wrap(wrap(d << 8) + (p * b1[:, None]).sum(0))
+        d = wrap(wrap(wrap(d << 8) + (1 << 21)) + (p * b0[:, None]).sum(0))
+        assert np.array_equal(d, ref)
