@@ -280,9 +280,11 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
 // with Wv the [Ho x h] band matrix of 22-bit coefficients and tmp the [h x Wo] horizontal pass -- and the kernel above
 // spends 7 IMAD per output byte on it (bound by the fma pipe at a fifth of the HBM rate).  Integer MMA is exact, so
 // the product can go to the tensor cores bit for bit: a coefficient (|w| < 2^23) is split into three bytes
-// w = b0 + 2^8 b1 + 2^16 b2 (b0, b1 unsigned, b2 signed), three mma.sync.m16n8k16 (u8 x u8, u8 x u8, s8 x u8) give
-// exact int32 partial products (< 2^21 each) and d0 + (d1 << 8) + (d2 << 16) is Pillow's int32 accumulator
-// (two's-complement wrap-around cancels, the true sum fits).  K = 16 source rows: a tile of output rows taps at
+// w = b0 + 2^8 b1 + 2^16 b2 (b0, b1 unsigned, b2 signed), three mma.sync.m16n8k16 (s8 x u8, u8 x u8, u8 x u8) give
+// exact int32 partial products (< 2^21 each), chained through the accumulator as ((A2 B << 8) + A1 B << 8) + 2^21 +
+// A0 B: Pillow's int32 accumulator (two's-complement wrap-around of the shifted parts cancels, the true sum fits;
+// tests/test_mask_path.py::test_byte_plane_horner_equals_the_int32_accumulator checks the arithmetic on the host).
+// K = 16 source rows: a tile of output rows taps at
 // most 16 of them (the launcher sizes the tiles so), all relative to the tile's first tapped row.
 //   CTA  = (tile of output rows) x (up to 8 strips of 64 columns), one warp per strip;
 //   tmpT [column][16] bytes: the horizontal pass of the tile's source rows, transposed, so that a B fragment

@@ -183,10 +183,11 @@ maps_from_tokens_kernel(const float* __restrict__ tok, int nsplit, float scale,
 //   memory (per-column-tile partials).  Both partial sets are summed in fixed order by the
 //   finish kernel -> deterministic.
 //   TR >= 0: NumPy path (clamp, transform TR, + 1e-9)   TR == kClampOnly: gt_marginals (clamp only).
-//   The transform is a template parameter: with a run-time switch in the pixel loop the unrolled bodies of the
-//   five transforms (float64 exp and log among them) did not fit the instruction cache and a float32 sqrt map
-//   ran at 0.12 of the HBM rate.  uint8 maps (TR == kByteTable) look their 256 possible values up in a
-//   shared-memory table the CTA fills with the run-time transform first.
+//   The transform is a template parameter: the pixel loops hold one transform instead of a five-way run-time switch
+//   (9000 -> 1000-3700 SASS instructions per kernel; by itself that did not change the run time -- the float64
+//   evaluation of the transform is the cost, see marginals_f32_rows_kernel -- but it lets each transform have its own
+//   arithmetic).  uint8 maps (TR == kByteTable) look their 256 possible values up in a shared-memory table the CTA
+//   fills with the run-time transform first.
 // -------------------------------------------------------------------------------------------
 constexpr int kClampOnly = -1;
 constexpr int kByteTable = 8;
