@@ -290,13 +290,14 @@ resize_lanczos_up_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, 
 //   tmpT [column][16] bytes: the horizontal pass of the tile's source rows, transposed, so that a B fragment
 //        (4 consecutive source rows of one column) is one aligned 32-bit shared load; a warp keeps its 8 B fragments
 //        (64 columns) in registers for the whole tile;
-//   Apl  [3][row][16] bytes: the byte planes of the coefficient band, an A fragment is two 32-bit loads per plane;
+//   Apl  [3][row][16] bytes: the byte planes of the coefficient band (copied from the table get_planes built once per
+//        (h, Ho, rows per tile)), an A fragment is two 32-bit loads per plane;
 //   the 8 column tiles of a strip interleave their columns (tile j holds columns 16 c + 2 j, + 1 of the strip) so
 //   that a thread ends up with 16 ADJACENT output bytes of rows g and g + 8: two 128-bit stores per 16 x 64 block.
 // Measured (profiles/r06h_row_kernels.txt, r06i ncu): 176 warp instructions per 16 x 64 block (24 IMMA, 62 shift-adds
 // of the Horner combination, 32 shifts, 16 saturating packs) instead of ~10 per byte; revise + resize 64 x 24^2 ->
-// 1344^2 127 -> 57 us, 256 x 24^2 -> 336^2 37 -> 28.5 us; with MARG the fused mask -> maps path 188 -> 78 us.  Issue
-// slots are 58 % busy (a third of the instructions are the per-CTA prologue), DRAM at 13 %: still not its output stream.
+// 1344^2 127 -> 52 us, 256 x 24^2 -> 336^2 37 -> 27 us; with MARG the fused mask -> maps path 188 -> 73 us
+// (profiles/r08e_row_kernels.txt).  Issue slots 58 % busy, tensor pipe 44 %, DRAM 13 %: still not its output stream.
 constexpr int kMmaK = 16, kMmaStrip = 64, kMmaMaxWarps = 8;
 __device__ __forceinline__ void mma_u8u8(int (&d)[4], const uint32_t (&a)[2], uint32_t b) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32)
 resize_lanczos_up_mma_kernel(const uint8_t* __restrict__ src, int h, int w, int Ho, int Wo,
                              const int2* __restrict__ bx, const int* __restrict__ kx, int ksx,
                              const int2* __restrict__ by, const int* __restrict__ ky, int ksy,
-                             int rows_per_tile, uint8_t* __restrict__ dst, double* __restrict__ colpart,
-                             double* __restrict__ rowpart) {
+                             const uint8_t* __restrict__ planes, int rows_per_tile, uint8_t* __restrict__ dst,
+                             double* __restrict__ colpart, double* __restrict__ rowpart) {
     extern __shared__ __align__(16) uint8_t sm_b[];
     const int n_warps = blockDim.x >> 5, cols_cta = n_warps * kMmaStrip;
     const int b = blockIdx.z;
@@ -331,21 +332,13 @@ resize_lanczos_up_mma_kernel(const uint8_t* __restrict__ src, int h, int w, int 
     uint8_t* in = reinterpret_cast<uint8_t*>(rsum + rows_per_tile);    // [nr][w]
     const uint8_t* img = src + ((int64_t)b * h + r0) * w;
     for (int i = threadIdx.x; i < nr * w; i += blockDim.x) in[i] = img[i];
-    for (int i = threadIdx.x; i < 3 * rows_per_tile * kMmaK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(apl)[i] = 0u;
+    {   // the coefficient band of this tile, byte planes (get_planes built them once)
+        const uint4* pl = reinterpret_cast<const uint4*>(planes) + (size_t)blockIdx.y * 3 * rows_per_tile;
+        for (int i = threadIdx.x; i < 3 * rows_per_tile; i += blockDim.x) reinterpret_cast<uint4*>(apl)[i] = __ldg(pl + i);
+    }
     if (MARG)
         for (int i = threadIdx.x; i < rows_per_tile; i += blockDim.x) rsum[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < (y1 - y0) * ksy; i += blockDim.x) {      // the coefficient band, byte planes
-        const int yy = i / ksy, t = i - yy * ksy;
-        const int2 bd = by[y0 + yy];
-        if (t < bd.y) {
-            const int wv = __ldg(ky + (int64_t)(y0 + yy) * ksy + t);
-            const int k = bd.x - r0 + t;
-            apl[(0 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)(wv & 0xff);
-            apl[(1 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)((wv >> 8) & 0xff);
-            apl[(2 * rows_per_tile + yy) * kMmaK + k] = (uint8_t)((wv >> 16) & 0xff);
-        }
-    }
     for (int xl = threadIdx.x; xl < cols_cta; xl += blockDim.x) {          // horizontal pass, column x, transposed
         const int x = x_base + xl;
         uint32_t packed[4] = {0u, 0u, 0u, 0u};
@@ -491,13 +484,14 @@ struct CoeffTable {
     int ksize = 0;
 };
 
-int build_table(int in_size, int out_size, CoeffTable* t) {
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc on the host: bounds [out] = {first tap, taps}, kk [out][ksize]
+static int compute_table(int in_size, int out_size, std::vector<int2>& bounds, std::vector<int>& kk) {
     const double scale = (double)in_size / (double)out_size;
     const double fscale = scale < 1.0 ? 1.0 : scale;
     const double support = 3.0 * fscale;
     const int ksize = (int)ceil(support) * 2 + 1;
-    std::vector<int2> bounds((size_t)out_size);
-    std::vector<int> kk((size_t)out_size * ksize, 0);
+    bounds.assign((size_t)out_size, make_int2(0, 0));
+    kk.assign((size_t)out_size * ksize, 0);
     std::vector<double> w((size_t)ksize);
     const double ss = 1.0 / fscale;
     for (int xx = 0; xx < out_size; ++xx) {
@@ -518,6 +512,13 @@ int build_table(int in_size, int out_size, CoeffTable* t) {
         }
         bounds[(size_t)xx] = make_int2(xmin, xmax);
     }
+    return ksize;
+}
+
+int build_table(int in_size, int out_size, CoeffTable* t) {
+    std::vector<int2> bounds;
+    std::vector<int> kk;
+    const int ksize = compute_table(in_size, out_size, bounds, kk);
     AW_CUDA(cudaMalloc(&t->bounds, sizeof(int2) * (size_t)out_size));
     AW_CUDA(cudaMalloc(&t->weights, sizeof(int) * kk.size()));
     AW_CUDA(cudaMemcpy(t->bounds, bounds.data(), sizeof(int2) * (size_t)out_size, cudaMemcpyHostToDevice));
@@ -541,6 +542,46 @@ int get_table(int in_size, int out_size, CoeffTable* out) {
         const int rc = build_table(in_size, out_size, &t);
         if (rc != ATTWARP_OK) return rc;
         it = cache.emplace(key, t).first;
+    }
+    *out = it->second;
+    return ATTWARP_OK;
+}
+
+// The byte planes of the vertical coefficient band for the tensor-core kernel, per tile of `rows` output rows:
+// [tile][plane][row][16] bytes, k relative to the tile's first tapped source row.  Constants of (device, h, Ho, rows),
+// built once like the tables (the CTAs used to rebuild their slice from the int32 table: a sixth of the kernel's
+// instructions).
+int get_planes(int h, int Ho, int rows, const uint8_t** out) {
+    static std::mutex mu;
+    static std::map<std::pair<std::pair<int, int>, std::pair<int, int>>, uint8_t*> cache;
+    int dev = 0;
+    AW_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(std::make_pair(dev, h), std::make_pair(Ho, rows));
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<int2> bounds;
+        std::vector<int> kk;
+        const int ksize = compute_table(h, Ho, bounds, kk);
+        const int n_tiles = (Ho + rows - 1) / rows;
+        std::vector<uint8_t> planes((size_t)n_tiles * 3 * rows * kMmaK, 0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int y0 = t * rows, r0 = bounds[(size_t)y0].x;
+            for (int yy = 0; yy < rows && y0 + yy < Ho; ++yy) {
+                const int2 bd = bounds[(size_t)(y0 + yy)];
+                for (int tap = 0; tap < bd.y; ++tap) {
+                    const int k = bd.x - r0 + tap;
+                    if (k < 0 || k >= kMmaK) return fail(ATTWARP_ERR_UNSUPPORTED, "lanczos planes: a tile of %d rows taps more than %d source rows", rows, kMmaK);
+                    const int wv = kk[(size_t)(y0 + yy) * ksize + tap];
+                    for (int p = 0; p < 3; ++p)
+                        planes[(((size_t)t * 3 + p) * rows + yy) * kMmaK + k] = (uint8_t)((wv >> (8 * p)) & 0xff);
+                }
+            }
+        }
+        uint8_t* d = nullptr;
+        AW_CUDA(cudaMalloc(&d, planes.size()));
+        AW_CUDA(cudaMemcpy(d, planes.data(), planes.size(), cudaMemcpyHostToDevice));
+        it = cache.emplace(key, d).first;
     }
     *out = it->second;
     return ATTWARP_OK;
@@ -670,8 +711,11 @@ int launch_lanczos_marginals(const uint8_t* src, int B, int h, int w, int H, int
         if (mg.ok && tx.ksize <= kUpTaps && ty.ksize <= kUpTaps) {
             if (mg.smem > 48 * 1024)
                 AW_CUDA(cudaFuncSetAttribute(resize_lanczos_up_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.smem));
+            const uint8_t* planes = nullptr;
+            const int prc = get_planes(h, H, mg.rows, &planes);
+            if (prc != ATTWARP_OK) return prc;
             resize_lanczos_up_mma_kernel<true><<<dim3(mg.x_ctas, mg.n_tiles, B), mg.warps * 32, mg.smem, st>>>(
-                src, h, w, H, W, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, mg.rows, nullptr, colpart, rowpart);
+                src, h, w, H, W, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, planes, mg.rows, nullptr, colpart, rowpart);
             *n_chunks = mg.n_tiles;
             *n_col_tiles = mg.x_ctas;
             return check_launch("resize_lanczos_up_mma_kernel<marginals>");
@@ -712,8 +756,11 @@ int launch_resize_lanczos_u8(const uint8_t* src, int B, int h, int w, int Ho, in
         if (mg.ok) {
             if (mg.smem > 48 * 1024)
                 AW_CUDA(cudaFuncSetAttribute(resize_lanczos_up_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.smem));
+            const uint8_t* planes = nullptr;
+            const int prc = get_planes(h, Ho, mg.rows, &planes);
+            if (prc != ATTWARP_OK) return prc;
             resize_lanczos_up_mma_kernel<false><<<dim3(mg.x_ctas, mg.n_tiles, B), mg.warps * 32, mg.smem, st>>>(
-                src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, mg.rows, dst, nullptr, nullptr);
+                src, h, w, Ho, Wo, tx.bounds, tx.weights, tx.ksize, ty.bounds, ty.weights, ty.ksize, planes, mg.rows, dst, nullptr, nullptr);
             return check_launch("resize_lanczos_up_mma_kernel");
         }
     }

@@ -163,7 +163,7 @@ def maps_from_mota_tokens(tok: torch.Tensor, image_hw, out_size=None, kernel_siz
     """tok [B,gh,gw] -> (map_x, map_y) of the driver flow ``blend_mask`` -> ``save_warped_image(..., "identity")``
     (llava.py:240-256 then new_method.py:207-261) for callers that only warp.  ``fused=True``: the image-size uint8
     mask is never written, its marginals are summed where the LANCZOS resize computes it, on the tensor cores (saves the
-    B x H x W buffer and time: 38.6 us vs 44.4 us for the two steps at 256 x 336^2, 78 us vs 101 us at 64 x 1344^2).
+    B x H x W buffer and time: 37 us vs 43 us for the two steps at 256 x 336^2, 73 us vs 93 us at 64 x 1344^2).
     Same maps as ``maps_from_attention(mota_mask(tok, image_hw), out_size)``, which ``fused=False`` runs."""
     lib = load()
     _, u8 = revise_mask(tok, kernel_size, enhance_coe, return_u8=True)
