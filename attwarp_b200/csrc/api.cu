@@ -2,6 +2,7 @@
 // batch drivers and the host-buffer convenience entry point.  No kernels live here.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -93,6 +94,8 @@ struct HostArena {
     cudaStream_t stream = nullptr;
     void* dev = nullptr;
     size_t cap = 0;
+    void* pin = nullptr;            // pinned staging for the caller's pageable buffers (see warp_image_host_impl)
+    size_t pin_cap = 0;
     int device = -1;
     // Device memory and the stream belong to `device`: they are released when the calling thread moves to
     // another device and when the thread exits (errors ignored: at process exit the runtime may be gone).
@@ -103,13 +106,33 @@ struct HostArena {
                                   cudaSetDevice(device) == cudaSuccess;
             if (stream != nullptr) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
             if (dev != nullptr) cudaFree(dev);
+            if (pin != nullptr) cudaFreeHost(pin);
             if (switched) cudaSetDevice(cur);
             (void)cudaGetLastError();
         }
         stream = nullptr;
         dev = nullptr;
         cap = 0;
+        pin = nullptr;
+        pin_cap = 0;
         device = -1;
+    }
+    // Pinned staging of at least `bytes` (after ensure(): the stream exists); false when the host cannot pin that
+    // much -- the caller then copies from / to the pageable buffers directly.
+    bool ensure_pinned(size_t bytes) {
+        if (bytes <= pin_cap) return true;
+        if (stream != nullptr) cudaStreamSynchronize(stream);
+        if (pin != nullptr) cudaFreeHost(pin);
+        pin = nullptr;
+        pin_cap = 0;
+        const size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        if (cudaHostAlloc(&pin, want, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            pin = nullptr;
+            return false;
+        }
+        pin_cap = want;
+        return true;
     }
     ~HostArena() { release(); }
     int ensure(size_t bytes) {
@@ -460,13 +483,47 @@ static int warp_image_host_impl(const void* image_host, int img_dtype, int C, in
     float* d_my = reinterpret_cast<float*>(p); p += my_b;
     int* d_flag = reinterpret_cast<int*>(p);
     cudaStream_t st = g_arena.stream;
-    AW_CUDA(cudaMemcpyAsync(d_att, att_host, (size_t)H * W * dtype_size(att_dtype), cudaMemcpyHostToDevice, st));
-    AW_CUDA(cudaMemcpyAsync(d_img, image_host, (size_t)H * W * C * es, cudaMemcpyHostToDevice, st));
+    const size_t n_att = (size_t)H * W * dtype_size(att_dtype), n_img = (size_t)H * W * C * es;
+    const size_t n_out = (size_t)Ho * Wo * C * es;
+    // The caller's buffers are pageable: the copies are most of the call (100 of 112 us at 336^2; the kernels take
+    // 14 us).  Measured per direction (profiles/r08i_pinned_modes.txt): receiving the output in pinned memory of this
+    // thread's arena and copying it to the caller with memcpy saves 9-14 us per call (112.8 -> 98.6 us at 336^2,
+    // 141 -> 132 us for a 500^2 output); staging the INPUTS the same way gains nothing (the driver's pageable
+    // host-to-device path already returns as soon as it has taken its copy), so they are passed as they are.
+    // ATTWARP_HOST_PINNED: 0 off, 1 both directions, 2 inputs only, 3 output only (default).
+    static const int pinned_mode = [] {
+        const char* e = getenv("ATTWARP_HOST_PINNED");
+        return e == nullptr ? 3 : atoi(e);
+    }();
+    const bool use_pinned = pinned_mode != 0, pin_in = pinned_mode != 3, pin_out = pinned_mode != 2;
+    if (use_pinned && att_b + img_b + out_b + 256 <= ((size_t)1 << 30) && g_arena.ensure_pinned(att_b + img_b + out_b + 256)) {
+        char* q = static_cast<char*>(g_arena.pin);
+        void* p_att = q; q += att_b;
+        void* p_img = q; q += img_b;
+        void* p_out = q; q += out_b;
+        int* p_flag = reinterpret_cast<int*>(q);
+        if (pin_in) memcpy(p_att, att_host, n_att);
+        AW_CUDA(cudaMemcpyAsync(d_att, pin_in ? p_att : att_host, n_att, cudaMemcpyHostToDevice, st));
+        rc = launch_maps_from_attention(d_att, att_dtype, 1, H, W, Wo, Ho, *tp, d_ws, ws_b, d_mx, d_my, d_flag, st);
+        if (rc != ATTWARP_OK) return rc;
+        if (pin_in) memcpy(p_img, image_host, n_img);   // while the map is on its way and the maps kernels run
+        AW_CUDA(cudaMemcpyAsync(d_img, pin_in ? p_img : image_host, n_img, cudaMemcpyHostToDevice, st));
+        rc = launch_remap(d_img, d_out, img_dtype, ATTWARP_LAYOUT_HWC, 1, C, H, W, Ho, Wo, d_mx, d_my, st);
+        if (rc != ATTWARP_OK) return rc;
+        AW_CUDA(cudaMemcpyAsync(pin_out ? p_out : out_host, d_out, n_out, cudaMemcpyDeviceToHost, st));
+        AW_CUDA(cudaMemcpyAsync(p_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        AW_CUDA(cudaStreamSynchronize(st));
+        if (pin_out) memcpy(out_host, p_out, n_out);
+        if (used_fallback) *used_fallback = *p_flag;
+        return ATTWARP_OK;
+    }
+    AW_CUDA(cudaMemcpyAsync(d_att, att_host, n_att, cudaMemcpyHostToDevice, st));
+    AW_CUDA(cudaMemcpyAsync(d_img, image_host, n_img, cudaMemcpyHostToDevice, st));
     rc = launch_maps_from_attention(d_att, att_dtype, 1, H, W, Wo, Ho, *tp, d_ws, ws_b, d_mx, d_my, d_flag, st);
     if (rc != ATTWARP_OK) return rc;
     rc = launch_remap(d_img, d_out, img_dtype, ATTWARP_LAYOUT_HWC, 1, C, H, W, Ho, Wo, d_mx, d_my, st);
     if (rc != ATTWARP_OK) return rc;
-    AW_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)Ho * Wo * C * es, cudaMemcpyDeviceToHost, st));
+    AW_CUDA(cudaMemcpyAsync(out_host, d_out, n_out, cudaMemcpyDeviceToHost, st));
     int flag = 0;
     AW_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     AW_CUDA(cudaStreamSynchronize(st));
