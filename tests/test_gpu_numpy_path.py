@@ -216,3 +216,31 @@ def test_f32_marginals_extreme_values(transform):
                                                return_maps=True)
         assert np.abs(mx[b].cpu().numpy() - rx).max() <= 1e-4
         assert np.abs(my[b].cpu().numpy() - ry).max() <= 1e-4
+
+
+def test_host_entry_point_from_several_threads():
+    """new_method.warp_image_by_attention keeps per-thread device and pinned scratch (api.cu: HostArena) that regrows
+    when the sizes change: six threads, sizes changing from call to call, every result within 1 LSB of the oracle."""
+    need_gpu()
+    import threading
+    from attwarp_b200 import new_method
+    rng = np.random.default_rng(1)
+    cases = [(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8), Wo, Ho)
+             for (H, W, Wo, Ho) in ((336, 336, 336, 336), (200, 333, 500, 400), (64, 48, 90, 70), (500, 500, 336, 336))]
+    refs = [ON.warp_image_by_attention(i, a, wo, ho, "identity") for i, a, wo, ho in cases]
+    bad = []
+
+    def work(tid):
+        for k in range(24):
+            j = (tid + k) % len(cases)
+            i, a, wo, ho = cases[j]
+            out = new_method.warp_image_by_attention(i, a, wo, ho, transform="identity")
+            if out.shape != refs[j].shape or np.abs(out.astype(int) - refs[j].astype(int)).max() > 1:
+                bad.append((tid, k, j))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not bad, bad[:5]
